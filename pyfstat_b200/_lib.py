@@ -1,0 +1,311 @@
+"""ctypes binding of ``libtcw_b200.so`` (C ABI declared in ``include/tcw_b200.h``).
+
+Thin by design: argument marshalling only.  There is no CPU fallback anywhere in this
+package -- if the library cannot be loaded or no CUDA device is usable, the calls raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .atoms import ATOM_DTYPE, AtomBatch
+from .window import TransientWindowRange
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libtcw_b200.so")
+
+TCW_ABI_VERSION = 1
+
+# flags (include/tcw_b200.h)
+WANT_FMN = 0x1
+WANT_BTSG = 0x2
+EXP_EXACT = 0x4
+ALLOW_DEGENERATE = 0x8
+FORCE_GENERIC = 0x10
+
+# error codes
+E_INVALID, E_WINDOW, E_CUDA, E_NOMEM, E_DEGENERATE, E_STATE = -1, -2, -3, -4, -5, -6
+
+EXPORTED_SYMBOLS = (
+    "tcw_abi_version", "tcw_create", "tcw_destroy", "tcw_last_error", "tcw_device_name",
+    "tcw_map_dims", "tcw_map_batch", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
+    "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
+    "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_host_alloc",
+    "tcw_host_free", "tcw_cell_index_range",
+)
+
+
+class CWindowRange(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("type", "t0", "t0Band", "dt0", "tau", "tauBand", "dtau")]
+
+
+class CResult(C.Structure):
+    _fields_ = [
+        ("lnBtSG", C.c_double),
+        ("t0_MP", C.c_double),
+        ("tau_MP", C.c_double),
+        ("maxF", C.c_float),
+        ("m_ML", C.c_uint32),
+        ("n_ML", C.c_uint32),
+        ("t0_ML", C.c_uint32),
+        ("tau_ML", C.c_uint32),
+        ("m_MP", C.c_uint32),
+        ("n_MP", C.c_uint32),
+        ("N_t0", C.c_uint32),
+        ("N_tau", C.c_uint32),
+        ("numAtoms", C.c_uint32),
+        ("t0_data", C.c_uint32),
+        ("status", C.c_int32),
+        ("path", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+RESULT_DTYPE = np.dtype(
+    [
+        ("lnBtSG", "<f8"), ("t0_MP", "<f8"), ("tau_MP", "<f8"), ("maxF", "<f4"),
+        ("m_ML", "<u4"), ("n_ML", "<u4"), ("t0_ML", "<u4"), ("tau_ML", "<u4"),
+        ("m_MP", "<u4"), ("n_MP", "<u4"), ("N_t0", "<u4"), ("N_tau", "<u4"),
+        ("numAtoms", "<u4"), ("t0_data", "<u4"), ("status", "<i4"), ("path", "<u4"),
+        ("reserved", "<u4"),
+    ],
+    align=True,
+)
+assert RESULT_DTYPE.itemsize == C.sizeof(CResult), (RESULT_DTYPE.itemsize, C.sizeof(CResult))
+
+
+class TcwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[tcw_b200 error {code}] {msg}")
+        self.code = code
+
+
+class DegenerateWindowError(TcwError, ValueError):
+    """A (t0,tau) cell has a single-atom window; lalpulsar aborts the map there (XLAL_EDOM)."""
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True):
+    """Load the CUDA library, building it in-tree when missing and nvcc is available.
+    Raises if that fails -- by design nothing else can compute a map."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+
+        if _build.needs_build() and _build.find_nvcc() is not None:
+            _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing and could not be built (nvcc not found). "
+            "pyfstat_b200 has no CPU fallback: build it with `python -m pyfstat_b200.build`."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.tcw_abi_version.restype = C.c_int
+    if L.tcw_abi_version() != TCW_ABI_VERSION:
+        raise ImportError("libtcw_b200.so ABI version mismatch; rebuild with pyfstat_b200.build")
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    L.tcw_create.argtypes = [i32, C.POINTER(vp)]
+    L.tcw_destroy.argtypes = [vp]
+    L.tcw_last_error.argtypes = [vp]
+    L.tcw_last_error.restype = C.c_char_p
+    L.tcw_device_name.argtypes = [vp, C.c_char_p, i32]
+    L.tcw_map_dims.argtypes = [C.POINTER(CWindowRange), C.POINTER(u32), C.POINTER(u32)]
+    L.tcw_map_batch.argtypes = [vp, vp, vp, u32, u32, i32, i32, C.POINTER(CWindowRange), u32, vp, vp]
+    L.tcw_upload_atoms.argtypes = [vp, vp, vp, u32, u32, i32, i32]
+    L.tcw_map_resident.argtypes = [vp, C.POINTER(CWindowRange), u32]
+    L.tcw_fetch_results.argtypes = [vp, vp]
+    L.tcw_fetch_fmn.argtypes = [vp, i32, vp]
+    L.tcw_fetch_merged.argtypes = [vp, i32, vp, u32]
+    L.tcw_synchronize.argtypes = [vp]
+    L.tcw_timer_start.argtypes = [vp]
+    L.tcw_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tcw_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tcw_launch_count.argtypes = [vp]
+    L.tcw_launch_count.restype = C.c_uint64
+    L.tcw_flush_l2.argtypes = [vp]
+    L.tcw_microbench.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tcw_host_alloc.argtypes = [C.c_uint64]
+    L.tcw_host_alloc.restype = vp
+    L.tcw_host_free.argtypes = [vp]
+    L.tcw_host_free.restype = None
+    L.tcw_cell_index_range.argtypes = [u32, u32, u32, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    _lib = L
+    return L
+
+
+def c_window(w) -> CWindowRange:
+    w = TransientWindowRange.from_any(w)
+    return CWindowRange(w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau)
+
+
+def cell_index_range(window_type, t0_m, tau_n, t0_data, TAtom, numAtoms):
+    """Host-only: (i_t0, i_t1) exactly as the kernels compute them."""
+    L = load_library()
+    a, b = C.c_uint32(), C.c_uint32()
+    rc = L.tcw_cell_index_range(
+        window_type, t0_m & 0xFFFFFFFF, tau_n & 0xFFFFFFFF, t0_data, TAtom, numAtoms, C.byref(a), C.byref(b)
+    )
+    if rc:
+        raise TcwError(rc, "tcw_cell_index_range failed")
+    return a.value, b.value
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'ed buffer exposing the Python buffer protocol through a ctypes array."""
+
+    def __init__(self, nbytes: int):
+        L = load_library()
+        self._ptr = L.tcw_host_alloc(nbytes)
+        if not self._ptr:
+            raise MemoryError(f"cudaHostAlloc({nbytes}) failed")
+        self.nbytes = nbytes
+        self.array = (C.c_ubyte * nbytes).from_address(self._ptr)
+
+    def __del__(self):
+        ptr, self._ptr = getattr(self, "_ptr", None), None
+        if ptr and _lib is not None:
+            _lib.tcw_host_free(ptr)
+
+
+class Handle:
+    """RAII wrapper of ``tcw_handle`` (one per device and process is enough: calls are
+    serialised on the handle's own stream)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.tcw_create(device, C.byref(h))
+        if rc:
+            raise TcwError(rc, (self.L.tcw_last_error(None) or b"").decode())
+        self._h = h
+        self._keep = None  # keeps the uploaded host arrays alive
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.L.tcw_destroy(h)
+
+    detach = close  # so the handle can stand in for a pycuda context (core.py:499-516)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, allow_degenerate_status: bool = False):
+        if rc == 0:
+            return
+        msg = (self.L.tcw_last_error(self._h) or b"").decode()
+        if rc == E_DEGENERATE:
+            if allow_degenerate_status:
+                return
+            raise DegenerateWindowError(rc, msg)
+        if rc == E_WINDOW:
+            raise ValueError(msg)
+        if rc == E_NOMEM:
+            raise MemoryError(msg)
+        raise TcwError(rc, msg)
+
+    @property
+    def device_name(self) -> str:
+        buf = C.create_string_buffer(256)
+        self._check(self.L.tcw_device_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    # ---- one-shot host API -----------------------------------------------------------
+    def map_batch(self, batch: AtomBatch, window, flags: int = 0, *, raise_on_degenerate: bool = True):
+        """``tcw_map_batch``: returns ``(results: np.ndarray[RESULT_DTYPE], F_mn or None)``."""
+        w = TransientWindowRange.from_any(window)
+        w.check_type()
+        cw = c_window(w)
+        N_t0, N_tau = w.dims()
+        results = np.zeros(batch.T, dtype=RESULT_DTYPE)
+        F = None
+        if flags & WANT_FMN:
+            F = np.empty((batch.T, N_t0, N_tau), dtype=np.float32)
+        rc = self.L.tcw_map_batch(
+            self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
+            batch.T, batch.numDet, C.byref(cw), flags, F.ctypes.data if F is not None else None,
+            results.ctypes.data,
+        )
+        self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        return results, F
+
+    # ---- resident API ----------------------------------------------------------------
+    def upload(self, batch: AtomBatch):
+        self._keep = batch
+        self._check(
+            self.L.tcw_upload_atoms(
+                self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
+                batch.T, batch.numDet,
+            )
+        )
+        self._T = batch.T
+
+    def map_resident(self, window, flags: int = 0):
+        cw = c_window(window)
+        self._check(self.L.tcw_map_resident(self._h, C.byref(cw), flags))
+
+    def fetch_results(self, raise_on_degenerate: bool = True) -> np.ndarray:
+        results = np.zeros(self._T, dtype=RESULT_DTYPE)
+        self._check(self.L.tcw_fetch_results(self._h, results.ctypes.data), not raise_on_degenerate)
+        return results
+
+    def fetch_fmn(self, t: int, N_t0: int, N_tau: int) -> np.ndarray:
+        F = np.empty((N_t0, N_tau), dtype=np.float32)
+        self._check(self.L.tcw_fetch_fmn(self._h, t, F.ctypes.data))
+        return F
+
+    def fetch_merged(self, t: int, numAtoms: int) -> np.ndarray:
+        out = np.empty((7, numAtoms), dtype=np.float32)
+        self._check(self.L.tcw_fetch_merged(self._h, t, out.ctypes.data, numAtoms))
+        return out
+
+    def synchronize(self):
+        self._check(self.L.tcw_synchronize(self._h))
+
+    def timer_start(self):
+        self._check(self.L.tcw_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self.L.tcw_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 5)()
+        self._check(self.L.tcw_last_stage_ms(self._h, ms))
+        return dict(zip(("prep", "table", "map", "btsg", "finalize"), (float(x) for x in ms)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.tcw_launch_count(self._h))
+
+    def flush_l2(self):
+        self._check(self.L.tcw_flush_l2(self._h))
+
+    def microbench(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.L.tcw_microbench(self._h, C.byref(a), C.byref(b)))
+        return {"ffma_tflops": a.value, "dadd_tflops": b.value}
+
+
+def pinned_atoms_alloc():
+    """Allocator for :func:`pyfstat_b200.atoms.synth_atoms` placing the batch in pinned memory."""
+    keep = []
+
+    def alloc(nbytes):
+        buf = PinnedBuffer(nbytes)
+        keep.append(buf)
+        return buf.array
+
+    alloc.keep = keep
+    return alloc

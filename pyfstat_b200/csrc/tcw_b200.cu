@@ -1,0 +1,792 @@
+// tcw_b200.cu -- C ABI (include/tcw_b200.h) of the B200-native transient F-stat map backend.
+//
+// Host orchestration only: buffer management in HBM, the host-side certificate that decides
+// between the tiled and the generic kernels, launches on the handle's stream, event timing.
+// No CPU compute path exists here: every map is computed by the sm_100a kernels in
+// tcw_prep.cuh / tcw_rect.cuh / tcw_exp.cuh / tcw_generic.cuh / tcw_btsg.cuh.
+//
+// Data layout in HBM (per handle, grown on demand, reused across calls):
+//   d_atoms  [T][numDet][stride] tcw_atom (32 B AoS, as uploaded)
+//   d_X      [T][7][xpad] float32   merged channels (zero padded)
+//   d_P      [T][7][ppad] float64   exclusive prefix sums (rect window)
+//   d_W      [n_tiles][KW][64] float32  exponential-window weight table (cached per window)
+//   d_Fmn    [T][N_t0][N_tau] float32   only with TCW_WANT_FMN; else a sub-batch scratch
+//                                       sized to stay L2-resident when lnBtSG needs a 2nd pass
+//   d_maxkey [T] u64, d_rowsum [T][N_t0] f64, d_colsum [T][N_tau] f64, d_results [T]
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "tcw_b200.h"
+#include "tcw_btsg.cuh"
+#include "tcw_common.cuh"
+#include "tcw_exp.cuh"
+#include "tcw_generic.cuh"
+#include "tcw_prep.cuh"
+#include "tcw_rect.cuh"
+
+static std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct tcw_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_timer[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // start, prep, table, loops end... finalize
+    cudaEvent_t ev_fin = nullptr;
+    std::vector<cudaEvent_t> ev_sub;  // 3 per sub-batch: map begin, map end, btsg end
+    int n_sub_last = 0;
+    bool stage_valid = false;
+    std::string err;
+    cudaDeviceProp prop;
+    uint64_t launches = 0;
+
+    // resident batch
+    bool uploaded = false;
+    int T = 0, numDet = 0;
+    uint32_t stride = 0, TAtom = 0;
+    uint32_t Nmax = 0, xpad = 0, ppad = 0;
+    bool uniform = true;  // all templates share (t0_data, numAtoms)
+    std::vector<TplMeta> meta;
+    DevBuf d_atoms, d_natoms, d_meta, d_X, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
+        d_flags, d_results, d_W, d_Kn, d_lut, d_flush;
+
+    // last map
+    bool have_fmn = false;
+    uint32_t last_N_t0 = 0, last_N_tau = 0;
+
+    // exp weight-table cache key
+    bool w_valid = false;
+    tcw_window_range w_key = {};
+    uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_i00 = 0;
+    int w_exact = -1;
+    std::vector<int32_t> w_Kn;
+};
+
+static int fail(tcw_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            return fail(h, _e == cudaErrorMemoryAllocation ? TCW_E_NOMEM : TCW_E_CUDA,           \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+        }                                                                                        \
+    } while (0)
+
+static int ensure(tcw_handle *h, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return TCW_OK;
+    if (b.p) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8;  // a little slack against repeated growth
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(h, TCW_E_NOMEM,
+                    "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return TCW_OK;
+}
+
+static void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" int tcw_abi_version(void) { return TCW_ABI_VERSION; }
+
+extern "C" const char *tcw_last_error(const tcw_handle *h) {
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int tcw_map_dims(const tcw_window_range *win, uint32_t *N_t0, uint32_t *N_tau) {
+    if (!win || !N_t0 || !N_tau) return TCW_E_INVALID;
+    if (win->type >= TCW_WINDOW_LAST) return TCW_E_WINDOW;
+    if (win->type == TCW_WINDOW_NONE) {
+        *N_t0 = *N_tau = 1;
+        return TCW_OK;
+    }
+    if (win->dt0 == 0 || win->dtau == 0) return TCW_E_INVALID;
+    *N_t0 = win->t0Band / win->dt0 + 1;    // floor(t0Band/dt0)+1 (tcw:775-777)
+    *N_tau = win->tauBand / win->dtau + 1;  // tcw:778-780
+    return TCW_OK;
+}
+
+extern "C" int tcw_cell_index_range(uint32_t window_type, uint32_t t0_m, uint32_t tau_n,
+                                    uint32_t t0_data, uint32_t TAtom, uint32_t numAtoms,
+                                    uint32_t *i_t0, uint32_t *i_t1) {
+    if (!i_t0 || !i_t1 || TAtom == 0 || numAtoms == 0) return TCW_E_INVALID;
+    if (window_type != TCW_WINDOW_RECT && window_type != TCW_WINDOW_EXP) return TCW_E_WINDOW;
+    IndexGeom g;
+    g.TAtom = TAtom;
+    g.TAtomHalf = TAtom / 2;
+    g.md = make_magic(TAtom);
+    g.ef = window_type == TCW_WINDOW_EXP ? TCW_EXP_EFOLDING : 1;
+    *i_t0 = index_t0(t0_m, t0_data, numAtoms, g);
+    *i_t1 = index_t1(t0_m + g.ef * tau_n, t0_data, numAtoms, g);
+    return TCW_OK;
+}
+
+extern "C" int tcw_create(int device, tcw_handle **out) {
+    if (!out) return fail(nullptr, TCW_E_INVALID, "tcw_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, TCW_E_CUDA,
+                    std::string("no usable CUDA device: ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (this backend has no CPU fallback)");
+    if (device < 0) {  // $CUDA_DEVICE like the reference (tcw:434-437)
+        const char *env = getenv("CUDA_DEVICE");
+        device = env ? atoi(env) : 0;
+    }
+    if (device >= count)
+        return fail(nullptr, TCW_E_CUDA,
+                    "Requested CUDA device number " + std::to_string(device) +
+                        " exceeds number of available devices!");
+    tcw_handle *h = new tcw_handle();
+    h->device = device;
+    CUDA_TRY(nullptr, cudaSetDevice(device));
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&h->prop, device));
+    if (h->prop.major < 10) {
+        std::string m = std::string("device ") + h->prop.name + " is sm_" + std::to_string(h->prop.major) +
+                        std::to_string(h->prop.minor) + "; this library is built for sm_100a only";
+        delete h;
+        return fail(nullptr, TCW_E_CUDA, m);
+    }
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &ev : h->ev_timer) CUDA_TRY(nullptr, cudaEventCreate(&ev));
+    for (auto &ev : h->ev_stage) CUDA_TRY(nullptr, cudaEventCreate(&ev));
+    CUDA_TRY(nullptr, cudaEventCreate(&h->ev_fin));
+    // XLALFastNegExp table, computed on the host exactly like lalpulsar builds it
+    // (recalled: exp(-i*dx), dx = 20/2000), so the device lookups are bit-identical
+    std::vector<double> lut(TCW_LUT_LEN + 1);
+    const double dx = TCW_LUT_XMAX / TCW_LUT_LEN;
+    for (int i = 0; i <= TCW_LUT_LEN; i++) lut[i] = exp(-(i * dx));
+    int rc = ensure(h, h->d_lut, lut.size() * sizeof(double));
+    if (rc) {
+        g_create_error = h->err;
+        delete h;
+        return rc;
+    }
+    CUDA_TRY(nullptr, cudaMemcpy(h->d_lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // opt in to large dynamic shared memory once
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_RECT_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_RECT_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_RECT_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_RECT_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_EXP_SMEM));
+    *out = h;
+    return TCW_OK;
+}
+
+extern "C" int tcw_destroy(tcw_handle *h) {
+    if (!h) return TCW_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_P, &h->d_Fmn, &h->d_scratch,
+                      &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
+                      &h->d_Kn, &h->d_lut, &h->d_flush})
+        release(*b);
+    for (auto ev : h->ev_timer)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : h->ev_stage)
+        if (ev) cudaEventDestroy(ev);
+    if (h->ev_fin) cudaEventDestroy(h->ev_fin);
+    for (auto ev : h->ev_sub) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return TCW_OK;
+}
+
+extern "C" int tcw_device_name(const tcw_handle *h, char *buf, int buflen) {
+    if (!h || !buf || buflen < 1) return TCW_E_INVALID;
+    snprintf(buf, buflen, "%s", h->prop.name);
+    return TCW_OK;
+}
+
+extern "C" uint64_t tcw_launch_count(const tcw_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int tcw_synchronize(tcw_handle *h) {
+    if (!h) return TCW_E_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return TCW_OK;
+}
+
+extern "C" void *tcw_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void tcw_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int tcw_timer_start(tcw_handle *h) {
+    if (!h) return TCW_E_INVALID;
+    CUDA_TRY(h, cudaEventRecord(h->ev_timer[0], h->stream));
+    return TCW_OK;
+}
+extern "C" int tcw_timer_stop(tcw_handle *h, float *ms) {
+    if (!h || !ms) return TCW_E_INVALID;
+    CUDA_TRY(h, cudaEventRecord(h->ev_timer[1], h->stream));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_timer[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(ms, h->ev_timer[0], h->ev_timer[1]));
+    return TCW_OK;
+}
+
+extern "C" int tcw_flush_l2(tcw_handle *h) {
+    if (!h) return TCW_E_INVALID;
+    const size_t bytes = 256u << 20;
+    int rc = ensure(h, h->d_flush, bytes);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flush.p, 0xA5, bytes, h->stream));
+    return TCW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------
+extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                                uint32_t atom_stride, uint32_t TAtom, int T, int numDet) {
+    if (!h) return TCW_E_INVALID;
+    if (!atoms || !n_atoms || T < 1 || numDet < 1 || atom_stride < 1 || TAtom < 1)
+        return fail(h, TCW_E_INVALID, "tcw_upload_atoms: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->uploaded = false;
+    h->have_fmn = false;
+    // merged geometry per template (XLALmergeMultiFstatAtomsBinned sizing):
+    // tMin/tMax over detectors, numAtoms = floor((tMax - tMin)/TAtom) + 1
+    h->meta.resize(T);
+    uint32_t Nmax = 0;
+    bool uniform = true;
+    for (int t = 0; t < T; t++) {
+        uint32_t tMin = 0xFFFFFFFFu, tMax = 0;
+        for (int X = 0; X < numDet; X++) {
+            const uint32_t n = n_atoms[(size_t)t * numDet + X];
+            if (n < 1 || n > atom_stride)
+                return fail(h, TCW_E_INVALID, "tcw_upload_atoms: n_atoms out of range [1, atom_stride]");
+            const tcw_atom *a = atoms + ((size_t)t * numDet + X) * atom_stride;
+            tMin = std::min(tMin, a[0].timestamp);
+            tMax = std::max(tMax, a[n - 1].timestamp);
+        }
+        if (tMax < tMin) return fail(h, TCW_E_INVALID, "tcw_upload_atoms: timestamps not increasing");
+        h->meta[t].t0_data = tMin;
+        h->meta[t].numAtoms = (tMax - tMin) / TAtom + 1;
+        Nmax = std::max(Nmax, h->meta[t].numAtoms);
+        if (h->meta[t].t0_data != h->meta[0].t0_data || h->meta[t].numAtoms != h->meta[0].numAtoms)
+            uniform = false;
+    }
+    if ((uint64_t)Nmax * TAtom >= (1ull << 32))
+        return fail(h, TCW_E_INVALID, "tcw_upload_atoms: data span does not fit UINT4 seconds");
+    h->T = T;
+    h->numDet = numDet;
+    h->stride = atom_stride;
+    h->TAtom = TAtom;
+    h->Nmax = Nmax;
+    h->uniform = uniform;
+    // zero padding: the exp tiles read up to TM + KC + 4 atoms past the last needed one
+    h->xpad = ((Nmax + TCW_EXP_TM + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
+    h->ppad = ((Nmax + 1 + 8) + 1u) & ~1u;
+    const size_t n_vec = (size_t)T * numDet;
+    int rc;
+    if ((rc = ensure(h, h->d_atoms, n_vec * atom_stride * sizeof(tcw_atom)))) return rc;
+    if ((rc = ensure(h, h->d_natoms, n_vec * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(h, h->d_meta, (size_t)T * sizeof(TplMeta)))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_atoms.p, atoms, n_vec * atom_stride * sizeof(tcw_atom),
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_natoms.p, n_atoms, n_vec * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_meta.p, h->meta.data(), (size_t)T * sizeof(TplMeta),
+                                cudaMemcpyHostToDevice, h->stream));
+    // n_atoms / meta are small pageable buffers owned by the caller / by us: make sure the
+    // copies have consumed them before returning
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->uploaded = true;
+    return TCW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side certificate for the tiled kernels
+// ---------------------------------------------------------------------------------------
+// True if, for this template, no uint32 wrap-around and no signed re-interpretation can occur
+// anywhere in the (skew-extended) map, so i_t0 / i_t1 are monotone in m and n.
+static bool no_wrap(const MapWindow &w, uint32_t ef, uint32_t slack_n, const TplMeta &mt, uint32_t TAtom) {
+    const int64_t half = TAtom / 2;
+    const int64_t x0 = (int64_t)w.t0 - (int64_t)mt.t0_data + half;
+    if (x0 < 0) return false;
+    const uint64_t t0_last = (uint64_t)w.t0 + (uint64_t)(w.N_t0 - 1) * w.dt0;
+    const uint64_t tau_last = (uint64_t)w.tau + (uint64_t)(w.N_tau - 1 + slack_n) * w.dtau;
+    const uint64_t t1_max = t0_last + (uint64_t)ef * tau_last;
+    if (t1_max >= (1ull << 32)) return false;
+    const uint64_t q_max = (t1_max - mt.t0_data + (uint64_t)half) / TAtom;
+    return q_max < (1ull << 31);
+}
+
+struct ExpPlan {
+    bool ok = false;
+    uint32_t i00 = 0, KW = 0;
+    int32_t delta = 0;
+    std::vector<int32_t> Kn;
+};
+
+static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
+    ExpPlan p;
+    const uint32_t TAtom = h->TAtom;
+    if (w.dt0 != TAtom) return p;  // rows must advance by exactly one atom (sliding window)
+    const uint32_t t0_data = h->meta[0].t0_data;
+    for (int t = 0; t < h->T; t++) {
+        if (h->meta[t].t0_data != t0_data) return p;  // the weight table depends on t0 - t0_data
+        if (!no_wrap(w, TCW_EXP_EFOLDING, 0, h->meta[t], TAtom)) return p;
+    }
+    const int64_t half = TAtom / 2;
+    const int64_t x0 = (int64_t)w.t0 - t0_data + half;
+    const int64_t i00 = x0 / TAtom;
+    for (int t = 0; t < h->T; t++)  // i_t0 must never hit the numAtoms-1 clamp
+        if (i00 + (int64_t)w.N_t0 - 1 > (int64_t)h->meta[t].numAtoms - 1) return p;
+    p.Kn.resize(w.N_tau);
+    int64_t Kmax = -1;
+    for (uint32_t n = 0; n < w.N_tau; n++) {
+        const int64_t tau_n = (int64_t)w.tau + (int64_t)n * w.dtau;
+        const int64_t K = (x0 + (int64_t)TCW_EXP_EFOLDING * tau_n) / TAtom - 1 - i00;  // unclamped i_t1 - i_t0
+        p.Kn[n] = (int32_t)K;
+        Kmax = std::max(Kmax, K);
+    }
+    if (i00 == 0 && p.Kn[0] < 0) return p;  // the `< 0 -> 0` clamp of i_t1 would engage
+    if (Kmax > (int64_t)h->Nmax + 64) Kmax = (int64_t)h->Nmax + 64;  // never need k beyond the data
+    for (auto &K : p.Kn) K = (int32_t)std::min<int64_t>(K, Kmax);
+    p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
+    const uint64_t n_tiles = (w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN;
+    if (n_tiles * p.KW * TCW_EXP_TN * 4ull > (8ull << 30)) return p;  // table too large
+    p.i00 = (uint32_t)i00;
+    p.delta = (int32_t)((int64_t)t0_data + i00 * TAtom - (int64_t)w.t0);
+    p.ok = true;
+    return p;
+}
+
+static size_t subbatch_bytes() {
+    const char *env = getenv("TCW_SUBBATCH_MB");
+    size_t mb = env ? (size_t)atol(env) : 64;
+    if (mb < 1) mb = 1;
+    return mb << 20;
+}
+
+// ---------------------------------------------------------------------------------------
+// the map
+// ---------------------------------------------------------------------------------------
+extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags) {
+    if (!h) return TCW_E_INVALID;
+    if (!win) return fail(h, TCW_E_INVALID, "tcw_map_resident: window range is NULL");
+    if (!h->uploaded) return fail(h, TCW_E_STATE, "tcw_map_resident: no resident atoms (call tcw_upload_atoms)");
+    if (win->type >= TCW_WINDOW_LAST)
+        return fail(h, TCW_E_WINDOW, "Unknown window-type (" + std::to_string(win->type) +
+                                         ") passed as input. Allowed are [0," +
+                                         std::to_string(TCW_WINDOW_LAST - 1) + "].");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int T = h->T;
+    const uint32_t TAtom = h->TAtom;
+    const bool want_fmn = flags & TCW_WANT_FMN;
+    const bool want_btsg = flags & TCW_WANT_BTSG;
+    const bool exact = flags & TCW_EXP_EXACT;
+    const bool none_window = win->type == TCW_WINDOW_NONE;
+
+    MapWindow w;
+    if (none_window) {  // rect window spanning the data, per template, 1x1 (tcw:742-749)
+        w.type = TCW_WINDOW_RECT;
+        w.t0 = 0;  // taken from the template's meta inside the kernels
+        w.tau = 0;
+        w.dt0 = w.dtau = TAtom;
+        w.t0Band = w.tauBand = 0;
+        w.N_t0 = w.N_tau = 1;
+    } else {
+        if (win->dt0 == 0 || win->dtau == 0)
+            return fail(h, TCW_E_INVALID, "windowRange.dt0 and .dtau must be positive");
+        w.type = win->type;
+        w.t0 = win->t0;
+        w.dt0 = win->dt0;
+        w.tau = win->tau;
+        w.dtau = win->dtau;
+        w.t0Band = win->t0Band;
+        w.tauBand = win->tauBand;
+        w.N_t0 = win->t0Band / win->dt0 + 1;
+        w.N_tau = win->tauBand / win->dtau + 1;
+    }
+    const uint64_t cells64 = (uint64_t)w.N_t0 * w.N_tau;
+    if (cells64 >= (1ull << 32)) return fail(h, TCW_E_INVALID, "map has more than 2^32-1 cells");
+    const size_t cells = (size_t)cells64;
+
+    IndexGeom g;
+    g.TAtom = TAtom;
+    g.TAtomHalf = TAtom / 2;
+    g.md = make_magic(TAtom);
+    g.ef = w.type == TCW_WINDOW_EXP ? TCW_EXP_EFOLDING : 1;
+
+    // ---- choose the kernels ----
+    enum { PATH_GENERIC = 0, PATH_FAST = 1 };
+    int path = PATH_GENERIC;
+    int rect_R = 1;
+    bool rect_staged = false;
+    ExpPlan ep;
+    if (!(flags & TCW_FORCE_GENERIC) && !none_window) {
+        if (w.type == TCW_WINDOW_RECT) {
+            rect_R = (w.dt0 == w.dtau) ? 4 : 1;
+            bool ok = true;
+            for (int t = 0; t < T && ok; t++) ok = no_wrap(w, 1, rect_R - 1, h->meta[t], TAtom);
+            if (ok) {
+                path = PATH_FAST;
+                const uint64_t span = ((uint64_t)(TCW_RECT_WARPS * rect_R - 1) * w.dt0 +
+                                       (uint64_t)(TCW_RECT_DT - 1) * w.dtau) / TAtom + 6;
+                rect_staged = span <= TCW_RECT_ECAP;
+            }
+        } else {
+            ep = plan_exp(h, w);
+            if (ep.ok) path = PATH_FAST;
+        }
+    }
+
+    // ---- buffers ----
+    int rc;
+    if ((rc = ensure(h, h->d_X, (size_t)T * TCW_NCH * h->xpad * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->d_P, (size_t)T * TCW_NCH * h->ppad * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->d_maxkey, (size_t)T * sizeof(unsigned long long)))) return rc;
+    if ((rc = ensure(h, h->d_flags, (size_t)T * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(h, h->d_results, (size_t)T * sizeof(tcw_result)))) return rc;
+    if (want_btsg) {
+        if ((rc = ensure(h, h->d_rowsum, (size_t)T * w.N_t0 * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_colsum, (size_t)T * w.N_tau * sizeof(double)))) return rc;
+    }
+    // templates per sub-batch: with lnBtSG the F_mn of a sub-batch is written by the map kernel
+    // and re-read by the BtSG pass, so keep it L2-sized; otherwise only the grid.z limit applies
+    int S = T;
+    if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (cells * 4)));
+    S = std::min(S, 32768);
+    float *fmn_full = nullptr, *fmn_scratch = nullptr;
+    if (want_fmn) {
+        if ((rc = ensure(h, h->d_Fmn, (size_t)T * cells * sizeof(float)))) return rc;
+        fmn_full = (float *)h->d_Fmn.p;
+    } else if (want_btsg) {
+        if ((rc = ensure(h, h->d_scratch, (size_t)S * cells * sizeof(float)))) return rc;
+        fmn_scratch = (float *)h->d_scratch.p;
+    }
+    const int n_sub = (T + S - 1) / S;
+    while ((int)h->ev_sub.size() < 3 * n_sub) {
+        cudaEvent_t ev;
+        CUDA_TRY(h, cudaEventCreate(&ev));
+        h->ev_sub.push_back(ev);
+    }
+
+    cudaStream_t st = h->stream;
+    h->stage_valid = false;
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_maxkey.p, 0, (size_t)T * sizeof(unsigned long long), st));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (size_t)T * sizeof(uint32_t), st));
+    if (want_btsg) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_rowsum.p, 0, (size_t)T * w.N_t0 * sizeof(double), st));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_colsum.p, 0, (size_t)T * w.N_tau * sizeof(double), st));
+    }
+
+    // ---- stage 0: merge detectors, transpose to channels, FP64 prefix scan ----
+    tcw_prep_kernel<<<T, TCW_PREP_THREADS, 0, st>>>(
+        (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p,
+        h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, h->xpad, (double *)h->d_P.p, h->ppad,
+        (uint32_t *)h->d_flags.p);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
+
+    // ---- stage 1: exponential-window weight table (cached across calls) ----
+    if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
+        const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
+                         h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom &&
+                         h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn;
+        if (!hit) {
+            const uint32_t n_tiles = (w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN;
+            const size_t total = (size_t)n_tiles * ep.KW * TCW_EXP_TN;
+            if ((rc = ensure(h, h->d_W, total * sizeof(float)))) return rc;
+            if ((rc = ensure(h, h->d_Kn, (size_t)w.N_tau * sizeof(int32_t)))) return rc;
+            h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_Kn.p, h->w_Kn.data(), (size_t)w.N_tau * sizeof(int32_t),
+                                        cudaMemcpyHostToDevice, st));
+            ExpTableGeom eg;
+            eg.N_tau = w.N_tau;
+            eg.n_tiles = n_tiles;
+            eg.KW = ep.KW;
+            eg.tau = w.tau;
+            eg.dtau = w.dtau;
+            eg.TAtom = TAtom;
+            eg.delta = ep.delta;
+            const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->prop.multiProcessorCount * 16);
+            tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg,
+                                                         (const double *)h->d_lut.p, (int)exact);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+            CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
+            h->w_valid = true;
+            h->w_key = *win;
+            h->w_t0_data = h->meta[0].t0_data;
+            h->w_TAtom = TAtom;
+            h->w_exact = (int)exact;
+            h->w_KW = ep.KW;
+            h->w_i00 = ep.i00;
+        }
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[2], st));
+
+    // ---- stage 2/3: map kernel (+ lnBtSG pass) per sub-batch ----
+    for (int sb = 0; sb < n_sub; sb++) {
+        const int t_base = sb * S;
+        const int cnt = std::min(S, T - t_base);
+        float *fmn = fmn_full ? fmn_full + (size_t)t_base * cells : fmn_scratch;
+        CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 0], st));
+        if (path == PATH_GENERIC) {
+            dim3 grid((unsigned)((cells + TCW_GENERIC_THREADS - 1) / TCW_GENERIC_THREADS), 1, cnt);
+#define LAUNCH_GENERIC(WT, EX)                                                                         \
+    tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                              \
+        (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, (int)none_window, g, \
+        (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
+            if (w.type == TCW_WINDOW_RECT) LAUNCH_GENERIC(TCW_WINDOW_RECT, false);
+            else if (exact) LAUNCH_GENERIC(TCW_WINDOW_EXP, true);
+            else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);
+#undef LAUNCH_GENERIC
+        } else if (w.type == TCW_WINDOW_RECT) {
+            const uint32_t n_groups = (w.N_t0 + rect_R - 1) / rect_R;
+            dim3 grid((w.N_tau + rect_R - 1 + TCW_RECT_DT - 1) / TCW_RECT_DT,
+                      (n_groups + TCW_RECT_WARPS - 1) / TCW_RECT_WARPS, cnt);
+            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
+            const size_t smem = TCW_RECT_SMEM;
+#define LAUNCH_RECT(RR, STG)                                                                        \
+    tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                             \
+        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, fmn,         \
+        (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
+            if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);
+            else if (rect_R == 4) LAUNCH_RECT(4, false);
+            else if (rect_staged) LAUNCH_RECT(1, true);
+            else LAUNCH_RECT(1, false);
+#undef LAUNCH_RECT
+        } else {
+            dim3 grid((w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN, (w.N_t0 + TCW_EXP_TM - 1) / TCW_EXP_TM, cnt);
+            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
+            tcw_exp_map_kernel<<<grid, TCW_EXP_THREADS, TCW_EXP_SMEM, st>>>(
+                (const float *)h->d_X.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,
+                (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, (unsigned long long *)h->d_maxkey.p,
+                (uint32_t *)h->d_flags.p);
+        }
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 1], st));
+        if (want_btsg) {
+            dim3 grid((w.N_tau + TCW_BTSG_COLS - 1) / TCW_BTSG_COLS, (w.N_t0 + TCW_BTSG_ROWS - 1) / TCW_BTSG_ROWS,
+                      cnt);
+            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the lnBtSG pass");
+            if (exact)
+                tcw_btsg_kernel<true><<<grid, TCW_BTSG_THREADS, 0, st>>>(
+                    fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
+                    (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
+            else
+                tcw_btsg_kernel<false><<<grid, TCW_BTSG_THREADS, 0, st>>>(
+                    fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
+                    (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+        }
+        CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 2], st));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_stage[3], st));
+
+    // ---- stage 4: one result record per template ----
+    tcw_finalize_kernel<<<T, TCW_FIN_THREADS, 0, st>>>(
+        (const unsigned long long *)h->d_maxkey.p, (const uint32_t *)h->d_flags.p, (const double *)h->d_rowsum.p,
+        (const double *)h->d_colsum.p, (const TplMeta *)h->d_meta.p, w, (int)none_window, TAtom, (int)want_btsg,
+        (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)path, (tcw_result *)h->d_results.p);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev_fin, st));
+    h->n_sub_last = n_sub;
+    h->stage_valid = true;
+    h->have_fmn = want_fmn;
+    h->last_N_t0 = w.N_t0;
+    h->last_N_tau = w.N_tau;
+    return TCW_OK;
+}
+
+extern "C" int tcw_last_stage_ms(tcw_handle *h, float ms[5]) {
+    if (!h || !ms) return TCW_E_INVALID;
+    if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_last_stage_ms: no map has been run");
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_fin));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[0], h->ev_stage[0], h->ev_stage[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[1], h->ev_stage[1], h->ev_stage[2]));
+    ms[2] = ms[3] = 0.0f;
+    for (int sb = 0; sb < h->n_sub_last; sb++) {
+        float a = 0, b = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&a, h->ev_sub[3 * sb + 0], h->ev_sub[3 * sb + 1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&b, h->ev_sub[3 * sb + 1], h->ev_sub[3 * sb + 2]));
+        ms[2] += a;
+        ms[3] += b;
+    }
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[4], h->ev_stage[3], h->ev_fin));
+    return TCW_OK;
+}
+
+extern "C" int tcw_fetch_results(tcw_handle *h, tcw_result *results) {
+    if (!h || !results) return TCW_E_INVALID;
+    if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_fetch_results: no map has been run");
+    CUDA_TRY(h, cudaMemcpyAsync(results, h->d_results.p, (size_t)h->T * sizeof(tcw_result),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int worst = TCW_OK;
+    for (int t = 0; t < h->T; t++) {
+        if (results[t].status == TCW_E_INVALID) {
+            worst = TCW_E_INVALID;
+            h->err = "atoms of template " + std::to_string(t) + " are not sorted by timestamp";
+        } else if (results[t].status == TCW_E_DEGENERATE && worst == TCW_OK) {
+            worst = TCW_E_DEGENERATE;
+            h->err = "template " + std::to_string(t) +
+                     ": encountered a single-atom Fstat-calculation (i_t1 == i_t0). This is degenerate and "
+                     "cannot be computed; t0 must stay away at least 2*TAtom from the end of the data";
+        }
+    }
+    return worst;
+}
+
+extern "C" int tcw_fetch_fmn(tcw_handle *h, int t, float *out) {
+    if (!h || !out) return TCW_E_INVALID;
+    if (!h->have_fmn) return fail(h, TCW_E_STATE, "tcw_fetch_fmn: last map did not materialise F_mn");
+    if (t < 0 || t >= h->T) return fail(h, TCW_E_INVALID, "tcw_fetch_fmn: template index out of range");
+    const size_t cells = (size_t)h->last_N_t0 * h->last_N_tau;
+    CUDA_TRY(h, cudaMemcpyAsync(out, (const float *)h->d_Fmn.p + (size_t)t * cells, cells * sizeof(float),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return TCW_OK;
+}
+
+extern "C" int tcw_fetch_merged(tcw_handle *h, int t, float *out, uint32_t capacityN) {
+    if (!h || !out) return TCW_E_INVALID;
+    if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_fetch_merged: no map has been run");
+    if (t < 0 || t >= h->T) return fail(h, TCW_E_INVALID, "tcw_fetch_merged: template index out of range");
+    const uint32_t N = h->meta[t].numAtoms;
+    if (capacityN < N) return fail(h, TCW_E_INVALID, "tcw_fetch_merged: capacity too small");
+    for (int c = 0; c < TCW_NCH; c++)
+        CUDA_TRY(h, cudaMemcpyAsync(out + (size_t)c * capacityN,
+                                    (const float *)h->d_X.p + ((size_t)t * TCW_NCH + c) * h->xpad,
+                                    (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return TCW_OK;
+}
+
+extern "C" int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                             uint32_t atom_stride, uint32_t TAtom, int T, int numDet,
+                             const tcw_window_range *win, uint32_t flags, float *F_mn_out,
+                             tcw_result *results) {
+    if (!h) return TCW_E_INVALID;
+    if (!results) return fail(h, TCW_E_INVALID, "tcw_map_batch: results is NULL");
+    if ((flags & TCW_WANT_FMN) && !F_mn_out)
+        return fail(h, TCW_E_INVALID, "tcw_map_batch: TCW_WANT_FMN needs F_mn_out");
+    int rc = tcw_upload_atoms(h, atoms, n_atoms, atom_stride, TAtom, T, numDet);
+    if (rc) return rc;
+    rc = tcw_map_resident(h, win, flags);
+    if (rc) return rc;
+    if (flags & TCW_WANT_FMN) {
+        const size_t cells = (size_t)h->last_N_t0 * h->last_N_tau;
+        CUDA_TRY(h, cudaMemcpyAsync(F_mn_out, h->d_Fmn.p, (size_t)T * cells * sizeof(float),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+    return tcw_fetch_results(h, results);
+}
+
+// ---------------------------------------------------------------------------------------
+// SIMT peak microbenchmarks (roofline denominators not in MEASURED_PEAKS.json)
+// ---------------------------------------------------------------------------------------
+__global__ void tcw_ffma_peak_kernel(float *out, int iters) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3f + i;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void tcw_dadd_peak_kernel(double *out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+    const double c = 1e-7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __dadd_rn(a[i], c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int tcw_microbench(tcw_handle *h, double *ffma_tflops, double *dadd_tflops) {
+    if (!h || !ffma_tflops || !dadd_tflops) return TCW_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure(h, h->d_scratch, 1024);
+    if (rc) return rc;
+    const int blocks = h->prop.multiProcessorCount * 8, threads = 256;
+    const int iters_f = 4096, iters_d = 1024;
+    float ms = 0;
+    for (int rep = 0; rep < 2; rep++) {  // first rep warms up
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[0], h->stream));
+        tcw_ffma_peak_kernel<<<blocks, threads, 0, h->stream>>>((float *)h->d_scratch.p, iters_f);
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[1], h->stream));
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_timer[1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]));
+    }
+    *ffma_tflops = 2.0 * 64.0 * iters_f * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 2; rep++) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[0], h->stream));
+        tcw_dadd_peak_kernel<<<blocks, threads, 0, h->stream>>>((double *)h->d_scratch.p, iters_d);
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[1], h->stream));
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_timer[1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]));
+    }
+    *dadd_tflops = 64.0 * iters_d * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    h->launches += 4;
+    return TCW_OK;
+}

@@ -1,0 +1,183 @@
+// tcw_btsg.cuh -- lnBtSG marginalisation pass and the per-template finalize kernel.
+//
+// Replaces the host-side numpy reductions of the reference's GPU path (a full D2H of F_mn
+// followed by max/argmax, tcw:810-815, and exp-sums, tcw:210-216, 247-251, 282-286) and the
+// lalpulsar calls of its CPU path (XLALComputeTransientBstat, XLALComputeTransientPosterior_t0
+// / _tau, XLALFindModeOfPDF1D; tcw:577-586).
+//
+//   lnBtSG = ln(70/(N_t0 N_tau)) + maxF + ln sum_mn e^{-(maxF - F_mn)}
+//   t0_MP  = t0  + (argmax_m sum_n e^{..} + 1/2) t0Band / N_t0      (bin centre)
+//   tau_MP = tau + (argmax_n sum_m e^{..} + 1/2) tauBand / N_tau
+//
+// In `lal` mode every term is XLALFastNegExp(maxF - F_mn): a nearest-point table lookup whose
+// argument needs the FINAL maxF, so this is a second pass after the map kernel's atomicMax has
+// settled (it re-reads the float32 F_mn the map kernel left in HBM/L2 -- 4 B per cell).  All
+// sums are FP64, as in lalpulsar.
+#pragma once
+#include "tcw_common.cuh"
+#include "tcw_generic.cuh"
+
+#define TCW_BTSG_THREADS 256
+#define TCW_BTSG_ROWS 64
+#define TCW_BTSG_COLS 256
+
+template <bool EXACT_EXP>
+__global__ void __launch_bounds__(TCW_BTSG_THREADS)
+tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32_t N_tau,
+                const unsigned long long *__restrict__ maxkey, const double *__restrict__ lut,
+                double *__restrict__ rowsum, double *__restrict__ colsum) {
+    __shared__ double scol[TCW_BTSG_THREADS / 32][TCW_BTSG_COLS];
+    const int tz = blockIdx.z;
+    const int t = t_base + tz;
+    const unsigned long long key = maxkey[t];
+    const double maxF = key ? (double)orderable_float((uint32_t)(key >> 32)) : -1.0;
+    const size_t cells = (size_t)N_t0 * N_tau;
+    const float *Ft = Fmn + (size_t)tz * cells;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t m0 = blockIdx.y * TCW_BTSG_ROWS, n0 = blockIdx.x * TCW_BTSG_COLS;
+
+    double colacc[TCW_BTSG_COLS / 32];
+#pragma unroll
+    for (int j = 0; j < TCW_BTSG_COLS / 32; j++) colacc[j] = 0.0;
+
+    for (int i = 0; i < TCW_BTSG_ROWS / (TCW_BTSG_THREADS / 32); i++) {
+        const uint32_t m = m0 + warp + i * (TCW_BTSG_THREADS / 32);
+        if (m >= N_t0) break;
+        double rowacc = 0.0;
+#pragma unroll
+        for (int j = 0; j < TCW_BTSG_COLS / 32; j++) {
+            const uint32_t n = n0 + lane + 32 * j;
+            if (n < N_tau) {
+                const double dF = maxF - (double)__ldg(Ft + (size_t)m * N_tau + n);  // >= 0
+                const double e = EXACT_EXP ? exp(-dF) : fast_neg_exp_lut(dF, lut);
+                rowacc += e;
+                colacc[j] += e;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rowacc += __shfl_xor_sync(0xffffffffu, rowacc, o);
+        if (lane == 0) atomicAdd(&rowsum[(size_t)t * N_t0 + m], rowacc);
+    }
+#pragma unroll
+    for (int j = 0; j < TCW_BTSG_COLS / 32; j++) scol[warp][lane + 32 * j] = colacc[j];
+    __syncthreads();
+    {
+        const uint32_t n = n0 + threadIdx.x;
+        if (n < N_tau) {
+            double s = 0.0;
+#pragma unroll
+            for (int wv = 0; wv < TCW_BTSG_THREADS / 32; wv++) s += scol[wv][threadIdx.x];
+            atomicAdd(&colsum[(size_t)t * N_tau + n], s);
+        }
+    }
+}
+
+// (value desc, index asc) argmax + sum, one CTA per template
+struct ArgMaxD {
+    double v;
+    uint32_t i;
+};
+__device__ __forceinline__ ArgMaxD argmax_better(ArgMaxD a, ArgMaxD b) {
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+
+#define TCW_FIN_THREADS 256
+
+__device__ __forceinline__ void block_sum_argmax(const double *__restrict__ v, uint32_t n,
+                                                 double *sum_out, uint32_t *arg_out) {
+    __shared__ double ssum[TCW_FIN_THREADS / 32];
+    __shared__ ArgMaxD sarg[TCW_FIN_THREADS / 32];
+    double s = 0.0;
+    ArgMaxD a;
+    a.v = -INFINITY;
+    a.i = 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < n; i += TCW_FIN_THREADS) {
+        const double x = v[i];
+        s += x;
+        ArgMaxD b;
+        b.v = x;
+        b.i = i;
+        a = argmax_better(a, b);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ArgMaxD b;
+        b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+        b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+        a = argmax_better(a, b);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        ssum[warp] = s;
+        sarg[warp] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        ArgMaxD best = sarg[0];
+        for (int wv = 0; wv < TCW_FIN_THREADS / 32; wv++) {
+            tot += ssum[wv];
+            best = argmax_better(best, sarg[wv]);
+        }
+        *sum_out = tot;
+        *arg_out = best.i == 0xFFFFFFFFu ? 0u : best.i;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TCW_FIN_THREADS)
+tcw_finalize_kernel(const unsigned long long *__restrict__ maxkey, const uint32_t *__restrict__ flags,
+                    const double *__restrict__ rowsum, const double *__restrict__ colsum,
+                    const TplMeta *__restrict__ meta, MapWindow w, int none_window, uint32_t TAtom,
+                    int want_btsg, int allow_degenerate, uint32_t path, tcw_result *__restrict__ results) {
+    const int t = blockIdx.x;
+    __shared__ double s_tot, s_tot2;
+    __shared__ uint32_t s_mMP, s_nMP;
+    if (want_btsg) {
+        block_sum_argmax(rowsum + (size_t)t * w.N_t0, w.N_t0, &s_tot, &s_mMP);
+        block_sum_argmax(colsum + (size_t)t * w.N_tau, w.N_tau, &s_tot2, &s_nMP);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    tcw_result r;
+    r.N_t0 = w.N_t0;
+    r.N_tau = w.N_tau;
+    r.numAtoms = meta[t].numAtoms;
+    r.t0_data = meta[t].t0_data;
+    r.path = path;
+    r.reserved = 0;
+    // TRANSIENT_NONE: rect window spanning this template's data (tcw:742-749)
+    const uint32_t w_t0 = none_window ? meta[t].t0_data : w.t0;
+    const uint32_t w_tau = none_window ? meta[t].numAtoms * TAtom : w.tau;
+    const unsigned long long key = maxkey[t];
+    if (key) {
+        r.maxF = orderable_float((uint32_t)(key >> 32));
+        const uint32_t flat = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+        r.m_ML = flat / w.N_tau;
+        r.n_ML = flat - r.m_ML * w.N_tau;
+        r.t0_ML = w_t0 + r.m_ML * w.dt0;
+        r.tau_ML = w_tau + r.n_ML * w.dtau;
+    } else {  // no cell exceeded the initial -1: lalpulsar leaves the calloc'ed zeros
+        r.maxF = -1.0f;
+        r.m_ML = r.n_ML = 0;
+        r.t0_ML = r.tau_ML = 0;
+    }
+    r.m_MP = r.n_MP = 0;
+    r.lnBtSG = r.t0_MP = r.tau_MP = __longlong_as_double(0x7ff8000000000000LL);  // NaN (tcw:142-144)
+    if (want_btsg) {
+        const double normBh = 70.0 / ((double)w.N_t0 * (double)w.N_tau);
+        const double logBhat = (double)r.maxF + log(s_tot);
+        r.lnBtSG = log(normBh) + logBhat;
+        r.m_MP = s_mMP;
+        r.n_MP = s_nMP;
+        r.t0_MP = (double)w_t0 + ((double)s_mMP + 0.5) * ((double)w.t0Band / (double)w.N_t0);
+        r.tau_MP = (double)w_tau + ((double)s_nMP + 0.5) * ((double)w.tauBand / (double)w.N_tau);
+    }
+    const uint32_t f = flags[t];
+    r.status = TCW_OK;
+    if ((f & TCW_FLAG_DEGENERATE) && !allow_degenerate) r.status = TCW_E_DEGENERATE;
+    if (f & TCW_FLAG_UNSORTED) r.status = TCW_E_INVALID;
+    results[t] = r;
+}

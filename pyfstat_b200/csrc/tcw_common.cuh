@@ -1,0 +1,228 @@
+// tcw_common.cuh -- shared device/host helpers of the B200 transient F-stat map backend.
+//
+// Index arithmetic follows the reference kernels bit for bit
+// (pyCUDAkernels/cudaTransientFstatRectWindow.cu:21-31, 54-69; ...ExpWindow.cu:27-65):
+// all uint32, signed re-interpretation only for the `< 0` clamp.  The runtime division by
+// TAtom is done with a Granlund-Montgomery magic multiplier that is exact for every uint32
+// dividend (tests/test_host_logic.py sweeps it against Python integers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "tcw_b200.h"
+
+#define TCW_NCH 7          // a2, b2, ab, Fa_re, Fa_im, Fb_re, Fb_im (tcw:711-721)
+#define TCW_LUT_LEN 2000   // XLALFastNegExp table (recalled: EXPLUT_LENGTH)
+#define TCW_LUT_XMAX 20.0  // (recalled: EXPLUT_XMAX)
+
+// ---------------------------------------------------------------------------------------
+// exact uint32 division by a runtime-invariant divisor
+//   q = (t + ((x - t) >> sh1)) >> sh2,  t = mulhi(m, x)      (Granlund & Montgomery 1994, fig 4.1)
+// ---------------------------------------------------------------------------------------
+struct MagicDiv {
+    uint32_t m, sh1, sh2;
+};
+
+static inline MagicDiv make_magic(uint32_t d) {
+    MagicDiv md;
+    uint32_t l = 0;
+    while (l < 32 && (1ull << l) < (uint64_t)d) l++;  // l = ceil(log2 d)
+    uint64_t num = ((1ull << l) - (uint64_t)d) << 32;  // 2^32 * (2^l - d) < 2^64
+    md.m = (uint32_t)(num / d + 1);
+    md.sh1 = l < 1 ? l : 1;
+    md.sh2 = l > 1 ? l - 1 : 0;
+    return md;
+}
+
+__host__ __device__ __forceinline__ uint32_t magic_div(uint32_t x, const MagicDiv md) {
+#ifdef __CUDA_ARCH__
+    uint32_t t = __umulhi(md.m, x);
+#else
+    uint32_t t = (uint32_t)(((uint64_t)md.m * (uint64_t)x) >> 32);
+#endif
+    return (t + ((x - t) >> md.sh1)) >> md.sh2;
+}
+
+// per-template geometry of the merged (binned) atoms + what the index math needs
+struct TplMeta {
+    uint32_t t0_data;   // first merged timestamp (tcw:725)
+    uint32_t numAtoms;  // merged atoms on the TAtom grid (tcw:709)
+};
+
+struct IndexGeom {
+    uint32_t TAtom, TAtomHalf;
+    MagicDiv md;
+    uint32_t ef;  // 1 (rect: t1 = t0+tau) or 3 (exp: t1 = t0 + 3 tau)
+};
+
+// clamp as the reference does: int i_tmp = q; if (i_tmp < 0) i_tmp = 0; min(., numAtoms-1)
+__host__ __device__ __forceinline__ uint32_t clamp_index(uint32_t q, uint32_t numAtoms) {
+    int32_t i = (int32_t)q;
+    if (i < 0) i = 0;
+    uint32_t u = (uint32_t)i;
+    return u >= numAtoms ? numAtoms - 1 : u;
+}
+__host__ __device__ __forceinline__ uint32_t index_t0(uint32_t t0_m, uint32_t t0_data,
+                                                      uint32_t numAtoms, const IndexGeom g) {
+    return clamp_index(magic_div(t0_m - t0_data + g.TAtomHalf, g.md), numAtoms);
+}
+__host__ __device__ __forceinline__ uint32_t index_t1(uint32_t t1, uint32_t t0_data,
+                                                      uint32_t numAtoms, const IndexGeom g) {
+    return clamp_index(magic_div(t1 - t0_data + g.TAtomHalf, g.md) - 1u, numAtoms);
+}
+
+// window range with the TRANSIENT_NONE substitution already applied
+struct MapWindow {
+    uint32_t type;  // TCW_WINDOW_RECT or TCW_WINDOW_EXP
+    uint32_t t0, dt0, tau, dtau;
+    uint32_t t0Band, tauBand;
+    uint32_t N_t0, N_tau;
+};
+
+// ---------------------------------------------------------------------------------------
+// max / argmax bookkeeping: one packed 64-bit key per template,
+//   (orderable float bits << 32) | (0xFFFFFFFF - flat_index)
+// so atomicMax picks the larger F and, among equal F, the smaller row-major index
+// (first occurrence = np.argmax order, tcw:194, 810-813).  Key 0 = "no cell exceeded -1".
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_float(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long pack_key(float F, uint32_t flat) {
+    return ((unsigned long long)float_orderable(F) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+// block-wide max of a packed key, then one atomicMax per CTA (hierarchical reduction)
+template <int NWARPS>
+__device__ __forceinline__ void block_atomic_max_key(unsigned long long key,
+                                                     unsigned long long *dst,
+                                                     unsigned long long *smem_scratch) {
+    key = warp_max_u64(key);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem_scratch[warp] = key;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = lane < NWARPS ? smem_scratch[lane] : 0ull;
+        v = warp_max_u64(v);
+        if (lane == 0 && v != 0ull) atomicMax(dst, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy (1-D cp.async.bulk -> SASS UBLKCP) + mbarrier helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0,
+// both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// F-statistic from the 7 window sums.
+//
+// fstat_faithful: rounding for rounding what the reference kernels compute
+// (Rect.cu:98-118 == Exp.cu:109-129; double literals promote sub-expressions), with explicit
+// _rn intrinsics so nvcc cannot contract anything into FMAs.  Used by the generic kernels,
+// which are bit-identical to the CPU oracle.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float fstat_faithful(float Ad, float Bd, float Cd, float Fa_re,
+                                                float Fa_im, float Fb_re, float Fb_im) {
+    const float sumAB = __fadd_rn(Ad, Bd);
+    const float diffAB = __fsub_rn(Ad, Bd);
+    const double d2 = __dadd_rn((double)__fmul_rn(diffAB, diffAB),
+                                __dmul_rn(__dmul_rn(4.0, (double)Cd), (double)Cd));
+    const float disc = __double2float_rn(__dsqrt_rn(d2));
+    const float denom = __fsub_rn(sumAB, disc);
+    const float cond = (denom > 0.0f) ? __fdiv_rn(__fadd_rn(sumAB, disc), denom) : INFINITY;
+    float DdInv = 0.0f;
+    if (cond < 1e4f) {
+        const float det = __fsub_rn(__fmul_rn(Ad, Bd), __fmul_rn(Cd, Cd));
+        DdInv = __double2float_rn(__ddiv_rn(1.0, (double)det));
+    }
+    float F = 2.0f;
+    if (DdInv > 0.0f) {
+        const float fa2 = __fadd_rn(__fmul_rn(Fa_re, Fa_re), __fmul_rn(Fa_im, Fa_im));
+        const float fb2 = __fadd_rn(__fmul_rn(Fb_re, Fb_re), __fmul_rn(Fb_im, Fb_im));
+        const float re = __fadd_rn(__fmul_rn(Fa_re, Fb_re), __fmul_rn(Fa_im, Fb_im));
+        const float s1 = __fadd_rn(__fmul_rn(Bd, fa2), __fmul_rn(Ad, fb2));
+        const double u = __dsub_rn((double)s1, __dmul_rn(__dmul_rn(2.0, (double)Cd), (double)re));
+        F = __double2float_rn(__dmul_rn((double)DdInv, u));
+    }
+    return F;
+}
+
+// fstat_fast: the same guarded formula in pure FP32 for the tiled kernels, without sqrt or
+// division in the conditioning test:
+//   cond = (s + d)/(s - d) < 1e4,  d = sqrt(diff^2 + 4 C^2) >= 0,  s - d > 0
+//     <=>  s > 0  and  d < s (1e4-1)/(1e4+1)   <=>  s > 0  and  d^2 < (s k)^2
+// and DdInv = 1/(AB - C^2) via one MUFU.RCP (1 ulp).  Differences to the faithful form are
+// O(ulp) and only matter for cells sitting exactly on the cond = 1e4 boundary (listed
+// separately by the parity tests).  ~27 FP32 instructions per cell.
+__device__ __forceinline__ float fstat_fast(float Ad, float Bd, float Cd, float Fa_re, float Fa_im,
+                                            float Fb_re, float Fb_im) {
+    const float sumAB = Ad + Bd;
+    const float diffAB = Ad - Bd;
+    const float c2 = Cd * Cd;
+    const float disc2 = fmaf(diffAB, diffAB, 4.0f * c2);
+    const float sk = sumAB * (9999.0f / 10001.0f);
+    const float det = fmaf(Ad, Bd, -c2);
+    const bool ok = (sumAB > 0.0f) && (disc2 < sk * sk) && (det > 0.0f);
+    const float fa2 = fmaf(Fa_re, Fa_re, Fa_im * Fa_im);
+    const float fb2 = fmaf(Fb_re, Fb_re, Fb_im * Fb_im);
+    const float re = fmaf(Fa_re, Fb_re, Fa_im * Fb_im);
+    const float num = fmaf(Bd, fa2, fmaf(Ad, fb2, (-2.0f * Cd) * re));
+    float rdet;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdet) : "f"(det));
+    return ok ? num * rdet : 2.0f;
+}
+#endif  // __CUDACC__

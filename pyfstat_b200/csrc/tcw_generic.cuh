@@ -1,0 +1,82 @@
+// tcw_generic.cuh -- generic map kernels: any window geometry, bit-faithful arithmetic.
+//
+// One thread per (t0,tau) cell.  Index ranges use the reference's uint32 formulas verbatim
+// (Rect.cu:21-31, 54-69; Exp.cu:27-65) so wrap-around / clamped / unaligned windows behave
+// exactly like the reference; sums are sequential float32 in atom order, which is what the
+// reference's running sums produce (Rect.cu:33-40, 75-91), and every operation is an explicit
+// round-to-nearest intrinsic so the results are bit-identical to the CPU oracle
+// (oracle/tcw_oracle.c, semantics "lal").
+//
+// These kernels are the correctness path: they serve windows the tiled kernels do not certify
+// (tcw_b200.cu: fast_path_certificate) and anchor the parity tests of the tiled kernels.
+#pragma once
+#include "tcw_common.cuh"
+#include "tcw_prep.cuh"
+
+#define TCW_GENERIC_THREADS 256
+
+// XLALFastNegExp (recalled): nearest-point lookup in a table of e^{-x},
+// x in [0,20], 2000 steps; 0 beyond; (libm exp for negative x never happens here: x >= 0).
+__device__ __forceinline__ double fast_neg_exp_lut(double mx, const double *__restrict__ lut) {
+    if (mx > TCW_LUT_XMAX) return 0.0;
+    const uint32_t i0 = __double2uint_rz(__dadd_rn(__dmul_rn(mx, (double)TCW_LUT_LEN / TCW_LUT_XMAX), 0.5));
+    return __ldg(lut + i0);
+}
+
+template <int WTYPE, bool EXACT_EXP>
+__global__ void __launch_bounds__(TCW_GENERIC_THREADS)
+tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
+                       int t_base, MapWindow w, int none_window, IndexGeom g,
+                       const double *__restrict__ lut,
+                       float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
+                       uint32_t *__restrict__ flags) {
+    __shared__ unsigned long long red[TCW_GENERIC_THREADS / 32];
+    const int tz = blockIdx.z;
+    const int t = t_base + tz;
+    const uint32_t numAtoms = meta[t].numAtoms;
+    const uint32_t t0_data = meta[t].t0_data;
+    const size_t cells = (size_t)w.N_t0 * w.N_tau;
+    const size_t flat = (size_t)blockIdx.x * TCW_GENERIC_THREADS + threadIdx.x;
+    unsigned long long key = 0ull;
+    if (flat < cells) {
+        const uint32_t m = (uint32_t)(flat / w.N_tau);
+        const uint32_t n = (uint32_t)(flat - (size_t)m * w.N_tau);
+        // TRANSIENT_NONE: rect window spanning this template's data, 1x1 map (tcw:742-749)
+        const uint32_t t0_m = (none_window ? t0_data : w.t0) + m * w.dt0;
+        const uint32_t tau_n = (none_window ? numAtoms * g.TAtom : w.tau) + n * w.dtau;
+        const uint32_t t1 = t0_m + g.ef * tau_n;
+        const uint32_t i_t0 = index_t0(t0_m, t0_data, numAtoms, g);
+        const uint32_t i_t1 = index_t1(t1, t0_data, numAtoms, g);
+        if (i_t1 == i_t0) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
+        const float *x = X + (size_t)t * TCW_NCH * xpad;
+        float S[TCW_NCH];
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++) S[c] = 0.0f;
+        if (WTYPE == TCW_WINDOW_RECT) {
+            for (uint32_t i = i_t0; i <= i_t1; i++) {
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++) S[c] = __fadd_rn(S[c], __ldg(x + (size_t)c * xpad + i));
+            }
+        } else {
+            for (uint32_t i = i_t0; i <= i_t1; i++) {
+                const uint32_t t_i = t0_data + i * g.TAtom;  // Exp.cu:84
+                double win = 0.0;
+                if (t_i >= t0_m && t_i <= t1) {
+                    const double xx = __ddiv_rn((double)(t_i - t0_m), (double)tau_n);
+                    win = EXACT_EXP ? exp(-xx) : fast_neg_exp_lut(xx, lut);
+                }
+                const double win2 = __dmul_rn(win, win);
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++) {
+                    const double a = (double)__ldg(x + (size_t)c * xpad + i);
+                    // REAL4 accumulator += REAL4 atom * REAL8 window, evaluated in double
+                    S[c] = __double2float_rn(__dadd_rn((double)S[c], __dmul_rn(a, c < 3 ? win2 : win)));
+                }
+            }
+        }
+        const float F = fstat_faithful(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+        if (Fmn) Fmn[(size_t)tz * cells + flat] = F;
+        if (F > -1.0f) key = pack_key(F, (uint32_t)flat);  // maxF starts at -1, strict > (tcw:135-139)
+    }
+    block_atomic_max_key<TCW_GENERIC_THREADS / 32>(key, &maxkey[t], red);
+}

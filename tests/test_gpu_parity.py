@@ -1,0 +1,421 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at the
+BASELINE sizes -- through size-independent properties.
+
+Parity bars (BASELINE.json north_star):
+  * window index ranges: bit-exact (generic kernels reproduce the oracle's F_mn BIT FOR BIT,
+    which implies identical index ranges; the kernels' index functions are additionally swept
+    on the host in tests/test_host_logic.py);
+  * F_mn: <= 1e-4 relative for the tiled kernels (RTOL below), with the documented exception
+    of ill-conditioned cells (antenna-pattern condition number within a factor ~2 of the 1e4
+    cut), where float32 window sums -- the reference's as much as ours -- carry O(eps*cond)
+    noise;
+  * lnBtSG: <= 1e-4 absolute (ATOL_LNB);
+  * argmax identical except on documented near-ties.
+Nothing here reads /root/reference.
+"""
+
+import math
+
+import numpy as np
+import pytest
+from conftest import golden_cases, load_golden
+
+from pyfstat_b200 import _lib as L
+from pyfstat_b200.atoms import ATOM_DTYPE, AtomBatch, batch_from_detector_lists, synth_atoms
+from pyfstat_b200.window import TransientWindowRange, canonical_window
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4      # F_mn relative tolerance of the tiled kernels vs the oracle
+ATOL_LNB = 1e-4  # lnBtSG absolute tolerance
+
+
+def run_gpu(gpu, batch, w, flags=0, btsg=True, fmn=True):
+    fl = flags | (L.WANT_BTSG if btsg else 0) | (L.WANT_FMN if fmn else 0)
+    return gpu.map_batch(batch, w, fl, raise_on_degenerate=False)
+
+
+def cond_number(oracle_result, w, TAtom):
+    """Condition number of the window-summed antenna-pattern matrix per cell (float64), to
+    separate ill-conditioned cells in the tolerance statistics."""
+    m = oracle_result["merged"]
+    N = len(m)
+    P = {c: np.concatenate([[0.0], np.cumsum(m[c].astype(np.float64))]) for c in ("a2_alpha", "b2_alpha", "ab_alpha")}
+    N_t0, N_tau = oracle_result["F_mn"].shape
+    ef = 3 if w.type == 2 else 1
+    t0d = int(m["timestamp"][0])
+    cond = np.full((N_t0, N_tau), np.inf)
+    if w.type != 1:
+        return cond  # only used for rect
+    for mm in range(N_t0):
+        t0m = w.t0 + mm * w.dt0
+        i0 = min(max((t0m - t0d + TAtom // 2) // TAtom, 0), N - 1)
+        for nn in range(N_tau):
+            t1 = t0m + ef * (w.tau + nn * w.dtau)
+            i1 = min(max((t1 - t0d + TAtom // 2) // TAtom - 1, 0), N - 1)
+            A = P["a2_alpha"][i1 + 1] - P["a2_alpha"][i0]
+            B = P["b2_alpha"][i1 + 1] - P["b2_alpha"][i0]
+            C = P["ab_alpha"][i1 + 1] - P["ab_alpha"][i0]
+            d = math.sqrt((A - B) ** 2 + 4 * C * C)
+            cond[mm, nn] = (A + B + d) / (A + B - d) if A + B - d > 0 else np.inf
+    return cond
+
+
+def assert_records_match(res, t, o, w, check_mp=True):
+    assert int(res["N_t0"][t]) == o["N_t0"] and int(res["N_tau"][t]) == o["N_tau"]
+    assert int(res["numAtoms"][t]) == o["numAtoms"] and int(res["t0_data"][t]) == o["t0_data"]
+    assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == (o["m_ML"], o["n_ML"])
+    assert (int(res["t0_ML"][t]), int(res["tau_ML"][t])) == (o["t0_ML"], o["tau_ML"])
+    if check_mp:
+        assert (int(res["m_MP"][t]), int(res["n_MP"][t])) == (o["m_MP"], o["n_MP"])
+
+
+# ---- generic kernels: bit-exact -------------------------------------------------------------
+
+GENERIC_CASES = [
+    ("rect", ("H1",), 48, 0.0, 1),
+    ("exp", ("H1",), 48, 0.0, 2),
+    ("rect", ("H1", "L1"), 150, 0.0, 3),
+    ("exp", ("H1", "L1"), 150, 0.0, 4),
+    ("rect", ("H1", "L1"), 200, 0.15, 5),
+    ("exp", ("H1", "L1"), 200, 0.15, 6),
+    ("rect", ("H1", "L1", "V1"), 96, 0.1, 7),
+]
+
+
+@pytest.mark.parametrize("win,dets,n,gap,seed", GENERIC_CASES)
+def test_generic_kernels_bit_exact_vs_oracle(gpu, oracle, win, dets, n, gap, seed):
+    """On-device merge + generic map + lnBtSG pass == oracle, bit for bit (F_mn, maxF, merged
+    atoms) and to rounding (lnBtSG, summed in a different order)."""
+    b = synth_atoms(2, n, dets, seed=seed, gap_fraction=gap)
+    w = canonical_window(win, 10**9, n)
+    res, F = run_gpu(gpu, b, w, L.FORCE_GENERIC)
+    for t in range(b.T):
+        o = oracle.compute_map(b.template(t), b.TAtom, w, allow_degenerate=True)
+        assert int(res["path"][t]) == 0
+        assert np.array_equal(F[t], o["F_mn"].astype(np.float32)), f"t={t}: F_mn differs"
+        assert float(res["maxF"][t]) == o["maxF"]
+        assert_records_match(res, t, o, w)
+        assert float(res["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=1e-11)
+        assert float(res["t0_MP"][t]) == pytest.approx(o["t0_MP"], abs=1e-6)
+        assert float(res["tau_MP"][t]) == pytest.approx(o["tau_MP"], abs=1e-6)
+        merged = gpu.fetch_merged(t, o["numAtoms"])
+        assert np.array_equal(merged.T, oracle.merged_to_matrix(o["merged"]))
+
+
+WEIRD_WINDOWS = [
+    # (type, t0 offset from t0_data, t0Band, dt0, tau, tauBand, dtau)
+    (1, 700, 60 * 1800, 2700, 5000, 40 * 1800, 4500),     # unaligned, dt0 != dtau
+    (2, 700, 40 * 1800, 2700, 5000, 12 * 1800, 4500),
+    (1, -1000, 5 * 1800, 1800, 3600, 30 * 1800, 1800),    # t0 before the data: uint32 wrap -> clamp to N-1
+    (1, -900, 5 * 1800, 1800, 3600, 30 * 1800, 1800),     # exactly half an atom before: rounds to 0
+    (1, 0, 200 * 1800, 1800, 3600, 300 * 1800, 1800),     # window far beyond the data end (clamps)
+    (2, 0, 10 * 1800, 1800, 900, 50 * 1800, 450),         # tau < TAtom, fine tau steps
+    (1, 0, 10 * 1800, 1, 3600, 5, 1),                     # 1-second steps
+    (1, 0, 0, 1800, 3600, 0, 1800),                       # 1x1 (the MCMC case)
+    (2, 3 * 1800, 0, 1800, 5 * 1800, 0, 1800),
+    (1, 0, 20 * 1800, 1800, 1800, 20 * 1800, 1800),       # tau = 1 atom: degenerate cells everywhere
+    (1, 0, 10 * 1801, 1801, 3601, 10 * 1799, 1799),       # odd steps
+]
+
+
+@pytest.mark.parametrize("spec", WEIRD_WINDOWS)
+def test_generic_kernels_arbitrary_windows_bit_exact(gpu, oracle, spec):
+    """Unaligned / wrapped / clamped / degenerate windows: identical
+    F_mn means identical (i_t0, i_t1) for every cell."""
+    wtype, off, t0Band, dt0, tau, tauBand, dtau = spec
+    b = synth_atoms(1, 96, ("H1", "L1"), seed=31, gap_fraction=0.05)
+    w = TransientWindowRange(wtype, 10**9 + off, t0Band, dt0, tau, tauBand, dtau)
+    res, F = run_gpu(gpu, b, w, L.FORCE_GENERIC)
+    o = oracle.compute_map(b.template(0), b.TAtom, w, allow_degenerate=True)
+    assert np.array_equal(F[0], o["F_mn"].astype(np.float32))
+    assert_records_match(res, 0, o, w)
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=1e-11)
+    # lal's single-atom abort is reported per template
+    o_strict = oracle.compute_map(b.template(0), b.TAtom, w, want_btsg=False)
+    assert int(res["status"][0]) == o_strict["status"]
+
+
+@pytest.mark.parametrize("spec", WEIRD_WINDOWS)
+def test_default_path_handles_arbitrary_windows(gpu, oracle, spec):
+    """Same windows through the default dispatch (tiled kernels where the host certificate
+    allows, generic otherwise): within tolerance of the oracle, same argmax, same status."""
+    wtype, off, t0Band, dt0, tau, tauBand, dtau = spec
+    b = synth_atoms(1, 96, ("H1", "L1"), seed=31, gap_fraction=0.05)
+    w = TransientWindowRange(wtype, 10**9 + off, t0Band, dt0, tau, tauBand, dtau)
+    res, F = run_gpu(gpu, b, w, 0)
+    o = oracle.compute_map(b.template(0), b.TAtom, w, allow_degenerate=True)
+    Fo = o["F_mn"]
+    rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+    assert rel.max() <= RTOL, (spec, rel.max())
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+    o_strict = oracle.compute_map(b.template(0), b.TAtom, w, want_btsg=False)
+    assert int(res["status"][0]) == o_strict["status"]
+    if rel.max() == 0:
+        assert_records_match(res, 0, o, w)
+
+
+# ---- tiled kernels: tolerance ---------------------------------------------------------------
+
+FAST_CASES = [
+    ("rect", ("H1", "L1"), 300, 0.0, 11),
+    ("exp", ("H1", "L1"), 300, 0.0, 12),
+    ("rect", ("H1", "L1"), 700, 0.1, 13),
+    ("exp", ("H1", "L1"), 500, 0.1, 14),
+    ("rect", ("H1", "L1", "V1"), 257, 0.0, 15),
+    ("exp", ("H1",), 200, 0.0, 16),
+]
+
+
+@pytest.mark.parametrize("win,dets,n,gap,seed", FAST_CASES)
+def test_tiled_kernels_within_tolerance(gpu, oracle, win, dets, n, gap, seed):
+    b = synth_atoms(2, n, dets, seed=seed, gap_fraction=gap)
+    w = canonical_window(win, 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    for t in range(b.T):
+        assert int(res["path"][t]) == 1, "canonical windows must take the tiled kernels"
+        o = oracle.compute_map(b.template(t), b.TAtom, w, allow_degenerate=True)
+        Fo = o["F_mn"]
+        rel = np.abs(F[t] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+        assert rel.max() <= RTOL, f"{win} t={t}: max rel {rel.max():.3e} at {np.unravel_index(rel.argmax(), rel.shape)}"
+        assert float(res["maxF"][t]) == pytest.approx(o["maxF"], rel=RTOL)
+        # argmax identical unless the runner-up is a near-tie (documented exception)
+        top2 = np.sort(Fo.ravel())[-2:]
+        near_tie = (top2[1] - top2[0]) <= 2 * RTOL * top2[1]
+        if not near_tie:
+            assert_records_match(res, t, o, w, check_mp=False)
+        assert float(res["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+        # the lnBtSG pass itself is exact given the map it sees (LUT emulation is bit-faithful)
+        again = oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=True)
+        assert float(res["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=1e-11)
+        assert (int(res["m_MP"][t]), int(res["n_MP"][t])) == (again["m_MP"], again["n_MP"])
+
+
+def test_tiled_rect_single_detector_conditioning(gpu, oracle):
+    """H1 only: short windows are ill-conditioned (cond up to the 1e4 cut), where float32 sums
+    carry O(eps*cond) noise in the reference's arithmetic as well as ours.  Cells with
+    cond < 2e3 must meet RTOL; all cells must meet RTOL * max(1, cond/2e3); cells straddling
+    the cut (F = 2 fallback on one side) are counted and must be rare."""
+    n = 400
+    b = synth_atoms(1, n, ("H1",), seed=41)
+    w = canonical_window("rect", 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    o = oracle.compute_map(b.template(0), b.TAtom, w, allow_degenerate=True)
+    Fo = o["F_mn"]
+    cond = cond_number(o, w, b.TAtom)
+    rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+    flipped = (F[0] == 2.0) != (Fo == 2.0)
+    assert flipped.sum() <= 5 and np.all(np.abs(cond[flipped] / 1e4 - 1) < 1e-3)
+    ok = ~flipped
+    well = ok & (cond < 2e3)
+    assert well.sum() > 0.5 * rel.size
+    assert rel[well].max() <= RTOL
+    assert np.all(rel[ok] <= RTOL * np.maximum(1.0, cond[ok] / 2e3))
+
+
+def test_exact_exp_mode(gpu, oracle):
+    """TCW_EXP_EXACT: exact exp() for window weights and lnBtSG terms (what the reference's
+    pycuda/numpy path computes), vs the oracle's exact flavour."""
+    b = synth_atoms(1, 240, ("H1", "L1"), seed=51)
+    w = canonical_window("exp", 10**9, 240)
+    for force in (L.FORCE_GENERIC, 0):
+        res, F = run_gpu(gpu, b, w, L.EXP_EXACT | force)
+        o = oracle.compute_map(b.template(0), b.TAtom, w, exact_exp=True, allow_degenerate=True)
+        rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
+        assert rel.max() <= RTOL
+        assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+    lut = run_gpu(gpu, b, w, 0)[1]
+    assert np.abs(lut[0] - F[0]).max() / F[0].max() > 1e-4  # the two modes really differ
+
+
+# ---- golden fixtures (reference's own kernels / Python class) --------------------------------
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_fixtures(gpu, name):
+    """CUDA path vs outputs of the REFERENCE ITSELF (its .cu kernels run on the host and its
+    pyTransientFstatMap reductions; tests/golden/make_golden.py).  The reference kernels use
+    exact float exp and do not abort on degenerate cells, hence EXP_EXACT|ALLOW_DEGENERATE."""
+    z, batch, w = load_golden(name)
+    for force in (L.FORCE_GENERIC, 0):
+        res, F = run_gpu(gpu, batch, w, L.EXP_EXACT | L.ALLOW_DEGENERATE | force)
+        Fr = z["F_ref"].astype(np.float64)
+        rel = np.abs(F[0] - Fr) / np.maximum(np.abs(Fr), 1e-30)
+        if w.type == 1 and force:
+            assert np.array_equal(F[0], z["F_ref"])  # rect generic: bit-identical to Rect.cu
+        # single-detector maps contain ill-conditioned short windows (cond up to the 1e4 cut)
+        # where float32 sums carry O(eps*cond) noise: see test_tiled_rect_single_detector_conditioning
+        tol = RTOL if (batch.numDet > 1 or force) else 1e-3
+        assert rel.max() <= tol, (name, force, rel.max())
+        assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == tuple(int(x) for x in z["argmax"])
+        assert float(res["maxF"][0]) == pytest.approx(float(z["maxF"]), rel=RTOL)
+        assert float(res["lnBtSG"][0]) == pytest.approx(float(z["lnBtSG_numpy"]), abs=ATOL_LNB)
+        assert float(res["t0_MP"][0]) == pytest.approx(float(z["t0_MP"]), abs=1e-6)
+        assert float(res["tau_MP"][0]) == pytest.approx(float(z["tau_MP"]), abs=1e-6)
+        assert int(res["status"][0]) == 0
+
+
+# ---- known answers and edge cases ------------------------------------------------------------
+
+
+def test_known_answers_on_gpu(gpu, oracle):
+    b = synth_atoms(1, 96, ("H1", "L1"), seed=61)
+    # 1x1 map: lnBtSG = ln 70 + F
+    w = TransientWindowRange(1, 10**9 + 5 * 1800, 0, 1800, 20 * 1800, 0, 1800)
+    res, F = run_gpu(gpu, b, w)
+    assert F.shape == (1, 1, 1)
+    assert float(res["lnBtSG"][0]) == pytest.approx(math.log(70.0) + float(res["maxF"][0]), abs=1e-9)
+    assert (float(res["t0_MP"][0]), float(res["tau_MP"][0])) == (w.t0, w.tau)
+    # TRANSIENT_NONE == rect over all data == F_mn[0,-1] of the canonical map; input untouched
+    wn = TransientWindowRange(0, 1, 2, 3, 4, 5, 6)
+    rn, Fn = run_gpu(gpu, b, wn)
+    wc = canonical_window("rect", 10**9, 96)
+    rc, Fc = run_gpu(gpu, b, wc, L.FORCE_GENERIC)
+    assert Fn.shape == (1, 1, 1) and Fn[0, 0, 0] == Fc[0, 0, -1]
+    assert (int(rn["t0_ML"][0]), int(rn["tau_ML"][0])) == (10**9, 96 * 1800)
+    assert (wn.type, wn.t0, wn.tau) == (0, 1, 4)
+    # unknown window type -> ValueError (tcw:691-697)
+    with pytest.raises(ValueError):
+        gpu.map_batch(b, TransientWindowRange(3, 0, 0, 1, 0, 0, 1), 0)
+    with pytest.raises(L.TcwError):
+        gpu.map_batch(b, TransientWindowRange(1, 0, 10, 0, 0, 10, 1), 0)
+
+
+def test_degenerate_window_raises_like_lal(gpu):
+    b = synth_atoms(2, 48, ("H1",), seed=71)
+    w = canonical_window("rect", 10**9, 48)
+    w.t0Band = 47 * 1800  # t0 reaches the last atom -> single-atom window
+    for force in (L.FORCE_GENERIC, 0):
+        with pytest.raises(L.DegenerateWindowError):
+            gpu.map_batch(b, w, force)
+        res, _ = gpu.map_batch(b, w, force, raise_on_degenerate=False)
+        assert list(res["status"]) == [L.E_DEGENERATE] * 2
+        res, F = gpu.map_batch(b, w, force | L.ALLOW_DEGENERATE | L.WANT_FMN)  # pycuda semantics
+        assert list(res["status"]) == [0, 0] and F[0, -1, 0] == 2.0
+    we = canonical_window("exp", 10**9, 48)
+    we.t0Band = 47 * 1800
+    for force in (L.FORCE_GENERIC, 0):
+        with pytest.raises(L.DegenerateWindowError):
+            gpu.map_batch(b, we, force)
+
+
+def test_tie_rule_smallest_flat_index(gpu):
+    """Duplicated maximal cells -> first occurrence in row-major order (np.argmax, tcw:194)."""
+    a = np.zeros(64, dtype=ATOM_DTYPE)
+    a["timestamp"] = 10**9 + 1800 * np.arange(64)
+    batch = batch_from_detector_lists([[a]], 1800)
+    for win in ("rect", "exp"):
+        w = canonical_window(win, 10**9, 64)
+        for force in (L.FORCE_GENERIC, 0):
+            res, F = run_gpu(gpu, batch, w, force)
+            assert np.all(F == 2.0)
+            assert (int(res["m_ML"][0]), int(res["n_ML"][0]), float(res["maxF"][0])) == (0, 0, 2.0)
+            assert (int(res["m_MP"][0]), int(res["n_MP"][0])) == (0, 0)
+            assert float(res["lnBtSG"][0]) == pytest.approx(math.log(70.0) + 2.0, abs=1e-9)
+    # a plateau in the middle: constant atoms make F depend on the window LENGTH only, so all
+    # cells of the last column that are not clamped by the data end tie
+    a["a2_alpha"], a["b2_alpha"], a["ab_alpha"] = 0.5, 0.25, 0.125
+    a["Fa_re"], a["Fa_im"], a["Fb_re"], a["Fb_im"] = 1.0, 0.5, -0.25, 0.75
+    batch = batch_from_detector_lists([[a]], 1800)
+    w = TransientWindowRange(1, 10**9, 20 * 1800, 1800, 2 * 1800, 16 * 1800, 1800)
+    for force in (L.FORCE_GENERIC, 0):
+        res, F = run_gpu(gpu, batch, w, force)
+        flat = int(np.argmax(F[0]))
+        assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, F.shape[2])
+        assert int(res["m_ML"][0]) == 0 and int(res["n_ML"][0]) == F.shape[2] - 1
+
+
+def test_unsorted_atoms_rejected(gpu):
+    b = synth_atoms(1, 32, ("H1",), seed=81)
+    b.atoms["timestamp"][0, 0, 5], b.atoms["timestamp"][0, 0, 6] = (
+        b.atoms["timestamp"][0, 0, 6], b.atoms["timestamp"][0, 0, 5])
+    with pytest.raises(L.TcwError):
+        gpu.map_batch(b, canonical_window("rect", 10**9, 32), 0)
+
+
+def test_batch_equals_loop_bit_for_bit(gpu):
+    """Appendix E.6: batched results equal per-template calls, and flags do not change F."""
+    for win, n in (("rect", 180), ("exp", 130)):
+        b = synth_atoms(5, n, ("H1", "L1"), seed=91)
+        w = canonical_window(win, 10**9, n)
+        res, F = run_gpu(gpu, b, w, 0)
+        for t in range(b.T):
+            r1, F1 = run_gpu(gpu, b[t], w, 0)
+            assert np.array_equal(F1[0], F[t])
+            for k in ("maxF", "m_ML", "n_ML", "m_MP", "n_MP", "t0_ML", "tau_ML"):
+                assert r1[k][0] == res[k][t], k
+            assert float(r1["lnBtSG"][0]) == pytest.approx(float(res["lnBtSG"][t]), abs=1e-12)
+        # fused-only run (F_mn never materialised): same max/argmax
+        r2, none = run_gpu(gpu, b, w, 0, btsg=False, fmn=False)
+        assert none is None and np.array_equal(r2["maxF"], res["maxF"])
+        assert np.array_equal(r2["m_ML"], res["m_ML"]) and np.array_equal(r2["n_ML"], res["n_ML"])
+        assert np.all(np.isnan(r2["lnBtSG"]))  # BtSG=False leaves nan (tcw:142-144)
+
+
+def test_mixed_geometry_batch(gpu, oracle):
+    """Templates with different data spans / start times in one batch."""
+    t1 = synth_atoms(1, 100, ("H1", "L1"), seed=101).template(0)
+    t2 = synth_atoms(1, 140, ("H1", "L1"), seed=102, t0_data=10**9 + 3600).template(0)
+    b = batch_from_detector_lists([t1, t2], 1800)
+    for win in ("rect", "exp"):
+        w = canonical_window(win, 10**9 + 3600, 90)
+        res, F = run_gpu(gpu, b, w, 0)
+        for t, tpl in enumerate((t1, t2)):
+            o = oracle.compute_map(tpl, 1800, w, allow_degenerate=True)
+            rel = np.abs(F[t] - o["F_mn"]) / np.abs(o["F_mn"])
+            assert rel.max() <= RTOL
+            assert (int(res["numAtoms"][t]), int(res["t0_data"][t])) == (o["numAtoms"], o["t0_data"])
+
+
+# ---- BASELINE sizes: size-independent properties ---------------------------------------------
+
+
+@pytest.mark.parametrize("win,n,dets", [("rect", 1440, ("H1",)), ("exp", 1440, ("H1", "L1")), ("rect", 2880, ("H1", "L1"))])
+def test_full_size_properties(gpu, oracle, win, n, dets):
+    """Configs 1-3 at full size.  (a) fused max/argmax == np.argmax of the materialised map;
+    (b) lnBtSG == oracle's Bstat of that very map; (c) scaling the atoms by powers of two
+    (a2,b2,ab x4; Fa,Fb x2) leaves F bit-identical; (d) shifting all timestamps and the window
+    by the same offset leaves F bit-identical; (e) rect: F_mn[0,-1] == full-span F."""
+    b = synth_atoms(1, n, dets, seed=111)
+    w = canonical_window(win, 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    assert F.shape == (1, n - 1, n + 1) and int(res["status"][0]) == 0
+    flat = int(np.argmax(F[0]))
+    assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, n + 1)
+    assert float(res["maxF"][0]) == float(F[0].max())
+    again = oracle.bstat(F[0].astype(np.float64), float(res["maxF"][0]), w, use_lut=True)
+    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=1e-10)
+    assert (int(res["m_MP"][0]), int(res["n_MP"][0])) == (again["m_MP"], again["n_MP"])
+
+    scaled = AtomBatch(b.atoms.copy(), b.n_atoms, b.TAtom)
+    for k in ("a2_alpha", "b2_alpha", "ab_alpha"):
+        scaled.atoms[k] *= 4.0
+    for k in ("Fa_re", "Fa_im", "Fb_re", "Fb_im"):
+        scaled.atoms[k] *= 2.0
+    _, Fs = run_gpu(gpu, scaled, w, 0, btsg=False)
+    assert np.array_equal(Fs, F)
+
+    shifted = AtomBatch(b.atoms.copy(), b.n_atoms, b.TAtom)
+    shifted.atoms["timestamp"] += 86400 * 365
+    ws = TransientWindowRange(w.type, w.t0 + 86400 * 365, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau)
+    _, Fsh = run_gpu(gpu, shifted, ws, 0, btsg=False)
+    assert np.array_equal(Fsh, F)
+
+    if win == "rect":
+        rn, Fn = run_gpu(gpu, b, TransientWindowRange(0, 0, 0, 0, 0, 0, 0), 0, btsg=False)
+        assert float(Fn[0, 0, 0]) == pytest.approx(float(F[0, 0, -1]), rel=2e-5)
+
+
+def test_full_size_oracle_parity_rect_30d(gpu, oracle):
+    """30 d rect map (config 1 shape, two detectors) against the oracle at full size (the
+    oracle needs < 1 s for a rect map)."""
+    n = 1440
+    b = synth_atoms(1, n, ("H1", "L1"), seed=121)
+    w = canonical_window("rect", 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    o = oracle.compute_map(b.template(0), b.TAtom, w)
+    rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
+    assert rel.max() <= RTOL
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+    assert_records_match(res, 0, o, w)

@@ -207,6 +207,10 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
                                            TCW_RECT_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_EXP_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_BTSG_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_BTSG_SMEM));
     *out = h;
     return TCW_OK;
 }
@@ -459,6 +463,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     enum { PATH_GENERIC = 0, PATH_FAST = 1 };
     int path = PATH_GENERIC;
     int rect_R = 1;
+    uint32_t rect_DD = 32;
     bool rect_staged = false;
     ExpPlan ep;
     if (!(flags & TCW_FORCE_GENERIC) && !none_window) {
@@ -468,7 +473,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             for (int t = 0; t < T && ok; t++) ok = no_wrap(w, 1, rect_R - 1, h->meta[t], TAtom);
             if (ok) {
                 path = PATH_FAST;
-                const uint64_t span = ((uint64_t)(TCW_RECT_WARPS * rect_R - 1) * w.dt0 +
+                const uint64_t span = ((uint64_t)(TCW_RECT_WARPS * TCW_RECT_G * rect_R - 1) * w.dt0 +
                                        (uint64_t)(TCW_RECT_DT - 1) * w.dtau) / TAtom + 6;
                 rect_staged = span <= TCW_RECT_ECAP;
             }
@@ -583,14 +588,39 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);
 #undef LAUNCH_GENERIC
         } else if (w.type == TCW_WINDOW_RECT) {
-            const uint32_t n_groups = (w.N_t0 + rect_R - 1) / rect_R;
-            dim3 grid((w.N_tau + rect_R - 1 + TCW_RECT_DT - 1) / TCW_RECT_DT,
-                      (n_groups + TCW_RECT_WARPS - 1) / TCW_RECT_WARPS, cnt);
+            const uint32_t rows_per_tile = TCW_RECT_WARPS * TCW_RECT_G * rect_R;
+            const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
+            // width DD of the head strip: the smallest multiple of 32 such that every tile
+            // starting at d = DD is off-diagonal (split point inside all its windows, see
+            // tcw_rect.cuh); the device re-checks per tile, so this only affects speed
+            if (sb == 0) {
+                rect_DD = 32;
+                const TplMeta &mt0 = h->meta[0];
+                for (uint32_t cand = 32; rect_staged && cand <= TCW_RECT_DT; cand += 32) {
+                    bool all_off = true;
+                    for (uint32_t gy = 0; gy < n_gy && all_off; gy++) {
+                        const uint32_t m0 = gy * rows_per_tile;
+                        const uint32_t m_last = std::min(m0 + rows_per_tile, w.N_t0) - 1;
+                        const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + cand * w.dtau, mt0.t0_data,
+                                                       mt0.numAtoms, g);
+                        const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, mt0.t0_data, mt0.numAtoms, g);
+                        all_off = ((e_lo + 1) & ~1u) >= s_hi + 2;
+                    }
+                    if (all_off) {
+                        rect_DD = cand;
+                        break;
+                    }
+                }
+            }
+            const uint32_t DD = rect_DD;
+            const uint32_t d_total = w.N_tau + rect_R - 1;
+            const uint32_t n_reg = d_total > DD ? (d_total - DD + TCW_RECT_DT - 1) / TCW_RECT_DT : 0;
+            dim3 grid(1 + n_reg, n_gy, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
 #define LAUNCH_RECT(RR, STG)                                                                        \
     tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                             \
-        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, fmn,         \
+        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, fmn,     \
         (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
             if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);
             else if (rect_R == 4) LAUNCH_RECT(4, false);
@@ -613,11 +643,11 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
                       cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the lnBtSG pass");
             if (exact)
-                tcw_btsg_kernel<true><<<grid, TCW_BTSG_THREADS, 0, st>>>(
+                tcw_btsg_kernel<true><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(
                     fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
                     (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
             else
-                tcw_btsg_kernel<false><<<grid, TCW_BTSG_THREADS, 0, st>>>(
+                tcw_btsg_kernel<false><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(
                     fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
                     (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
             h->launches++;

@@ -18,15 +18,35 @@
 #include "tcw_generic.cuh"
 
 #define TCW_BTSG_THREADS 256
-#define TCW_BTSG_ROWS 64
-#define TCW_BTSG_COLS 256
+#define TCW_BTSG_WARPS (TCW_BTSG_THREADS / 32)
+#define TCW_BTSG_RPW 8  // rows per warp
+#define TCW_BTSG_ROWS (TCW_BTSG_WARPS * TCW_BTSG_RPW)
+#define TCW_BTSG_CPL 8  // columns per lane
+#define TCW_BTSG_COLS (32 * TCW_BTSG_CPL)
+#define TCW_BTSG_SMEM ((TCW_LUT_LEN + 2) * 8 + TCW_BTSG_WARPS * TCW_BTSG_COLS * 8 + TCW_BTSG_WARPS * TCW_BTSG_RPW * 32 * 8)
 
+// e^{-(maxF - F)}: XLALFastNegExp emulation from a shared-memory copy of the table, or exact
+template <bool EXACT_EXP>
+__device__ __forceinline__ double btsg_term(double maxF, float F, const double *__restrict__ slut) {
+    const double dF = maxF - (double)F;  // >= 0
+    if (EXACT_EXP) return exp(-dF);
+    // LUT[(UINT4)(dF*100 + 0.5)], 0 beyond 20 (also catches NaN-free huge values)
+    const uint32_t i0 = __double2uint_rz(__dadd_rn(__dmul_rn(dF, (double)TCW_LUT_LEN / TCW_LUT_XMAX), 0.5));
+    return dF > TCW_LUT_XMAX ? 0.0 : slut[min(i0, (uint32_t)TCW_LUT_LEN)];
+}
+
+// CTA tile: 64 rows x 256 columns; a warp owns 8 rows, a lane 8 columns (stride 32, coalesced
+// row reads).  Column partials stay in registers over the warp's rows, row partials are
+// combined through shared memory; one FP64 atomicAdd per row / column per CTA.
 template <bool EXACT_EXP>
 __global__ void __launch_bounds__(TCW_BTSG_THREADS)
 tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32_t N_tau,
                 const unsigned long long *__restrict__ maxkey, const double *__restrict__ lut,
                 double *__restrict__ rowsum, double *__restrict__ colsum) {
-    __shared__ double scol[TCW_BTSG_THREADS / 32][TCW_BTSG_COLS];
+    extern __shared__ __align__(16) unsigned char tcw_btsg_smem[];
+    double *slut = reinterpret_cast<double *>(tcw_btsg_smem);               // [LUT_LEN + 2]
+    double *scol = slut + (TCW_LUT_LEN + 2);                                // [WARPS][COLS]
+    double *srow = scol + TCW_BTSG_WARPS * TCW_BTSG_COLS;                   // [WARPS][RPW][32]
     const int tz = blockIdx.z;
     const int t = t_base + tz;
     const unsigned long long key = maxkey[t];
@@ -34,39 +54,70 @@ tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32
     const size_t cells = (size_t)N_t0 * N_tau;
     const float *Ft = Fmn + (size_t)tz * cells;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t m0 = blockIdx.y * TCW_BTSG_ROWS, n0 = blockIdx.x * TCW_BTSG_COLS;
+    const uint32_t m0 = blockIdx.y * TCW_BTSG_ROWS + warp * TCW_BTSG_RPW, n0 = blockIdx.x * TCW_BTSG_COLS;
+    if (!EXACT_EXP) {
+        for (int i = threadIdx.x; i <= TCW_LUT_LEN; i += TCW_BTSG_THREADS) slut[i] = __ldg(lut + i);
+        __syncthreads();
+    }
 
-    double colacc[TCW_BTSG_COLS / 32];
+    double colacc[TCW_BTSG_CPL];
 #pragma unroll
-    for (int j = 0; j < TCW_BTSG_COLS / 32; j++) colacc[j] = 0.0;
-
-    for (int i = 0; i < TCW_BTSG_ROWS / (TCW_BTSG_THREADS / 32); i++) {
-        const uint32_t m = m0 + warp + i * (TCW_BTSG_THREADS / 32);
-        if (m >= N_t0) break;
-        double rowacc = 0.0;
+    for (int j = 0; j < TCW_BTSG_CPL; j++) colacc[j] = 0.0;
+    const bool full = (m0 + TCW_BTSG_RPW <= N_t0) && (n0 + TCW_BTSG_COLS <= N_tau);
+    if (full) {
+        const float *p = Ft + (size_t)m0 * N_tau + n0 + lane;
+#pragma unroll(EXACT_EXP ? 1 : 4)
+        for (int i = 0; i < TCW_BTSG_RPW; i++) {
+            float f[TCW_BTSG_CPL];
 #pragma unroll
-        for (int j = 0; j < TCW_BTSG_COLS / 32; j++) {
-            const uint32_t n = n0 + lane + 32 * j;
-            if (n < N_tau) {
-                const double dF = maxF - (double)__ldg(Ft + (size_t)m * N_tau + n);  // >= 0
-                const double e = EXACT_EXP ? exp(-dF) : fast_neg_exp_lut(dF, lut);
-                rowacc += e;
+            for (int j = 0; j < TCW_BTSG_CPL; j++) f[j] = __ldg(p + (size_t)i * N_tau + 32 * j);
+            double ra = 0.0;
+#pragma unroll
+            for (int j = 0; j < TCW_BTSG_CPL; j++) {
+                const double e = btsg_term<EXACT_EXP>(maxF, f[j], slut);
+                ra += e;
                 colacc[j] += e;
             }
+            srow[(warp * TCW_BTSG_RPW + i) * 32 + lane] = ra;
         }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < TCW_BTSG_RPW; i++) {
+            double ra = 0.0;
+            const uint32_t m = m0 + i;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rowacc += __shfl_xor_sync(0xffffffffu, rowacc, o);
-        if (lane == 0) atomicAdd(&rowsum[(size_t)t * N_t0 + m], rowacc);
+            for (int j = 0; j < TCW_BTSG_CPL; j++) {
+                const uint32_t n = n0 + lane + 32 * j;
+                if (m < N_t0 && n < N_tau) {
+                    const double e = btsg_term<EXACT_EXP>(maxF, __ldg(Ft + (size_t)m * N_tau + n), slut);
+                    ra += e;
+                    colacc[j] += e;
+                }
+            }
+            srow[(warp * TCW_BTSG_RPW + i) * 32 + lane] = ra;
+        }
     }
+    // row partials: [warp][row][lane] -> 4 lanes per row sum 8 entries each, 2 shuffles, 1 atomic
 #pragma unroll
-    for (int j = 0; j < TCW_BTSG_COLS / 32; j++) scol[warp][lane + 32 * j] = colacc[j];
+    for (int j = 0; j < TCW_BTSG_CPL; j++) scol[warp * TCW_BTSG_COLS + lane + 32 * j] = colacc[j];
     __syncthreads();
+    {
+        const int r = lane >> 2, q = lane & 3;
+        const double *src = srow + (warp * TCW_BTSG_RPW + r) * 32 + q * 8;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += src[k];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const uint32_t m = m0 + r;
+        if (q == 0 && m < N_t0) atomicAdd(&rowsum[(size_t)t * N_t0 + m], s);
+    }
     {
         const uint32_t n = n0 + threadIdx.x;
         if (n < N_tau) {
             double s = 0.0;
 #pragma unroll
-            for (int wv = 0; wv < TCW_BTSG_THREADS / 32; wv++) s += scol[wv][threadIdx.x];
+            for (int wv = 0; wv < TCW_BTSG_WARPS; wv++) s += scol[wv * TCW_BTSG_COLS + threadIdx.x];
             atomicAdd(&colsum[(size_t)t * N_tau + n], s);
         }
     }

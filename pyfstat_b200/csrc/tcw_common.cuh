@@ -202,25 +202,25 @@ __device__ __forceinline__ float fstat_faithful(float Ad, float Bd, float Cd, fl
 }
 
 // fstat_fast: the same guarded formula in pure FP32 for the tiled kernels, without sqrt or
-// division in the conditioning test:
-//   cond = (s + d)/(s - d) < 1e4,  d = sqrt(diff^2 + 4 C^2) >= 0,  s - d > 0
-//     <=>  s > 0  and  d < s (1e4-1)/(1e4+1)   <=>  s > 0  and  d^2 < (s k)^2
-// and DdInv = 1/(AB - C^2) via one MUFU.RCP (1 ulp).  Differences to the faithful form are
-// O(ulp) and only matter for cells sitting exactly on the cond = 1e4 boundary (listed
-// separately by the parity tests).  ~27 FP32 instructions per cell.
+// division in the conditioning test.  With s = A+B, d = sqrt((A-B)^2 + 4C^2), det = AB - C^2:
+//   s^2 - d^2 = 4 det,   cond = (s+d)/(s-d) < 1e4  <=>  d < k s,  k = (1e4-1)/(1e4+1)   (s > 0)
+//                                                   <=>  det > kappa s^2,  kappa = (1-k^2)/4
+// which also implies the reference's DdInv > 0 guard.  DdInv comes from one MUFU.RCP (1 ulp).
+// Near the cut both this test and the reference's (s - d suffers the same cancellation) are
+// fuzzy at the few-1e-4 level in cond; cells flipping across it are listed by the parity
+// tests.  ~20 FP32 instructions per cell.
 __device__ __forceinline__ float fstat_fast(float Ad, float Bd, float Cd, float Fa_re, float Fa_im,
                                             float Fb_re, float Fb_im) {
+    constexpr float kK = 9999.0f / 10001.0f;
+    constexpr float kKappa = (1.0f - kK * kK) * 0.25f;
     const float sumAB = Ad + Bd;
-    const float diffAB = Ad - Bd;
-    const float c2 = Cd * Cd;
-    const float disc2 = fmaf(diffAB, diffAB, 4.0f * c2);
-    const float sk = sumAB * (9999.0f / 10001.0f);
-    const float det = fmaf(Ad, Bd, -c2);
-    const bool ok = (sumAB > 0.0f) && (disc2 < sk * sk) && (det > 0.0f);
+    const float det = fmaf(Ad, Bd, -(Cd * Cd));
+    const float margin = fmaf(sumAB * (-kKappa), sumAB, det);  // det - kappa s^2
+    const bool ok = (sumAB > 0.0f) && (margin > 0.0f);
     const float fa2 = fmaf(Fa_re, Fa_re, Fa_im * Fa_im);
     const float fb2 = fmaf(Fb_re, Fb_re, Fb_im * Fb_im);
     const float re = fmaf(Fa_re, Fb_re, Fa_im * Fb_im);
-    const float num = fmaf(Bd, fa2, fmaf(Ad, fb2, (-2.0f * Cd) * re));
+    const float num = fmaf(Bd, fa2, fmaf(Cd * re, -2.0f, Ad * fb2));
     float rdet;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdet) : "f"(det));
     return ok ? num * rdet : 2.0f;

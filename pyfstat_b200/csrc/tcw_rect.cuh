@@ -4,82 +4,84 @@
 // over tau with float32 running sums, uncoalesced stores).  Here every (t0,tau) cell is an
 // O(1) difference of FP64 prefix sums,
 //     S_c[m,n] = P_c[i_t1(m,n)+1] - P_c[i_t0(m)],
-// the 7 differences are rounded to FP32 once and go through the guarded F-stat formula.
+// which goes through the guarded F-stat formula in FP32.
 //
 // Work decomposition ("skewed" tiles).  With dt0 == dtau (the canonical grids of the
 // reference's tests/examples) the cells (m, n) and (m+1, n-1) share the window END time
 // t1 = t0_m + tau_n, hence the same end index.  A thread therefore owns a group of R
-// consecutive rows and walks d = n + r: one end-prefix fetch (7 x FP64 from shared memory)
-// feeds R cells, and each row's start prefix lives in registers.  R = 1 is the plain mapping
-// for dt0 != dtau.  A warp's lanes cover 32 consecutive d, so F_mn stores are coalesced rows
-// (the reference kernel stores with stride N_tau).
+// consecutive rows and walks d = n + r: one end-prefix fetch from shared memory feeds R
+// cells, and each row's start prefix lives in registers.  R = 1 is the plain mapping for
+// dt0 != dtau.  A warp's lanes cover 32 consecutive d, so F_mn stores are coalesced rows (the
+// reference kernel stores with stride N_tau).
 //
 // Staging.  A tile's end indices form one contiguous range (monotone under the host-side
-// no-wrap certificate); that slice of the 7 prefix channels is brought into shared memory
-// with 1-D TMA bulk copies (cp.async.bulk + mbarrier -> SASS UBLKCP) while the CTA computes
-// the tile's end-index table (exact uint32 formulas, once per distinct end time instead of
-// once per cell).  STAGED = false reads the prefixes straight from global/L2 (very coarse
-// dtau, where a tile's range would not fit).
+// no-wrap certificate); that slice of the 7 FP64 prefix channels is brought into shared
+// memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier -> SASS UBLKCP) while the CTA
+// computes the tile's end-index table (exact uint32 formulas, once per distinct end time
+// instead of once per cell).
+//
+// Precision modes (measured: FP64->FP32 conversions issue on the XU pipe at 16/clk/SM, so 7
+// conversions per cell cap the kernel at ~2 cells/clk/SM):
+//   * off-diagonal tiles -- every window of the tile contains the tile's first staged end
+//     index rho -- split the difference at rho:
+//         S = fl32(P[e+1] - P[rho])  +  fl32(P[rho] - P[s])
+//     The first term is tabulated once per tile (FP64 subtract + convert, ~0.25 per cell), the
+//     second lives in registers per row, so a cell costs ONE FADD per channel.  Both terms are
+//     sub-window sums of the cell's own window: for a2, b2 they are non-negative (no
+//     cancellation), for the signed channels the error is that of a two-term float32
+//     summation -- tighter than the reference's sequential float32 running sums.
+//   * tiles touching the diagonal (short windows, where a common split point does not
+//     exist) keep the FP64 difference + conversion per cell.  The launch gives the diagonal
+//     its own narrow strip of d (host-chosen width DD), ~1 % of the cells, processed one
+//     row at a time to keep the kernel's register footprint at 3 CTAs/SM.
 //
 // Fused epilogue: per-row running (max F, first d), combined per CTA and published with one
 // 64-bit atomicMax per CTA; F_mn is stored only if the caller (or the lnBtSG pass) needs it.
-// Interior tiles (no map edge, no diagonal) run a branch-free body.
+// Tiles without a map edge run a branch-free body.
 #pragma once
 #include "tcw_common.cuh"
 #include "tcw_prep.cuh"
 
 #define TCW_RECT_THREADS 256
 #define TCW_RECT_WARPS (TCW_RECT_THREADS / 32)
-#define TCW_RECT_DT 512     // d values per tile (16 per lane)
-#define TCW_RECT_ECAP 1024  // staged end-prefix entries per channel (even)
-#define TCW_RECT_UCAP (TCW_RECT_DT + 32)  // end-index table entries (R*WARPS <= 32)
-#define TCW_RECT_SMEM (TCW_NCH * TCW_RECT_ECAP * 8 + TCW_RECT_UCAP * 4)
+#define TCW_RECT_DT 512    // d values per regular tile (16 per lane)
+#define TCW_RECT_ECAP 640  // staged end-prefix entries per channel (even)
+#define TCW_RECT_G 2       // row groups per warp (a tile has 8 warps x G groups x R rows)
+#define TCW_RECT_ROWS(R) (TCW_RECT_WARPS * TCW_RECT_G * (R))
+#define TCW_RECT_UCAP (TCW_RECT_DT + 64)  // end-index table entries (rows per tile <= 64)
+#define TCW_RECT_SMEM_P (TCW_NCH * TCW_RECT_ECAP * 8)
+#define TCW_RECT_SMEM_Q (TCW_NCH * TCW_RECT_ECAP * 4)
+#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q + TCW_RECT_UCAP * 4)
 
-// One warp's share of a tile: R rows x DT values of d.
-//   CHECKED = false: interior tile, every (row, d) is a valid cell and none is degenerate.
-template <int R, bool STAGED, bool CHECKED, bool STORE>
-__device__ __forceinline__ void rect_tile_rows(
-    const double *__restrict__ sP, const uint32_t *__restrict__ sE, const double *__restrict__ Pt,
-    uint32_t ppad, const double (&Ps)[R][TCW_NCH], const uint32_t (&s_idx)[R], float *const (&rowp)[R],
-    const bool (&rowok)[R], uint32_t u_off, uint32_t d0, uint32_t lane, uint32_t N_tau, uint32_t d_total,
-    uint32_t t1_lane, uint32_t t1_step, uint32_t a0, uint32_t t0_data, uint32_t numAtoms, const IndexGeom g,
-    float (&best)[R], uint32_t (&best_d)[R], bool &degenerate) {
+// Fast body of one warp: R rows x (32 * n_j) values of d, split-point FP32 sums.
+//   CHECKED = false: every (row, d) is a valid cell (off-diagonal tiles have no degenerate cell).
+template <int R, bool CHECKED, bool STORE>
+__device__ __forceinline__ void rect_rows_fp32(
+    const float *__restrict__ sQ, const uint32_t *__restrict__ sE, const float (&Rs)[R][TCW_NCH],
+    float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int n_j, uint32_t lane,
+    uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0, uint32_t t0_data,
+    uint32_t numAtoms, const IndexGeom g, float (&best)[R], uint32_t (&best_d)[R]) {
 #pragma unroll 4
-    for (int j = 0; j < TCW_RECT_DT / 32; j++) {
+    for (int j = 0; j < n_j; j++) {
         const uint32_t d = d0 + lane + 32u * j;
         if (CHECKED && d >= d_total) break;
-        uint32_t idx;  // index of P[e+1] relative to the staged slice (or absolute if !STAGED)
+        uint32_t idx;  // index of P[e+1] relative to the staged slice
         if (R > 1) {
             idx = sE[u_off + lane + 32u * j];
         } else {
-            const uint32_t e = index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g);
-            idx = e + 1 - a0;
+            idx = min(index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1 - a0,
+                      (uint32_t)(TCW_RECT_ECAP - 1));
         }
-        double E[TCW_NCH];
-        if (STAGED) {
+        float Q[TCW_NCH];
 #pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) E[c] = sP[c * TCW_RECT_ECAP + idx];
-        } else {
-#pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) E[c] = __ldg(Pt + (size_t)c * ppad + idx + a0);
-        }
+        for (int c = 0; c < TCW_NCH; c++) Q[c] = sQ[c * TCW_RECT_ECAP + idx];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            float S[TCW_NCH];
-#pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) S[c] = (float)(E[c] - Ps[r][c]);
-            const float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
-            if (CHECKED) {
-                const uint32_t n = d - r;  // wraps for d < r -> fails the n < N_tau test
-                if (rowok[r] && n < N_tau) {
-                    if (STORE) rowp[r][32 * j] = F;
-                    if (F > best[r]) {
-                        best[r] = F;
-                        best_d[r] = d;
-                    }
-                    if (idx + a0 - 1 == s_idx[r]) degenerate = true;  // i_t1 == i_t0
-                }
-            } else {
+            const float F = fstat_fast(Q[0] + Rs[r][0], Q[1] + Rs[r][1], Q[2] + Rs[r][2], Q[3] + Rs[r][3],
+                                       Q[4] + Rs[r][4], Q[5] + Rs[r][5], Q[6] + Rs[r][6]);
+            bool valid = true;
+            if (CHECKED) valid = rowok[r] && (d - r) < N_tau;  // d - r wraps for d < r
+            if (valid) {
                 if (STORE) rowp[r][32 * j] = F;
                 if (F > best[r]) {
                     best[r] = F;
@@ -90,14 +92,63 @@ __device__ __forceinline__ void rect_tile_rows(
     }
 }
 
+// Precise body (tiles touching the diagonal, or unstaged): FP64 difference per cell, ONE row
+// per call (its start prefix in registers), every cell bounds- and degeneracy-checked.  Scalar
+// in/out on purpose: the hot path's per-row state must stay in registers.
+struct RectRowResult {
+    float best;
+    uint32_t best_d;
+    uint32_t degenerate;
+};
+template <int R, bool STAGED, bool STORE>
+__device__ __noinline__ RectRowResult rect_row_fp64(
+    const double *__restrict__ sP, const uint32_t *__restrict__ sE, const double *__restrict__ Pt, uint32_t ppad,
+    uint32_t s_row, float *rowp, uint32_t r, uint32_t u_off, uint32_t d0, int n_j, uint32_t lane, uint32_t N_tau,
+    uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0, uint32_t t0_data, uint32_t numAtoms,
+    const IndexGeom g) {
+    RectRowResult out;
+    out.best = -1.0f;
+    out.best_d = r;
+    out.degenerate = 0;
+    double Ps[TCW_NCH];
+#pragma unroll
+    for (int c = 0; c < TCW_NCH; c++) Ps[c] = __ldg(Pt + (size_t)c * ppad + s_row);
+#pragma unroll 1
+    for (int j = 0; j < n_j; j++) {
+        const uint32_t d = d0 + lane + 32u * j;
+        if (d >= d_total) break;
+        if (d - r >= N_tau) continue;  // wraps for d < r
+        uint32_t e1;  // absolute index e + 1
+        if (R > 1) e1 = sE[u_off + lane + 32u * j] + a0;
+        else e1 = index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1;
+        float S[TCW_NCH];
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++) {
+            const double E = STAGED ? sP[c * TCW_RECT_ECAP + (e1 - a0)] : __ldg(Pt + (size_t)c * ppad + e1);
+            S[c] = (float)(E - Ps[c]);
+        }
+        const float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+        if (STORE) rowp[32 * j] = F;
+        if (F > out.best) {
+            out.best = F;
+            out.best_d = d;
+        }
+        if (e1 - 1 == s_row) out.degenerate = 1;  // i_t1 == i_t0
+    }
+    return out;
+}
+
+// grid: x = d tiles: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT)
+//       y = tiles of 8 warps x G row groups, z = template in sub-batch
 template <int R, bool STAGED>
-__global__ void __launch_bounds__(TCW_RECT_THREADS, 2)
+__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
 tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
-                    int t_base, MapWindow w, IndexGeom g, float *__restrict__ Fmn,
+                    int t_base, MapWindow w, IndexGeom g, uint32_t DD, float *__restrict__ Fmn,
                     unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
-    double *sP = reinterpret_cast<double *>(tcw_rect_smem);                                  // [7][ECAP]
-    uint32_t *sE = reinterpret_cast<uint32_t *>(tcw_rect_smem + TCW_NCH * TCW_RECT_ECAP * 8);  // [UCAP]
+    double *sP = reinterpret_cast<double *>(tcw_rect_smem);                                    // [7][ECAP]
+    float *sQ = reinterpret_cast<float *>(tcw_rect_smem + TCW_RECT_SMEM_P);                     // [7][ECAP]
+    uint32_t *sE = reinterpret_cast<uint32_t *>(tcw_rect_smem + TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q);  // [UCAP]
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long red[TCW_RECT_WARPS];
 
@@ -108,20 +159,24 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const double *Pt = P + (size_t)t * TCW_NCH * ppad;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    const uint32_t n_groups = (w.N_t0 + R - 1) / R;
+    constexpr uint32_t ROWS = TCW_RECT_ROWS(R);  // rows per tile
     const uint32_t d_total = w.N_tau + R - 1;
-    const uint32_t g0 = blockIdx.y * TCW_RECT_WARPS;
-    const uint32_t d0 = blockIdx.x * TCW_RECT_DT;
-    const uint32_t g_last = min(g0 + TCW_RECT_WARPS, n_groups) - 1;
-    const uint32_t d_last = min(d0 + TCW_RECT_DT, d_total) - 1;
+    const uint32_t m0 = blockIdx.y * ROWS;
+    const uint32_t m_last = min(m0 + ROWS, w.N_t0) - 1;
+    const uint32_t d0 = blockIdx.x == 0 ? 0u : DD + (blockIdx.x - 1) * TCW_RECT_DT;
+    const uint32_t d_cnt = blockIdx.x == 0 ? DD : (uint32_t)TCW_RECT_DT;
+    const uint32_t d_last = min(d0 + d_cnt, d_total) - 1;
+    const bool edge = (d0 < (uint32_t)(R - 1)) || (d0 + d_cnt > w.N_tau) || (m0 + ROWS > w.N_t0);
 
-    // end time of (group, d): rows of a group differ by dt0 == dtau, absorbed into d
-    const uint32_t t1_tile = w.t0 + w.tau + g0 * R * w.dt0 + d0 * w.dtau;
+    // end time of (row group, d): rows of a group differ by dt0 == dtau (R > 1), absorbed into d
+    const uint32_t t1_tile = w.t0 + w.tau + m0 * w.dt0 + d0 * w.dtau;
     const uint32_t e_lo = index_t1(t1_tile, t0_data, numAtoms, g);
     const uint32_t a0 = STAGED ? ((e_lo + 1) & ~1u) : 0u;
+    uint32_t cnt = 0;
     if (STAGED) {
-        const uint32_t e_hi = index_t1(w.t0 + w.tau + g_last * R * w.dt0 + d_last * w.dtau, t0_data, numAtoms, g);
-        const uint32_t cnt = (e_hi + 1 - a0 + 1 + 1) & ~1u;  // even count, <= ECAP (host-checked)
+        const uint32_t e_hi = index_t1(t1_tile + ((m_last - m0) / R * R) * w.dt0 + (d_last - d0) * w.dtau, t0_data,
+                                       numAtoms, g);
+        cnt = min((e_hi + 1 - a0 + 1 + 1) & ~1u, (uint32_t)TCW_RECT_ECAP);  // even; <= ECAP by the host check
         if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             mbar_fence_init();
@@ -131,80 +186,105 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
                 bulk_g2s(sP + c * TCW_RECT_ECAP, Pt + (size_t)c * ppad + a0, cnt * (uint32_t)sizeof(double), &bar);
         }
     }
-    // end-index table over u = (grp - g0)*R + (d - d0): t1 = t1_tile + u*dtau  (dt0 == dtau)
+    // end-index table over u = (row - m0)/R*R + (d - d0): t1 = t1_tile + u*dtau  (dt0 == dtau)
     if (R > 1) {
-        for (uint32_t u = threadIdx.x; u < TCW_RECT_UCAP; u += TCW_RECT_THREADS)
+        const uint32_t u_cnt = min((uint32_t)TCW_RECT_UCAP, ROWS + d_cnt);
+        for (uint32_t u = threadIdx.x; u < u_cnt; u += TCW_RECT_THREADS)
             sE[u] = STAGED ? min(index_t1(t1_tile + u * w.dtau, t0_data, numAtoms, g) + 1 - a0,
                                  (uint32_t)(TCW_RECT_ECAP - 1))  // overhang entries stay in bounds
                            : index_t1(t1_tile + u * w.dtau, t0_data, numAtoms, g) + 1;
     }
-    const uint32_t m_hi = min((g_last + 1) * R, w.N_t0) - 1;
-    const uint32_t s_hi = index_t0(w.t0 + m_hi * w.dt0, t0_data, numAtoms, g);
-    // degenerate (single-atom) cells can only occur in tiles touching the diagonal
-    const bool interior = (e_lo > s_hi) && (d0 >= (uint32_t)(R - 1)) && (d0 + TCW_RECT_DT <= w.N_tau) &&
-                          ((g0 + TCW_RECT_WARPS) * R <= w.N_t0);
-
-    // this warp's row group: start prefixes in registers
-    const uint32_t grp = g0 + warp;
+    const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, t0_data, numAtoms, g);
+    // off-diagonal: the split point rho = a0 lies strictly inside every window of the tile,
+    // s < rho <= e + 1 with e > s (so no cell of the tile is degenerate): rho >= s_hi + 2
+    const bool offdiag = STAGED && (a0 >= s_hi + 2);
     const size_t cells = (size_t)w.N_t0 * w.N_tau;
     float *Ft = Fmn ? Fmn + (size_t)tz * cells : nullptr;
-    double Ps[R][TCW_NCH];
-    uint32_t s_idx[R];
-    float best[R];
-    uint32_t best_d[R];
-    float *rowp[R];
-    bool rowok[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const uint32_t m = grp * R + r;
-        best[r] = -1.0f;  // maxF starts at -1, strict > (tcw:135-139)
-        best_d[r] = r;
-        rowok[r] = m < w.N_t0;
-        const uint32_t mc = rowok[r] ? m : 0u;
-        s_idx[r] = index_t0(w.t0 + mc * w.dt0, t0_data, numAtoms, g);
-#pragma unroll
-        for (int c = 0; c < TCW_NCH; c++) Ps[r][c] = __ldg(Pt + (size_t)c * ppad + s_idx[r]);
-        // cell (m, n = d - r) with d = d0 + lane + 32 j  ->  rowp[r][32 j]
-        rowp[r] = Ft ? Ft + ((size_t)mc * w.N_tau + d0 + lane) - r : nullptr;
-    }
+
     __syncthreads();  // sE visible; mbarrier init visible to all waiters
     if (STAGED) mbar_wait(&bar, 0);
+    if (offdiag) {
+        // tabulate fl32(P[i] - P[rho]) for the staged slice (all 7 channels of an entry per thread)
+        double pref[TCW_NCH];
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++) pref[c] = sP[c * TCW_RECT_ECAP];
+        for (uint32_t i = threadIdx.x; i < cnt; i += TCW_RECT_THREADS) {
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++)
+                sQ[c * TCW_RECT_ECAP + i] = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]);
+        }
+        __syncthreads();
+    }
 
-    bool degenerate = false;
-    const uint32_t u_off = warp * R;
-    const uint32_t t1_lane = t1_tile + (warp * R * w.dt0) + lane * w.dtau;  // used by R == 1 only
     const uint32_t t1_step = 32u * w.dtau;
-    if (grp < n_groups) {
-        if (interior) {
-            if (Ft)
-                rect_tile_rows<R, STAGED, false, true>(sP, sE, Pt, ppad, Ps, s_idx, rowp, rowok, u_off, d0, lane,
-                                                       w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms,
-                                                       g, best, best_d, degenerate);
-            else
-                rect_tile_rows<R, STAGED, false, false>(sP, sE, Pt, ppad, Ps, s_idx, rowp, rowok, u_off, d0, lane,
-                                                        w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms,
-                                                        g, best, best_d, degenerate);
+    const int n_j = (int)(d_cnt / 32);
+    unsigned long long key = 0ull;
+    uint32_t degenerate = 0;
+    // each warp walks TCW_RECT_G row groups of R rows: the tile's staging cost is shared
+#pragma unroll 1
+    for (uint32_t gi = 0; gi < TCW_RECT_G; gi++) {
+        const uint32_t grow = (gi * TCW_RECT_WARPS + warp) * R;  // first row of the group, relative to m0
+        if (m0 + grow >= w.N_t0) break;
+        const uint32_t u_off = grow;
+        const uint32_t t1_lane = t1_tile + grow * w.dt0 + lane * w.dtau;  // used by R == 1 only
+        uint32_t s_idx[R];
+        float best[R];
+        uint32_t best_d[R];
+        float *rowp[R];
+        bool rowok[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t m = m0 + grow + r;
+            best[r] = -1.0f;  // maxF starts at -1, strict > (tcw:135-139)
+            best_d[r] = r;
+            rowok[r] = m < w.N_t0;
+            const uint32_t mc = rowok[r] ? m : 0u;
+            s_idx[r] = index_t0(w.t0 + mc * w.dt0, t0_data, numAtoms, g);
+            // cell (m, n = d - r) with d = d0 + lane + 32 j  ->  rowp[r][32 j]
+            rowp[r] = Ft ? Ft + ((size_t)mc * w.N_tau + d0 + lane) - r : nullptr;
+        }
+        if (offdiag) {
+            float Rs[R][TCW_NCH];  // fl32(P[rho] - P[s]) per row
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) {
+                const double pref = sP[c * TCW_RECT_ECAP];
+#pragma unroll
+                for (int r = 0; r < R; r++) Rs[r][c] = (float)(pref - __ldg(Pt + (size_t)c * ppad + s_idx[r]));
+            }
+#define RECT_FAST(CHK_, STORE_)                                                                            \
+    rect_rows_fp32<R, CHK_, STORE_>(sQ, sE, Rs, rowp, rowok, u_off, d0, n_j, lane, w.N_tau, d_total, t1_lane, \
+                                    t1_step, a0, t0_data, numAtoms, g, best, best_d)
+            if (edge) {
+                if (Ft) RECT_FAST(true, true);
+                else RECT_FAST(true, false);
+            } else {
+                if (Ft) RECT_FAST(false, true);
+                else RECT_FAST(false, false);
+            }
+#undef RECT_FAST
         } else {
-            if (Ft)
-                rect_tile_rows<R, STAGED, true, true>(sP, sE, Pt, ppad, Ps, s_idx, rowp, rowok, u_off, d0, lane,
-                                                      w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms,
-                                                      g, best, best_d, degenerate);
-            else
-                rect_tile_rows<R, STAGED, true, false>(sP, sE, Pt, ppad, Ps, s_idx, rowp, rowok, u_off, d0, lane,
-                                                       w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms,
-                                                       g, best, best_d, degenerate);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (!rowok[r]) continue;
+                const RectRowResult rr =
+                    Ft ? rect_row_fp64<R, STAGED, true>(sP, sE, Pt, ppad, s_idx[r], rowp[r], r, u_off, d0, n_j, lane,
+                                                        w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g)
+                       : rect_row_fp64<R, STAGED, false>(sP, sE, Pt, ppad, s_idx[r], rowp[r], r, u_off, d0, n_j, lane,
+                                                         w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g);
+                best[r] = rr.best;
+                best_d[r] = rr.best_d;
+                degenerate |= rr.degenerate;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (best[r] > -1.0f) {
+                const uint32_t flat = (m0 + grow + r) * w.N_tau + (best_d[r] - r);
+                const unsigned long long k = pack_key(best[r], flat);
+                key = k > key ? k : key;
+            }
         }
     }
     if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
-
-    unsigned long long key = 0ull;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        if (best[r] > -1.0f) {
-            const uint32_t flat = (grp * R + r) * w.N_tau + (best_d[r] - r);
-            const unsigned long long k = pack_key(best[r], flat);
-            key = k > key ? k : key;
-        }
-    }
     block_atomic_max_key<TCW_RECT_WARPS>(key, &maxkey[t], red);
 }

@@ -404,7 +404,7 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
 
 static size_t subbatch_bytes() {
     const char *env = getenv("TCW_SUBBATCH_MB");
-    size_t mb = env ? (size_t)atol(env) : 64;
+    size_t mb = env ? (size_t)atol(env) : 2048;
     if (mb < 1) mb = 1;
     return mb << 20;
 }
@@ -495,7 +495,10 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
         if ((rc = ensure(h, h->d_colsum, (size_t)T * w.N_tau * sizeof(double)))) return rc;
     }
     // templates per sub-batch: with lnBtSG the F_mn of a sub-batch is written by the map kernel
-    // and re-read by the BtSG pass, so keep it L2-sized; otherwise only the grid.z limit applies
+    // and re-read by the BtSG pass.  Measured (60 d rect, T=64): 64 MB sub-batches (L2-resident
+    // scratch, one template per launch) 1.8e11 cells/s, 2-4 GB sub-batches 3.0e11 cells/s --
+    // launch gaps and tails cost more than the HBM round trip, so the scratch is sized for big
+    // launches (TCW_SUBBATCH_MB, default 2048)
     int S = T;
     if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (cells * 4)));
     S = std::min(S, 32768);

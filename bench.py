@@ -278,6 +278,11 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. NCCL's version
+    # banner) goes to stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyfstat_b200 has no CPU fallback (use --impl reference "
                          "for the CPU baseline)")
@@ -411,7 +416,10 @@ def run_gpu(args):
             line["rect"] = secondary_rect(h, L, hbm_peak, hbm_src)
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_single_thread(spec)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     h.close()
     if world > 1:
         dist.barrier()

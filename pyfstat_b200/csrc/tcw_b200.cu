@@ -68,7 +68,8 @@ struct tcw_handle {
     // exp weight-table cache key
     bool w_valid = false;
     tcw_window_range w_key = {};
-    uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_i00 = 0;
+    uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_i00 = 0, w_TN = 0;
+    int exp_variant = 1;  // ExpCfgB: measured fastest (r01: A 14.70 ms, B 13.77 ms, C 13.80 ms per 32 x 30-d templates)
     int w_exact = -1;
     std::vector<int32_t> w_Kn;
 };
@@ -205,8 +206,13 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
                                            TCW_RECT_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECT_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_EXP_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ExpCfgA::kSmem));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ExpCfgB::kSmem));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ExpCfgC::kSmem));
+    if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_BTSG_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -324,7 +330,7 @@ extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint
     h->Nmax = Nmax;
     h->uniform = uniform;
     // zero padding: the exp tiles read up to TM + KC + 4 atoms past the last needed one
-    h->xpad = ((Nmax + TCW_EXP_TM + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
+    h->xpad = ((Nmax + 64 /* max exp tile rows */ + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
     h->ppad = ((Nmax + 1 + 8) + 1u) & ~1u;
     const size_t n_vec = (size_t)T * numDet;
     int rc;
@@ -368,6 +374,14 @@ struct ExpPlan {
     std::vector<int32_t> Kn;
 };
 
+static void exp_tile_dims(int variant, uint32_t *TM, uint32_t *TN) {
+    switch (variant) {
+        case 0: *TM = ExpCfgA::kTM; *TN = ExpCfgA::kTN; break;
+        case 2: *TM = ExpCfgC::kTM; *TN = ExpCfgC::kTN; break;
+        default: *TM = ExpCfgB::kTM; *TN = ExpCfgB::kTN; break;
+    }
+}
+
 static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     ExpPlan p;
     const uint32_t TAtom = h->TAtom;
@@ -394,8 +408,10 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     if (Kmax > (int64_t)h->Nmax + 64) Kmax = (int64_t)h->Nmax + 64;  // never need k beyond the data
     for (auto &K : p.Kn) K = (int32_t)std::min<int64_t>(K, Kmax);
     p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
-    const uint64_t n_tiles = (w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN;
-    if (n_tiles * p.KW * TCW_EXP_TN * 4ull > (8ull << 30)) return p;  // table too large
+    uint32_t TM, TN;
+    exp_tile_dims(h->exp_variant, &TM, &TN);
+    const uint64_t n_tiles = (w.N_tau + TN - 1) / TN;
+    if (n_tiles * p.KW * TN * 4ull > (8ull << 30)) return p;  // table too large
     p.i00 = (uint32_t)i00;
     p.delta = (int32_t)((int64_t)t0_data + i00 * TAtom - (int64_t)w.t0);
     p.ok = true;
@@ -537,13 +553,15 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
 
     // ---- stage 1: exponential-window weight table (cached across calls) ----
+    uint32_t exp_TM = 0, exp_TN = 0;
+    exp_tile_dims(h->exp_variant, &exp_TM, &exp_TN);
     if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
         const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
                          h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom &&
-                         h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn;
+                         h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
-            const uint32_t n_tiles = (w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN;
-            const size_t total = (size_t)n_tiles * ep.KW * TCW_EXP_TN;
+            const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
+            const size_t total = (size_t)n_tiles * ep.KW * exp_TN;
             if ((rc = ensure(h, h->d_W, total * sizeof(float)))) return rc;
             if ((rc = ensure(h, h->d_Kn, (size_t)w.N_tau * sizeof(int32_t)))) return rc;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -553,6 +571,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             eg.N_tau = w.N_tau;
             eg.n_tiles = n_tiles;
             eg.KW = ep.KW;
+            eg.TN = exp_TN;
             eg.tau = w.tau;
             eg.dtau = w.dtau;
             eg.TAtom = TAtom;
@@ -570,6 +589,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             h->w_exact = (int)exact;
             h->w_KW = ep.KW;
             h->w_i00 = ep.i00;
+            h->w_TN = exp_TN;
         }
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[2], st));
@@ -631,12 +651,17 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             else LAUNCH_RECT(1, false);
 #undef LAUNCH_RECT
         } else {
-            dim3 grid((w.N_tau + TCW_EXP_TN - 1) / TCW_EXP_TN, (w.N_t0 + TCW_EXP_TM - 1) / TCW_EXP_TM, cnt);
+            dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, (w.N_t0 + exp_TM - 1) / exp_TM, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
-            tcw_exp_map_kernel<<<grid, TCW_EXP_THREADS, TCW_EXP_SMEM, st>>>(
-                (const float *)h->d_X.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,
-                (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, (unsigned long long *)h->d_maxkey.p,
-                (uint32_t *)h->d_flags.p);
+#define LAUNCH_EXP(CFG)                                                                                   \
+    tcw_exp_map_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                                     \
+        (const float *)h->d_X.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,     \
+        (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, (unsigned long long *)h->d_maxkey.p,        \
+        (uint32_t *)h->d_flags.p)
+            if (h->exp_variant == 0) LAUNCH_EXP(ExpCfgA);
+            else if (h->exp_variant == 2) LAUNCH_EXP(ExpCfgC);
+            else LAUNCH_EXP(ExpCfgB);
+#undef LAUNCH_EXP
         }
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());

@@ -14,8 +14,10 @@
 //     S_c[m,n] = sum_k X_c[i_t0(m)+k] * w(k,n)^(p_c),   p_c = 2 for a2,b2,ab; 1 for Fa,Fb
 // (Exp.cu:92-100).  No exp() in the inner loop, no recurrence.
 //
-// CTA tile 64 (t0) x 64 (tau) cells, 256 threads, 4x4 cells x 7 channels = 112 FP32
-// accumulators per thread.  Per k step a thread issues 112 FFMA + 4 FMUL (w^2) for
+// Default CTA tile 32 (t0) x 64 (tau) cells, 128 threads, 3 CTAs/SM, 4x4 cells x 7 channels =
+// 112 FP32 accumulators per thread (ExpCfg below parametrises the tile; measured in round 1:
+// 64x64/256 thr 14.70 ms, 32x64/128 thr 13.77 ms, 64x32/256 thr 13.80 ms per 32 30-d templates).
+// Per k step a thread issues 112 FFMA + 4 FMUL (w^2) for
 // 7 LDS.32 + 1 LDS.128: rows of a thread are consecutive t0, so their atoms form a sliding
 // window held in registers (one new atom per channel per step), weights are shared along m.
 // Operand tiles (64 k x 64 n weights, contiguous by construction of the table; 7 x 132 atoms)
@@ -27,21 +29,31 @@
 #include "tcw_generic.cuh"
 #include "tcw_prep.cuh"
 
-#define TCW_EXP_THREADS 256
-#define TCW_EXP_TM 64
-#define TCW_EXP_TN 64
-#define TCW_EXP_RM 4
-#define TCW_EXP_RN 4
-#define TCW_EXP_KC 64
-#define TCW_EXP_XS (TCW_EXP_TM + TCW_EXP_KC + 4)  // staged atoms per channel (132)
+#define TCW_EXP_KC 64      // k-steps per staged chunk
 #define TCW_EXP_STAGES 3
-#define TCW_EXP_W_BYTES (TCW_EXP_KC * TCW_EXP_TN * 4)
-#define TCW_EXP_X_BYTES (TCW_NCH * TCW_EXP_XS * 4)
-#define TCW_EXP_STAGE_BYTES (TCW_EXP_W_BYTES + TCW_EXP_X_BYTES)
-#define TCW_EXP_SMEM (TCW_EXP_STAGES * TCW_EXP_STAGE_BYTES)
+#define TCW_EXP_TNT 16     // threads along tau per CTA (fixed); a warp = 2 (t0) x 16 (tau) threads
+
+// Tile configuration: NT threads, RM x RN cells per thread.
+//   tile = (NT/16 * RM) rows x (16 * RN) columns
+template <int NT, int RM, int RN>
+struct ExpCfg {
+    static constexpr int kThreads = NT;
+    static constexpr int kRM = RM, kRN = RN;
+    static constexpr int kTM = NT / TCW_EXP_TNT * RM;
+    static constexpr int kTN = TCW_EXP_TNT * RN;
+    static constexpr int kXS = kTM + TCW_EXP_KC + 4;  // staged atoms per channel
+    static constexpr int kWBytes = TCW_EXP_KC * kTN * 4;
+    static constexpr int kXBytes = TCW_NCH * kXS * 4;
+    static constexpr int kStageBytes = kWBytes + kXBytes;
+    static constexpr int kSmem = TCW_EXP_STAGES * kStageBytes;
+    static_assert(kXS % 4 == 0 && kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
+    static_assert(RM == 4, "the register sliding window is written for 4 rows per thread");
+    static_assert(RN == 4 || RN == 2, "weights are fetched as float4 / float2");
+};
 
 struct ExpTableGeom {
     uint32_t N_tau, n_tiles, KW;  // KW: table rows per column tile (multiple of KC)
+    uint32_t TN;                  // columns per tile
     uint32_t tau, dtau, TAtom;
     int32_t delta;  // (t0_data + i00*TAtom) - t0, in (-TAtom/2, TAtom/2]
 };
@@ -49,14 +61,14 @@ struct ExpTableGeom {
 // W[nt][k][TN]: weight of relative atom k for column n = nt*TN + j.
 __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__restrict__ Kn,
                                      ExpTableGeom eg, const double *__restrict__ lut, int exact) {
-    const size_t total = (size_t)eg.n_tiles * eg.KW * TCW_EXP_TN;
+    const size_t total = (size_t)eg.n_tiles * eg.KW * eg.TN;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(idx % TCW_EXP_TN);
-        const size_t rest = idx / TCW_EXP_TN;
+        const uint32_t j = (uint32_t)(idx % eg.TN);
+        const size_t rest = idx / eg.TN;
         const uint32_t k = (uint32_t)(rest % eg.KW);
         const uint32_t nt = (uint32_t)(rest / eg.KW);
-        const uint32_t n = nt * TCW_EXP_TN + j;
+        const uint32_t n = nt * eg.TN + j;
         float wv = 0.0f;
         if (n < eg.N_tau && (int32_t)k <= Kn[n]) {
             const uint32_t tau_n = eg.tau + n * eg.dtau;
@@ -71,40 +83,43 @@ __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__res
     }
 }
 
-__global__ void __launch_bounds__(TCW_EXP_THREADS, 1)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, (Cfg::kThreads == 256 ? (Cfg::kRN == 4 ? 1 : 2) : 3))
 tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__restrict__ W,
                    const int32_t *__restrict__ Kn, uint32_t KW, const TplMeta *__restrict__ meta,
                    int t_base, MapWindow w, uint32_t i00, float *__restrict__ Fmn,
                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+    constexpr int TM = Cfg::kTM, TN = Cfg::kTN, RM = Cfg::kRM, RN = Cfg::kRN, XS = Cfg::kXS;
+    constexpr int NT = Cfg::kThreads;
     extern __shared__ __align__(128) unsigned char tcw_exp_smem[];
     __shared__ __align__(8) uint64_t full[TCW_EXP_STAGES];
-    __shared__ unsigned long long red[TCW_EXP_THREADS / 32];
+    __shared__ unsigned long long red[NT / 32];
 
     const int tz = blockIdx.z;
     const int t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
     const uint32_t nt = blockIdx.x, mt = blockIdx.y;
-    const uint32_t m0 = mt * TCW_EXP_TM, n0 = nt * TCW_EXP_TN;
+    const uint32_t m0 = mt * TM, n0 = nt * TN;
     const uint32_t s_base = i00 + m0;  // i_t0 of the tile's first row (dt0 == TAtom)
-    const uint32_t n_last = min(n0 + TCW_EXP_TN, w.N_tau) - 1;
+    const uint32_t n_last = min(n0 + TN, w.N_tau) - 1;
     const int k_end = min(Kn[n_last] + 1, (int)numAtoms - (int)s_base);
     const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
     const uint32_t off = s_base & 3u;  // bulk copies need 16-byte aligned sources
     const float *Xt = X + (size_t)t * TCW_NCH * xpad + (s_base - off);
-    const float *Wt = W + (size_t)nt * KW * TCW_EXP_TN;
+    const float *Wt = W + (size_t)nt * KW * TN;
 
     const int tid = threadIdx.x;
     const int tm = tid >> 4, tn = tid & 15;
 
     auto issue = [&](int chunk) {
         const int s = chunk % TCW_EXP_STAGES;
-        unsigned char *st = tcw_exp_smem + (size_t)s * TCW_EXP_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], TCW_EXP_STAGE_BYTES);
-        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TCW_EXP_TN, TCW_EXP_W_BYTES, &full[s]);
+        unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++)
-            bulk_g2s(st + TCW_EXP_W_BYTES + c * TCW_EXP_XS * 4,
-                     Xt + (size_t)c * xpad + (size_t)chunk * TCW_EXP_KC, TCW_EXP_XS * 4, &full[s]);
+            bulk_g2s(st + Cfg::kWBytes + c * XS * 4, Xt + (size_t)c * xpad + (size_t)chunk * TCW_EXP_KC, XS * 4,
+                     &full[s]);
     };
 
     if (tid == 0) {
@@ -117,32 +132,32 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
         for (int c = 0; c < TCW_EXP_STAGES - 1 && c < nchunks; c++) issue(c);
     }
 
-    float acc[TCW_NCH][TCW_EXP_RM][TCW_EXP_RN];
+    float acc[TCW_NCH][RM][RN];
 #pragma unroll
     for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
-        for (int r = 0; r < TCW_EXP_RM; r++)
+        for (int r = 0; r < RM; r++)
 #pragma unroll
-            for (int j = 0; j < TCW_EXP_RN; j++) acc[c][r][j] = 0.0f;
+            for (int j = 0; j < RN; j++) acc[c][r][j] = 0.0f;
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
         // refill the stage consumed in the previous iteration (all threads passed its sync)
         if (tid == 0 && chunk + TCW_EXP_STAGES - 1 < nchunks) issue(chunk + TCW_EXP_STAGES - 1);
         const int s = chunk % TCW_EXP_STAGES;
         mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
-        const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * TCW_EXP_STAGE_BYTES);
-        const float *Xs = Ws + TCW_EXP_KC * TCW_EXP_TN;
-        const float *xrow = Xs + off + tm * TCW_EXP_RM;  // + c*XS + k + r
-        const float4 *wrow = reinterpret_cast<const float4 *>(Ws) + tn;  // + k*(TN/4)
+        const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes);
+        const float *Xs = Ws + TCW_EXP_KC * TN;
+        const float *xrow = Xs + off + tm * RM;  // + c*XS + k + r
+        const float *wrow = Ws + tn * RN;        // + k*TN
 
         // sliding window of 4 consecutive atoms per channel: value with relative index q
         // lives in slot q & 3
         float xr[TCW_NCH][4];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) {
-            xr[c][0] = xrow[c * TCW_EXP_XS + 0];
-            xr[c][1] = xrow[c * TCW_EXP_XS + 1];
-            xr[c][2] = xrow[c * TCW_EXP_XS + 2];
+            xr[c][0] = xrow[c * XS + 0];
+            xr[c][1] = xrow[c * XS + 1];
+            xr[c][2] = xrow[c * XS + 2];
         }
 #pragma unroll 1
         for (int kk = 0; kk < TCW_EXP_KC; kk += 4) {
@@ -150,19 +165,24 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
             for (int u = 0; u < 4; u++) {
                 const int k = kk + u;
 #pragma unroll
-                for (int c = 0; c < TCW_NCH; c++) xr[c][(u + 3) & 3] = xrow[c * TCW_EXP_XS + k + 3];
-                const float4 wv = wrow[k * (TCW_EXP_TN / 4)];
-                const float w1[4] = {wv.x, wv.y, wv.z, wv.w};
-                float w2[4];
+                for (int c = 0; c < TCW_NCH; c++) xr[c][(u + 3) & 3] = xrow[c * XS + k + 3];
+                float w1[RN], w2[RN];
+                if (RN == 4) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                    w1[0] = wv.x; w1[1] = wv.y; w1[RN - 2] = wv.z; w1[RN - 1] = wv.w;
+                } else {
+                    const float2 wv = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                    w1[0] = wv.x; w1[1] = wv.y;
+                }
 #pragma unroll
-                for (int j = 0; j < 4; j++) w2[j] = w1[j] * w1[j];
+                for (int j = 0; j < RN; j++) w2[j] = w1[j] * w1[j];
 #pragma unroll
                 for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
-                    for (int r = 0; r < TCW_EXP_RM; r++) {
+                    for (int r = 0; r < RM; r++) {
                         const float xv = xr[c][(u + r) & 3];
 #pragma unroll
-                        for (int j = 0; j < TCW_EXP_RN; j++)
+                        for (int j = 0; j < RN; j++)
                             acc[c][r][j] = fmaf(xv, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
                     }
             }
@@ -177,11 +197,11 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
     uint32_t best_flat = 0;
     bool degenerate = false;
 #pragma unroll
-    for (int r = 0; r < TCW_EXP_RM; r++) {
-        const uint32_t m = m0 + tm * TCW_EXP_RM + r;
+    for (int r = 0; r < RM; r++) {
+        const uint32_t m = m0 + tm * RM + r;
 #pragma unroll
-        for (int j = 0; j < TCW_EXP_RN; j++) {
-            const uint32_t n = n0 + tn * TCW_EXP_RN + j;
+        for (int j = 0; j < RN; j++) {
+            const uint32_t n = n0 + tn * RN + j;
             if (m < w.N_t0 && n < w.N_tau) {
                 const float F = fstat_fast(acc[0][r][j], acc[1][r][j], acc[2][r][j], acc[3][r][j],
                                            acc[4][r][j], acc[5][r][j], acc[6][r][j]);
@@ -199,5 +219,10 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
     }
     if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
     const unsigned long long key = best > -1.0f ? pack_key(best, best_flat) : 0ull;
-    block_atomic_max_key<TCW_EXP_THREADS / 32>(key, &maxkey[t], red);
+    block_atomic_max_key<NT / 32>(key, &maxkey[t], red);
 }
+
+// variants selectable at run time (TCW_EXP_VARIANT = 0/1/2) while tuning; B (1) is the default
+typedef ExpCfg<256, 4, 4> ExpCfgA;  // 64 x 64 tile, 1 CTA/SM
+typedef ExpCfg<128, 4, 4> ExpCfgB;  // 32 x 64 tile, 3 CTAs/SM (default)
+typedef ExpCfg<256, 4, 2> ExpCfgC;  // 64 x 32 tile, 2 CTAs/SM

@@ -198,14 +198,18 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     }
     CUDA_TRY(nullptr, cudaMemcpy(h->d_lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
     // opt in to large dynamic shared memory once
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_RECT_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_RECT_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_RECT_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_RECT_SMEM));
+#define RECT_ATTR(RR, STG, TRK)                                                                     \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<RR, STG, TRK>,                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_RECT_SMEM))
+    RECT_ATTR(4, true, true);
+    RECT_ATTR(4, true, false);
+    RECT_ATTR(4, false, true);
+    RECT_ATTR(4, false, false);
+    RECT_ATTR(1, true, true);
+    RECT_ATTR(1, true, false);
+    RECT_ATTR(1, false, true);
+    RECT_ATTR(1, false, false);
+#undef RECT_ATTR
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ExpCfgA::kSmem));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -213,9 +217,13 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ExpCfgC::kSmem));
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_BTSG_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_BTSG_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_BTSG_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_BTSG_SMEM));
     *out = h;
     return TCW_OK;
@@ -480,6 +488,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     int path = PATH_GENERIC;
     int rect_R = 1;
     uint32_t rect_DD = 32;
+    const bool rect_track = !want_btsg;  // see LAUNCH_RECT
     bool rect_staged = false;
     ExpPlan ep;
     if (!(flags & TCW_FORCE_GENERIC) && !none_window) {
@@ -641,14 +650,23 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             dim3 grid(1 + n_reg, n_gy, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
-#define LAUNCH_RECT(RR, STG)                                                                        \
-    tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                             \
+#define LAUNCH_RECT(RR, STG, TRK)                                                                   \
+    tcw_rect_map_kernel<RR, STG, TRK><<<grid, TCW_RECT_THREADS, smem, st>>>(                        \
         (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, fmn,     \
         (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
-            if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);
-            else if (rect_R == 4) LAUNCH_RECT(4, false);
-            else if (rect_staged) LAUNCH_RECT(1, true);
-            else LAUNCH_RECT(1, false);
+            // with a following lnBtSG pass the map kernel only tracks max VALUES; the pass
+            // locates the first cell attaining the final max while it re-reads F_mn anyway
+            if (rect_track) {
+                if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true, true);
+                else if (rect_R == 4) LAUNCH_RECT(4, false, true);
+                else if (rect_staged) LAUNCH_RECT(1, true, true);
+                else LAUNCH_RECT(1, false, true);
+            } else {
+                if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true, false);
+                else if (rect_R == 4) LAUNCH_RECT(4, false, false);
+                else if (rect_staged) LAUNCH_RECT(1, true, false);
+                else LAUNCH_RECT(1, false, false);
+            }
 #undef LAUNCH_RECT
         } else {
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, (w.N_t0 + exp_TM - 1) / exp_TM, cnt);
@@ -670,14 +688,16 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             dim3 grid((w.N_tau + TCW_BTSG_COLS - 1) / TCW_BTSG_COLS, (w.N_t0 + TCW_BTSG_ROWS - 1) / TCW_BTSG_ROWS,
                       cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the lnBtSG pass");
-            if (exact)
-                tcw_btsg_kernel<true><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(
-                    fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
-                    (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
-            else
-                tcw_btsg_kernel<false><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(
-                    fmn, t_base, w.N_t0, w.N_tau, (const unsigned long long *)h->d_maxkey.p,
-                    (const double *)h->d_lut.p, (double *)h->d_rowsum.p, (double *)h->d_colsum.p);
+            const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT && !rect_track;
+#define LAUNCH_BTSG(EX, LOC)                                                                          \
+    tcw_btsg_kernel<EX, LOC><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(                          \
+        fmn, t_base, w.N_t0, w.N_tau, (unsigned long long *)h->d_maxkey.p, (const double *)h->d_lut.p, \
+        (double *)h->d_rowsum.p, (double *)h->d_colsum.p)
+            if (exact && locate) LAUNCH_BTSG(true, true);
+            else if (exact) LAUNCH_BTSG(true, false);
+            else if (locate) LAUNCH_BTSG(false, true);
+            else LAUNCH_BTSG(false, false);
+#undef LAUNCH_BTSG
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
         }

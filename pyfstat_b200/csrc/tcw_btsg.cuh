@@ -38,10 +38,13 @@ __device__ __forceinline__ double btsg_term(double maxF, float F, const double *
 // CTA tile: 64 rows x 256 columns; a warp owns 8 rows, a lane 8 columns (stride 32, coalesced
 // row reads).  Column partials stay in registers over the warp's rows, row partials are
 // combined through shared memory; one FP64 atomicAdd per row / column per CTA.
-template <bool EXACT_EXP>
+//
+// LOCATE: the rect map kernel published max VALUES only (key index part 0); complete the key
+// with the smallest flat index whose F equals the max (first occurrence, np.argmax order).
+template <bool EXACT_EXP, bool LOCATE>
 __global__ void __launch_bounds__(TCW_BTSG_THREADS)
 tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32_t N_tau,
-                const unsigned long long *__restrict__ maxkey, const double *__restrict__ lut,
+                unsigned long long *__restrict__ maxkey, const double *__restrict__ lut,
                 double *__restrict__ rowsum, double *__restrict__ colsum) {
     extern __shared__ __align__(16) unsigned char tcw_btsg_smem[];
     double *slut = reinterpret_cast<double *>(tcw_btsg_smem);               // [LUT_LEN + 2]
@@ -50,7 +53,8 @@ tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32
     const int tz = blockIdx.z;
     const int t = t_base + tz;
     const unsigned long long key = maxkey[t];
-    const double maxF = key ? (double)orderable_float((uint32_t)(key >> 32)) : -1.0;
+    const float maxFf = key ? orderable_float((uint32_t)(key >> 32)) : -1.0f;
+    const double maxF = (double)maxFf;
     const size_t cells = (size_t)N_t0 * N_tau;
     const float *Ft = Fmn + (size_t)tz * cells;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,6 +81,8 @@ tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32
                 const double e = btsg_term<EXACT_EXP>(maxF, f[j], slut);
                 ra += e;
                 colacc[j] += e;
+                if (LOCATE && f[j] == maxFf)
+                    atomicMax(&maxkey[t], pack_key(f[j], (m0 + i) * N_tau + n0 + lane + 32 * j));
             }
             srow[(warp * TCW_BTSG_RPW + i) * 32 + lane] = ra;
         }
@@ -89,9 +95,11 @@ tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32
             for (int j = 0; j < TCW_BTSG_CPL; j++) {
                 const uint32_t n = n0 + lane + 32 * j;
                 if (m < N_t0 && n < N_tau) {
-                    const double e = btsg_term<EXACT_EXP>(maxF, __ldg(Ft + (size_t)m * N_tau + n), slut);
+                    const float fv = __ldg(Ft + (size_t)m * N_tau + n);
+                    const double e = btsg_term<EXACT_EXP>(maxF, fv, slut);
                     ra += e;
                     colacc[j] += e;
+                    if (LOCATE && fv == maxFf) atomicMax(&maxkey[t], pack_key(fv, m * N_tau + n));
                 }
             }
             srow[(warp * TCW_BTSG_RPW + i) * 32 + lane] = ra;

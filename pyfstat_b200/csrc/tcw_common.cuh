@@ -215,8 +215,10 @@ __device__ __forceinline__ float fstat_fast(float Ad, float Bd, float Cd, float 
     constexpr float kKappa = (1.0f - kK * kK) * 0.25f;
     const float sumAB = Ad + Bd;
     const float det = fmaf(Ad, Bd, -(Cd * Cd));
-    const float margin = fmaf(sumAB * (-kKappa), sumAB, det);  // det - kappa s^2
-    const bool ok = (sumAB > 0.0f) && (margin > 0.0f);
+    // det - kappa s^2 > 0.  (The reference also needs s > 0, which holds for any physical atoms:
+    // a2, b2 >= 0; with all-zero sums margin == 0 and the fallback is taken as in the reference.)
+    const float margin = fmaf(sumAB * (-kKappa), sumAB, det);
+    const bool ok = margin > 0.0f;
     const float fa2 = fmaf(Fa_re, Fa_re, Fa_im * Fa_im);
     const float fb2 = fmaf(Fb_re, Fb_re, Fb_im * Fb_im);
     const float re = fmaf(Fa_re, Fb_re, Fa_im * Fb_im);

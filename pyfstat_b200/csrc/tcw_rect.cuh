@@ -48,14 +48,20 @@
 #define TCW_RECT_ECAP 640  // staged end-prefix entries per channel (even)
 #define TCW_RECT_G 2       // row groups per warp (a tile has 8 warps x G groups x R rows)
 #define TCW_RECT_ROWS(R) (TCW_RECT_WARPS * TCW_RECT_G * (R))
-#define TCW_RECT_UCAP (TCW_RECT_DT + 64)  // end-index table entries (rows per tile <= 64)
+#define TCW_RECT_MAXROWS (TCW_RECT_WARPS * TCW_RECT_G * 4)
+#define TCW_RECT_UCAP (TCW_RECT_DT + TCW_RECT_MAXROWS)  // end-index table entries
 #define TCW_RECT_SMEM_P (TCW_NCH * TCW_RECT_ECAP * 8)
 #define TCW_RECT_SMEM_Q (TCW_NCH * TCW_RECT_ECAP * 4)
-#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q + TCW_RECT_UCAP * 4)
+#define TCW_RECT_SMEM_E (TCW_RECT_UCAP * 4)
+#define TCW_RECT_SMEM_S (TCW_RECT_MAXROWS * 4)
+#define TCW_RECT_SMEM_R (TCW_RECT_MAXROWS * 8 * 4)
+#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q + TCW_RECT_SMEM_E + TCW_RECT_SMEM_S + TCW_RECT_SMEM_R)
 
 // Fast body of one warp: R rows x (32 * n_j) values of d, split-point FP32 sums.
 //   CHECKED = false: every (row, d) is a valid cell (off-diagonal tiles have no degenerate cell).
-template <int R, bool CHECKED, bool STORE>
+//   TRACK   = false: only the running max value is kept (the lnBtSG pass re-reads F_mn and
+//             locates the first cell equal to the final max), saving 2 instructions per cell.
+template <int R, bool CHECKED, bool STORE, bool TRACK>
 __device__ __forceinline__ void rect_rows_fp32(
     const float *__restrict__ sQ, const uint32_t *__restrict__ sE, const float (&Rs)[R][TCW_NCH],
     float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int n_j, uint32_t lane,
@@ -83,9 +89,13 @@ __device__ __forceinline__ void rect_rows_fp32(
             if (CHECKED) valid = rowok[r] && (d - r) < N_tau;  // d - r wraps for d < r
             if (valid) {
                 if (STORE) rowp[r][32 * j] = F;
-                if (F > best[r]) {
-                    best[r] = F;
-                    best_d[r] = d;
+                if (TRACK) {
+                    if (F > best[r]) {
+                        best[r] = F;
+                        best_d[r] = d;
+                    }
+                } else {
+                    best[r] = fmaxf(best[r], F);  // NaN-safe: fmaxf returns the non-NaN operand
                 }
             }
         }
@@ -140,15 +150,24 @@ __device__ __noinline__ RectRowResult rect_row_fp64(
 
 // grid: x = d tiles: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT)
 //       y = tiles of 8 warps x G row groups, z = template in sub-batch
-template <int R, bool STAGED>
+// TRACK = false (only with a following lnBtSG pass over a stored F_mn): publish max values
+// only; tcw_btsg_kernel completes the key with the first flat index that attains the max.
+template <int R, bool STAGED, bool TRACK>
 __global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
 tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
                     int t_base, MapWindow w, IndexGeom g, uint32_t DD, float *__restrict__ Fmn,
                     unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
-    double *sP = reinterpret_cast<double *>(tcw_rect_smem);                                    // [7][ECAP]
-    float *sQ = reinterpret_cast<float *>(tcw_rect_smem + TCW_RECT_SMEM_P);                     // [7][ECAP]
-    uint32_t *sE = reinterpret_cast<uint32_t *>(tcw_rect_smem + TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q);  // [UCAP]
+    unsigned char *sp = tcw_rect_smem;
+    double *sP = reinterpret_cast<double *>(sp);        // [7][ECAP]  staged FP64 end prefixes
+    sp += TCW_RECT_SMEM_P;
+    float *sQ = reinterpret_cast<float *>(sp);          // [7][ECAP]  fl32(P[i] - P[rho])
+    sp += TCW_RECT_SMEM_Q;
+    uint32_t *sE = reinterpret_cast<uint32_t *>(sp);    // [UCAP]     end index (rel. to slice) per u
+    sp += TCW_RECT_SMEM_E;
+    uint32_t *sS = reinterpret_cast<uint32_t *>(sp);    // [ROWS]     start index i_t0 per row
+    sp += TCW_RECT_SMEM_S;
+    float *sR = reinterpret_cast<float *>(sp);          // [ROWS][8]  fl32(P[rho] - P[s]) per row
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long red[TCW_RECT_WARPS];
 
@@ -186,13 +205,19 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
                 bulk_g2s(sP + c * TCW_RECT_ECAP, Pt + (size_t)c * ppad + a0, cnt * (uint32_t)sizeof(double), &bar);
         }
     }
-    // end-index table over u = (row - m0)/R*R + (d - d0): t1 = t1_tile + u*dtau  (dt0 == dtau)
+    // per-tile index tables, computed cooperatively while the bulk copies are in flight:
+    //   sE[u], u = (row - m0)/R*R + (d - d0): end index of t1 = t1_tile + u*dtau  (dt0 == dtau)
+    //   sS[row - m0]: start index i_t0 of the row
     if (R > 1) {
         const uint32_t u_cnt = min((uint32_t)TCW_RECT_UCAP, ROWS + d_cnt);
         for (uint32_t u = threadIdx.x; u < u_cnt; u += TCW_RECT_THREADS)
             sE[u] = STAGED ? min(index_t1(t1_tile + u * w.dtau, t0_data, numAtoms, g) + 1 - a0,
                                  (uint32_t)(TCW_RECT_ECAP - 1))  // overhang entries stay in bounds
                            : index_t1(t1_tile + u * w.dtau, t0_data, numAtoms, g) + 1;
+    }
+    if (threadIdx.x < ROWS) {
+        const uint32_t m = min(m0 + threadIdx.x, w.N_t0 - 1);
+        sS[threadIdx.x] = index_t0(w.t0 + m * w.dt0, t0_data, numAtoms, g);
     }
     const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, t0_data, numAtoms, g);
     // off-diagonal: the split point rho = a0 lies strictly inside every window of the tile,
@@ -201,10 +226,10 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const size_t cells = (size_t)w.N_t0 * w.N_tau;
     float *Ft = Fmn ? Fmn + (size_t)tz * cells : nullptr;
 
-    __syncthreads();  // sE visible; mbarrier init visible to all waiters
+    __syncthreads();  // sE, sS visible; mbarrier init visible to all waiters
     if (STAGED) mbar_wait(&bar, 0);
     if (offdiag) {
-        // tabulate fl32(P[i] - P[rho]) for the staged slice (all 7 channels of an entry per thread)
+        // sQ[c][i] = fl32(P_c[a0+i] - P_c[rho]) for the staged slice (7 channels of an entry per thread)
         double pref[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) pref[c] = sP[c * TCW_RECT_ECAP];
@@ -212,6 +237,11 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++)
                 sQ[c * TCW_RECT_ECAP + i] = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]);
+        }
+        // sR[row][c] = fl32(P_c[rho] - P_c[s_row])
+        for (uint32_t i = threadIdx.x; i < ROWS * 8; i += TCW_RECT_THREADS) {
+            const uint32_t row = i >> 3, c = i & 7;
+            if (c < TCW_NCH) sR[i] = (float)(sP[c * TCW_RECT_ECAP] - __ldg(Pt + (size_t)c * ppad + sS[row]));
         }
         __syncthreads();
     }
@@ -227,7 +257,6 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
         if (m0 + grow >= w.N_t0) break;
         const uint32_t u_off = grow;
         const uint32_t t1_lane = t1_tile + grow * w.dt0 + lane * w.dtau;  // used by R == 1 only
-        uint32_t s_idx[R];
         float best[R];
         uint32_t best_d[R];
         float *rowp[R];
@@ -239,21 +268,21 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
             best_d[r] = r;
             rowok[r] = m < w.N_t0;
             const uint32_t mc = rowok[r] ? m : 0u;
-            s_idx[r] = index_t0(w.t0 + mc * w.dt0, t0_data, numAtoms, g);
             // cell (m, n = d - r) with d = d0 + lane + 32 j  ->  rowp[r][32 j]
             rowp[r] = Ft ? Ft + ((size_t)mc * w.N_tau + d0 + lane) - r : nullptr;
         }
         if (offdiag) {
-            float Rs[R][TCW_NCH];  // fl32(P[rho] - P[s]) per row
+            float Rs[R][TCW_NCH];
 #pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) {
-                const double pref = sP[c * TCW_RECT_ECAP];
-#pragma unroll
-                for (int r = 0; r < R; r++) Rs[r][c] = (float)(pref - __ldg(Pt + (size_t)c * ppad + s_idx[r]));
+            for (int r = 0; r < R; r++) {
+                const float4 lo = *reinterpret_cast<const float4 *>(sR + (grow + r) * 8);
+                const float4 hi = *reinterpret_cast<const float4 *>(sR + (grow + r) * 8 + 4);
+                Rs[r][0] = lo.x; Rs[r][1] = lo.y; Rs[r][2] = lo.z; Rs[r][3] = lo.w;
+                Rs[r][4] = hi.x; Rs[r][5] = hi.y; Rs[r][6] = hi.z;
             }
-#define RECT_FAST(CHK_, STORE_)                                                                            \
-    rect_rows_fp32<R, CHK_, STORE_>(sQ, sE, Rs, rowp, rowok, u_off, d0, n_j, lane, w.N_tau, d_total, t1_lane, \
-                                    t1_step, a0, t0_data, numAtoms, g, best, best_d)
+#define RECT_FAST(CHK_, STORE_)                                                                                    \
+    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ, sE, Rs, rowp, rowok, u_off, d0, n_j, lane, w.N_tau, d_total, t1_lane, \
+                                           t1_step, a0, t0_data, numAtoms, g, best, best_d)
             if (edge) {
                 if (Ft) RECT_FAST(true, true);
                 else RECT_FAST(true, false);
@@ -266,10 +295,11 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (!rowok[r]) continue;
+                const uint32_t s_row = sS[grow + r];
                 const RectRowResult rr =
-                    Ft ? rect_row_fp64<R, STAGED, true>(sP, sE, Pt, ppad, s_idx[r], rowp[r], r, u_off, d0, n_j, lane,
+                    Ft ? rect_row_fp64<R, STAGED, true>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
                                                         w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g)
-                       : rect_row_fp64<R, STAGED, false>(sP, sE, Pt, ppad, s_idx[r], rowp[r], r, u_off, d0, n_j, lane,
+                       : rect_row_fp64<R, STAGED, false>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
                                                          w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g);
                 best[r] = rr.best;
                 best_d[r] = rr.best_d;
@@ -279,7 +309,8 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (best[r] > -1.0f) {
-                const uint32_t flat = (m0 + grow + r) * w.N_tau + (best_d[r] - r);
+                // TRACK == false: index part 0 (flat = 0xFFFFFFFF), completed by the lnBtSG pass
+                const uint32_t flat = TRACK ? (m0 + grow + r) * w.N_tau + (best_d[r] - r) : 0xFFFFFFFFu;
                 const unsigned long long k = pack_key(best[r], flat);
                 key = k > key ? k : key;
             }

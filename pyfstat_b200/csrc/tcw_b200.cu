@@ -63,7 +63,7 @@ struct tcw_handle {
 
     // last map
     bool have_fmn = false;
-    uint32_t last_N_t0 = 0, last_N_tau = 0;
+    uint32_t last_N_t0 = 0, last_N_tau = 0, last_pitch = 0;
 
     // exp weight-table cache key
     bool w_valid = false;
@@ -460,6 +460,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
         w.dt0 = w.dtau = TAtom;
         w.t0Band = w.tauBand = 0;
         w.N_t0 = w.N_tau = 1;
+        w.pitch = 4;
     } else {
         if (win->dt0 == 0 || win->dtau == 0)
             return fail(h, TCW_E_INVALID, "windowRange.dt0 and .dtau must be positive");
@@ -472,10 +473,12 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
         w.tauBand = win->tauBand;
         w.N_t0 = win->t0Band / win->dt0 + 1;
         w.N_tau = win->tauBand / win->dtau + 1;
+        w.pitch = (w.N_tau + 3u) & ~3u;
     }
     const uint64_t cells64 = (uint64_t)w.N_t0 * w.N_tau;
     if (cells64 >= (1ull << 32)) return fail(h, TCW_E_INVALID, "map has more than 2^32-1 cells");
     const size_t cells = (size_t)cells64;
+    const size_t pcells = (size_t)w.N_t0 * w.pitch;  // device F_mn elements per template (padded rows)
 
     IndexGeom g;
     g.TAtom = TAtom;
@@ -525,14 +528,14 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     // launch gaps and tails cost more than the HBM round trip, so the scratch is sized for big
     // launches (TCW_SUBBATCH_MB, default 2048)
     int S = T;
-    if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (cells * 4)));
+    if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (pcells * 4)));
     S = std::min(S, 32768);
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
     if (want_fmn) {
-        if ((rc = ensure(h, h->d_Fmn, (size_t)T * cells * sizeof(float)))) return rc;
+        if ((rc = ensure(h, h->d_Fmn, (size_t)T * pcells * sizeof(float)))) return rc;
         fmn_full = (float *)h->d_Fmn.p;
     } else if (want_btsg) {
-        if ((rc = ensure(h, h->d_scratch, (size_t)S * cells * sizeof(float)))) return rc;
+        if ((rc = ensure(h, h->d_scratch, (size_t)S * pcells * sizeof(float)))) return rc;
         fmn_scratch = (float *)h->d_scratch.p;
     }
     const int n_sub = (T + S - 1) / S;
@@ -607,7 +610,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     for (int sb = 0; sb < n_sub; sb++) {
         const int t_base = sb * S;
         const int cnt = std::min(S, T - t_base);
-        float *fmn = fmn_full ? fmn_full + (size_t)t_base * cells : fmn_scratch;
+        float *fmn = fmn_full ? fmn_full + (size_t)t_base * pcells : fmn_scratch;
         CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 0], st));
         if (path == PATH_GENERIC) {
             dim3 grid((unsigned)((cells + TCW_GENERIC_THREADS - 1) / TCW_GENERIC_THREADS), 1, cnt);
@@ -691,7 +694,8 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT && !rect_track;
 #define LAUNCH_BTSG(EX, LOC)                                                                          \
     tcw_btsg_kernel<EX, LOC><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(                          \
-        fmn, t_base, w.N_t0, w.N_tau, (unsigned long long *)h->d_maxkey.p, (const double *)h->d_lut.p, \
+        fmn, t_base, w.N_t0, w.N_tau, w.pitch, (unsigned long long *)h->d_maxkey.p,                    \
+        (const double *)h->d_lut.p,                                                                  \
         (double *)h->d_rowsum.p, (double *)h->d_colsum.p)
             if (exact && locate) LAUNCH_BTSG(true, true);
             else if (exact) LAUNCH_BTSG(true, false);
@@ -718,6 +722,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     h->have_fmn = want_fmn;
     h->last_N_t0 = w.N_t0;
     h->last_N_tau = w.N_tau;
+    h->last_pitch = w.pitch;
     return TCW_OK;
 }
 
@@ -764,9 +769,11 @@ extern "C" int tcw_fetch_fmn(tcw_handle *h, int t, float *out) {
     if (!h || !out) return TCW_E_INVALID;
     if (!h->have_fmn) return fail(h, TCW_E_STATE, "tcw_fetch_fmn: last map did not materialise F_mn");
     if (t < 0 || t >= h->T) return fail(h, TCW_E_INVALID, "tcw_fetch_fmn: template index out of range");
-    const size_t cells = (size_t)h->last_N_t0 * h->last_N_tau;
-    CUDA_TRY(h, cudaMemcpyAsync(out, (const float *)h->d_Fmn.p + (size_t)t * cells, cells * sizeof(float),
-                                cudaMemcpyDeviceToHost, h->stream));
+    // device rows are padded to a multiple of 4 floats; the host array is dense [N_t0][N_tau]
+    CUDA_TRY(h, cudaMemcpy2DAsync(out, (size_t)h->last_N_tau * sizeof(float),
+                                  (const float *)h->d_Fmn.p + (size_t)t * h->last_N_t0 * h->last_pitch,
+                                  (size_t)h->last_pitch * sizeof(float), (size_t)h->last_N_tau * sizeof(float),
+                                  h->last_N_t0, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return TCW_OK;
 }
@@ -798,9 +805,9 @@ extern "C" int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_
     rc = tcw_map_resident(h, win, flags);
     if (rc) return rc;
     if (flags & TCW_WANT_FMN) {
-        const size_t cells = (size_t)h->last_N_t0 * h->last_N_tau;
-        CUDA_TRY(h, cudaMemcpyAsync(F_mn_out, h->d_Fmn.p, (size_t)T * cells * sizeof(float),
-                                    cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,
+                                      (size_t)h->last_pitch * sizeof(float), (size_t)h->last_N_tau * sizeof(float),
+                                      (size_t)T * h->last_N_t0, cudaMemcpyDeviceToHost, h->stream));
     }
     return tcw_fetch_results(h, results);
 }

@@ -79,6 +79,7 @@ struct MapWindow {
     uint32_t t0, dt0, tau, dtau;
     uint32_t t0Band, tauBand;
     uint32_t N_t0, N_tau;
+    uint32_t pitch;  // row pitch (floats) of the device F_mn: N_tau rounded up to 4 -> 16-byte aligned rows
 };
 
 // ---------------------------------------------------------------------------------------

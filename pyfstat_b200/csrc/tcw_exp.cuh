@@ -191,8 +191,7 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
     }
 
     // ---- fused epilogue: F, optional store, max/argmax, degenerate flag ----
-    const size_t cells = (size_t)w.N_t0 * w.N_tau;
-    float *Ft = Fmn ? Fmn + (size_t)tz * cells : nullptr;
+    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
     float best = -1.0f;
     uint32_t best_flat = 0;
     bool degenerate = false;
@@ -206,7 +205,7 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
                 const float F = fstat_fast(acc[0][r][j], acc[1][r][j], acc[2][r][j], acc[3][r][j],
                                            acc[4][r][j], acc[5][r][j], acc[6][r][j]);
                 const uint32_t flat = m * w.N_tau + n;
-                if (Ft) Ft[flat] = F;
+                if (Ft) Ft[(size_t)m * w.pitch + n] = F;
                 if (F > best) {
                     best = F;
                     best_flat = flat;

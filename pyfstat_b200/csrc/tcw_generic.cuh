@@ -75,7 +75,7 @@ tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta
             }
         }
         const float F = fstat_faithful(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
-        if (Fmn) Fmn[(size_t)tz * cells + flat] = F;
+        if (Fmn) Fmn[(size_t)tz * w.N_t0 * w.pitch + (size_t)m * w.pitch + n] = F;
         if (F > -1.0f) key = pack_key(F, (uint32_t)flat);  // maxF starts at -1, strict > (tcw:135-139)
     }
     block_atomic_max_key<TCW_GENERIC_THREADS / 32>(key, &maxkey[t], red);

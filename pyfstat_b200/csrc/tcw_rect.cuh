@@ -64,11 +64,11 @@
 template <int R, bool CHECKED, bool STORE, bool TRACK>
 __device__ __forceinline__ void rect_rows_fp32(
     const float *__restrict__ sQ, const uint32_t *__restrict__ sE, const float (&Rs)[R][TCW_NCH],
-    float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int n_j, uint32_t lane,
-    uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0, uint32_t t0_data,
-    uint32_t numAtoms, const IndexGeom g, float (&best)[R], uint32_t (&best_d)[R]) {
+    float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int j_begin, int j_end,
+    uint32_t lane, uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0,
+    uint32_t t0_data, uint32_t numAtoms, const IndexGeom g, float (&best)[R], uint32_t (&best_d)[R]) {
 #pragma unroll 4
-    for (int j = 0; j < n_j; j++) {
+    for (int j = j_begin; j < j_end; j++) {
         const uint32_t d = d0 + lane + 32u * j;
         if (CHECKED && d >= d_total) break;
         uint32_t idx;  // index of P[e+1] relative to the staged slice
@@ -185,7 +185,7 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const uint32_t d0 = blockIdx.x == 0 ? 0u : DD + (blockIdx.x - 1) * TCW_RECT_DT;
     const uint32_t d_cnt = blockIdx.x == 0 ? DD : (uint32_t)TCW_RECT_DT;
     const uint32_t d_last = min(d0 + d_cnt, d_total) - 1;
-    const bool edge = (d0 < (uint32_t)(R - 1)) || (d0 + d_cnt > w.N_tau) || (m0 + ROWS > w.N_t0);
+    const bool edge_rows = (d0 < (uint32_t)(R - 1)) || (m0 + ROWS > w.N_t0);  // head strip / bottom row tile
 
     // end time of (row group, d): rows of a group differ by dt0 == dtau (R > 1), absorbed into d
     const uint32_t t1_tile = w.t0 + w.tau + m0 * w.dt0 + d0 * w.dtau;
@@ -223,8 +223,7 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     // off-diagonal: the split point rho = a0 lies strictly inside every window of the tile,
     // s < rho <= e + 1 with e > s (so no cell of the tile is degenerate): rho >= s_hi + 2
     const bool offdiag = STAGED && (a0 >= s_hi + 2);
-    const size_t cells = (size_t)w.N_t0 * w.N_tau;
-    float *Ft = Fmn ? Fmn + (size_t)tz * cells : nullptr;
+    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
 
     __syncthreads();  // sE, sS visible; mbarrier init visible to all waiters
     if (STAGED) mbar_wait(&bar, 0);
@@ -248,6 +247,7 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
 
     const uint32_t t1_step = 32u * w.dtau;
     const int n_j = (int)(d_cnt / 32);
+    const int j_full = w.N_tau > d0 ? (int)min((w.N_tau - d0) / 32u, (uint32_t)n_j) : 0;  // fully valid chunks
     unsigned long long key = 0ull;
     uint32_t degenerate = 0;
     // each warp walks TCW_RECT_G row groups of R rows: the tile's staging cost is shared
@@ -269,7 +269,7 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
             rowok[r] = m < w.N_t0;
             const uint32_t mc = rowok[r] ? m : 0u;
             // cell (m, n = d - r) with d = d0 + lane + 32 j  ->  rowp[r][32 j]
-            rowp[r] = Ft ? Ft + ((size_t)mc * w.N_tau + d0 + lane) - r : nullptr;
+            rowp[r] = Ft ? Ft + ((size_t)mc * w.pitch + d0 + lane) - r : nullptr;
         }
         if (offdiag) {
             float Rs[R][TCW_NCH];
@@ -280,15 +280,22 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
                 Rs[r][0] = lo.x; Rs[r][1] = lo.y; Rs[r][2] = lo.z; Rs[r][3] = lo.w;
                 Rs[r][4] = hi.x; Rs[r][5] = hi.y; Rs[r][6] = hi.z;
             }
-#define RECT_FAST(CHK_, STORE_)                                                                                    \
-    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ, sE, Rs, rowp, rowok, u_off, d0, n_j, lane, w.N_tau, d_total, t1_lane, \
-                                           t1_step, a0, t0_data, numAtoms, g, best, best_d)
-            if (edge) {
-                if (Ft) RECT_FAST(true, true);
-                else RECT_FAST(true, false);
+#define RECT_FAST(CHK_, STORE_, J0_, J1_)                                                                       \
+    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ, sE, Rs, rowp, rowok, u_off, d0, J0_, J1_, lane, w.N_tau, d_total, \
+                                           t1_lane, t1_step, a0, t0_data, numAtoms, g, best, best_d)
+            if (edge_rows) {
+                if (Ft) RECT_FAST(true, true, 0, n_j);
+                else RECT_FAST(true, false, 0, n_j);
             } else {
-                if (Ft) RECT_FAST(false, true);
-                else RECT_FAST(false, false);
+                // chunks of 32 d that are valid for every lane and row run unchecked; only the
+                // chunk(s) straddling the map's right edge are bounds-checked
+                if (Ft) {
+                    RECT_FAST(false, true, 0, j_full);
+                    if (j_full < n_j) RECT_FAST(true, true, j_full, n_j);
+                } else {
+                    RECT_FAST(false, false, 0, j_full);
+                    if (j_full < n_j) RECT_FAST(true, false, j_full, n_j);
+                }
             }
 #undef RECT_FAST
         } else {

@@ -8,6 +8,7 @@
 // Data layout in HBM (per handle, grown on demand, reused across calls):
 //   d_atoms  [T][numDet][stride] tcw_atom (32 B AoS, as uploaded)
 //   d_X      [T][7][xpad] float32   merged channels (zero padded)
+//   d_X8     [T][xpad][8] float32   the same atoms, channel-interleaved 32-byte records (exp kernel)
 //   d_P      [T][7][ppad] float64   exclusive prefix sums (rect window)
 //   d_W      [n_tiles][KW][64] float32  exponential-window weight table (cached per window)
 //   d_Fmn    [T][N_t0][N_tau] float32   only with TCW_WANT_FMN; else a sub-batch scratch
@@ -58,7 +59,7 @@ struct tcw_handle {
     uint32_t Nmax = 0, xpad = 0, ppad = 0;
     bool uniform = true;  // all templates share (t0_data, numAtoms)
     std::vector<TplMeta> meta;
-    DevBuf d_atoms, d_natoms, d_meta, d_X, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
+    DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
         d_flags, d_results, d_W, d_Kn, d_lut, d_flush;
 
     // last map
@@ -233,7 +234,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (!h) return TCW_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_P, &h->d_Fmn, &h->d_scratch,
+    for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
                       &h->d_Kn, &h->d_lut, &h->d_flush})
         release(*b);
@@ -514,6 +515,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     // ---- buffers ----
     int rc;
     if ((rc = ensure(h, h->d_X, (size_t)T * TCW_NCH * h->xpad * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->d_X8, (size_t)T * 8 * h->xpad * sizeof(float)))) return rc;
     if ((rc = ensure(h, h->d_P, (size_t)T * TCW_NCH * h->ppad * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->d_maxkey, (size_t)T * sizeof(unsigned long long)))) return rc;
     if ((rc = ensure(h, h->d_flags, (size_t)T * sizeof(uint32_t)))) return rc;
@@ -558,7 +560,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     // ---- stage 0: merge detectors, transpose to channels, FP64 prefix scan ----
     tcw_prep_kernel<<<T, TCW_PREP_THREADS, 0, st>>>(
         (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p,
-        h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, h->xpad, (double *)h->d_P.p, h->ppad,
+        h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, (float *)h->d_X8.p, h->xpad, (double *)h->d_P.p, h->ppad,
         (uint32_t *)h->d_flags.p);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -676,7 +678,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
 #define LAUNCH_EXP(CFG)                                                                                   \
     tcw_exp_map_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                                     \
-        (const float *)h->d_X.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,     \
+        (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,    \
         (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, (unsigned long long *)h->d_maxkey.p,        \
         (uint32_t *)h->d_flags.p)
             if (h->exp_variant == 0) LAUNCH_EXP(ExpCfgA);

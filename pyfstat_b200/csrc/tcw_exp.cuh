@@ -18,9 +18,10 @@
 // 112 FP32 accumulators per thread (ExpCfg below parametrises the tile; measured in round 1:
 // 64x64/256 thr 14.70 ms, 32x64/128 thr 13.77 ms, 64x32/256 thr 13.80 ms per 32 30-d templates).
 // Per k step a thread issues 112 FFMA + 4 FMUL (w^2) for
-// 7 LDS.32 + 1 LDS.128: rows of a thread are consecutive t0, so their atoms form a sliding
-// window held in registers (one new atom per channel per step), weights are shared along m.
-// Operand tiles (64 k x 64 n weights, contiguous by construction of the table; 7 x 132 atoms)
+// 3 LDS.128: rows of a thread are consecutive t0, so their atoms form a sliding window held in
+// registers (one new atom = one 32-byte record of all 7 channels per step), weights are shared
+// along m.
+// Operand tiles (64 k x 64 n weights and 100 atom records, both contiguous by construction)
 // are staged by 1-D TMA bulk copies through a 3-stage mbarrier ring.  Ragged edges: weights
 // are zero beyond each column's K_n, atoms are zero-padded beyond the data end, and a tile
 // stops at min(K of its last column, atoms left after its first row).
@@ -41,9 +42,9 @@ struct ExpCfg {
     static constexpr int kRM = RM, kRN = RN;
     static constexpr int kTM = NT / TCW_EXP_TNT * RM;
     static constexpr int kTN = TCW_EXP_TNT * RN;
-    static constexpr int kXS = kTM + TCW_EXP_KC + 4;  // staged atoms per channel
+    static constexpr int kXS = kTM + TCW_EXP_KC + 4;  // staged atoms (32-byte records: 7 channels + pad)
     static constexpr int kWBytes = TCW_EXP_KC * kTN * 4;
-    static constexpr int kXBytes = TCW_NCH * kXS * 4;
+    static constexpr int kXBytes = kXS * 32;
     static constexpr int kStageBytes = kWBytes + kXBytes;
     static constexpr int kSmem = TCW_EXP_STAGES * kStageBytes;
     static_assert(kXS % 4 == 0 && kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
@@ -85,7 +86,7 @@ __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__res
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, (Cfg::kThreads == 256 ? (Cfg::kRN == 4 ? 1 : 2) : 3))
-tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__restrict__ W,
+tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__restrict__ W,
                    const int32_t *__restrict__ Kn, uint32_t KW, const TplMeta *__restrict__ meta,
                    int t_base, MapWindow w, uint32_t i00, float *__restrict__ Fmn,
                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
@@ -104,8 +105,7 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
     const uint32_t n_last = min(n0 + TN, w.N_tau) - 1;
     const int k_end = min(Kn[n_last] + 1, (int)numAtoms - (int)s_base);
     const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
-    const uint32_t off = s_base & 3u;  // bulk copies need 16-byte aligned sources
-    const float *Xt = X + (size_t)t * TCW_NCH * xpad + (s_base - off);
+    const float *Xt = X8 + ((size_t)t * xpad + s_base) * 8;  // 32-byte atom records: always 16-byte aligned
     const float *Wt = W + (size_t)nt * KW * TN;
 
     const int tid = threadIdx.x;
@@ -116,10 +116,7 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
         unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
         bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
-#pragma unroll
-        for (int c = 0; c < TCW_NCH; c++)
-            bulk_g2s(st + Cfg::kWBytes + c * XS * 4, Xt + (size_t)c * xpad + (size_t)chunk * TCW_EXP_KC, XS * 4,
-                     &full[s]);
+        bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, Cfg::kXBytes, &full[s]);
     };
 
     if (tid == 0) {
@@ -146,26 +143,29 @@ tcw_exp_map_kernel(const float *__restrict__ X, uint32_t xpad, const float *__re
         const int s = chunk % TCW_EXP_STAGES;
         mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
         const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes);
-        const float *Xs = Ws + TCW_EXP_KC * TN;
-        const float *xrow = Xs + off + tm * RM;  // + c*XS + k + r
-        const float *wrow = Ws + tn * RN;        // + k*TN
+        const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
+        const float *wrow = Ws + tn * RN;                                                         // + k*TN
 
         // sliding window of 4 consecutive atoms per channel: value with relative index q
         // lives in slot q & 3
         float xr[TCW_NCH][4];
 #pragma unroll
-        for (int c = 0; c < TCW_NCH; c++) {
-            xr[c][0] = xrow[c * XS + 0];
-            xr[c][1] = xrow[c * XS + 1];
-            xr[c][2] = xrow[c * XS + 2];
+        for (int q = 0; q < 3; q++) {
+            const float4 lo = xrow[2 * q], hi = xrow[2 * q + 1];
+            xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+            xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
         }
 #pragma unroll 1
         for (int kk = 0; kk < TCW_EXP_KC; kk += 4) {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int k = kk + u;
-#pragma unroll
-                for (int c = 0; c < TCW_NCH; c++) xr[c][(u + 3) & 3] = xrow[c * XS + k + 3];
+                {  // the one new atom of this step: all 7 channels in two 128-bit loads
+                    const float4 lo = xrow[2 * (k + 3)], hi = xrow[2 * (k + 3) + 1];
+                    const int q = (u + 3) & 3;
+                    xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+                    xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+                }
                 float w1[RN], w2[RN];
                 if (RN == 4) {
                     const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);

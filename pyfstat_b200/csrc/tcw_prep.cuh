@@ -9,7 +9,8 @@
 // empty bins stay zero.  One CTA per template.
 //
 // Outputs (both zero padded):
-//   X[t][c][xpad] float32  merged channel c (SoA)  -- exp window and generic kernels
+//   X[t][c][xpad] float32  merged channel c (SoA)  -- generic kernels, tcw_fetch_merged
+//   X8[t][xpad][8] float32 merged atoms, channel-interleaved (7 + pad) -- exp window kernel
 //   P[t][c][ppad] float64  exclusive prefix: P[i] = sum_{j<i} X[j], P[0] = 0, i <= numAtoms
 //                          -- rect window: every (t0,tau) cell is one FP64 difference
 #pragma once
@@ -22,8 +23,8 @@
 __global__ void __launch_bounds__(TCW_PREP_THREADS)
 tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__ n_atoms,
                 const TplMeta *__restrict__ meta, int numDet, uint32_t stride, uint32_t TAtom,
-                MagicDiv md, float *__restrict__ X, uint32_t xpad, double *__restrict__ P,
-                uint32_t ppad, uint32_t *__restrict__ flags) {
+                MagicDiv md, float *__restrict__ X, float *__restrict__ X8, uint32_t xpad,
+                double *__restrict__ P, uint32_t ppad, uint32_t *__restrict__ flags) {
     const int t = blockIdx.x;
     const uint32_t N = meta[t].numAtoms;
     const uint32_t tMin = meta[t].t0_data;
@@ -76,6 +77,10 @@ tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__
         }
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) Xt[(size_t)c * xpad + j] = s[c];
+        // atom-interleaved copy for the exponential-window kernel: one 32-byte record per atom
+        float4 *x8 = reinterpret_cast<float4 *>(X8 + ((size_t)t * xpad + j) * 8);
+        x8[0] = make_float4(s[0], s[1], s[2], s[3]);
+        x8[1] = make_float4(s[4], s[5], s[6], 0.0f);
     }
     __syncthreads();
 

@@ -215,7 +215,7 @@ def cpu_baseline_single_thread(spec):
     from pyfstat_b200.atoms import synth_atoms
 
     O.build()
-    row_stride = 2 if spec["window"] == "exp" else 1
+    row_stride = 1
     T = 1 if spec["window"] == "exp" else 100
     ws, cells_per_tpl = cpu_sample_window(spec, row_stride)
     batch = synth_atoms(T, spec["n"], spec["dets"], seed=1000 * spec["cfg"], t0_data=T0_DATA, TAtom=TATOM)
@@ -433,7 +433,8 @@ def secondary_rect(h, L, hbm_peak, hbm_src):
 
     spec = workload_spec("rect60")
     T = spec["T"]
-    batch = synth_atoms(T, spec["n"], spec["dets"], seed=3000, t0_data=T0_DATA, TAtom=TATOM)
+    alloc = L.pinned_atoms_alloc()
+    batch = synth_atoms(T, spec["n"], spec["dets"], seed=3000, t0_data=T0_DATA, TAtom=TATOM, pinned_alloc=alloc)
     h.upload(batch)
     out = {}
     for name, flags in (("fmn", L.WANT_FMN), ("fmn_btsg", L.WANT_FMN | L.WANT_BTSG), ("fused_max_only", 0)):
@@ -451,6 +452,15 @@ def secondary_rect(h, L, hbm_peak, hbm_src):
             out[name]["roofline"] = {"bound": "hbm", "kernel": "tcw_rect_map_kernel", "achieved": gbs, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                                      "algorithmic_bytes_per_template": spec["alg_bytes"]}
+    # end to end through tcw_map_batch (pinned host atoms -> records), lnBtSG on, no F_mn copy
+    times = []
+    for i in range(8):
+        t0 = time.perf_counter()
+        h.map_batch(batch, spec["w"], L.WANT_BTSG)
+        if i >= 3:
+            times.append(time.perf_counter() - t0)
+    out["e2e_btsg"] = {"cells_per_s": T * spec["cells"] / statistics.mean(times), "ms_per_step": 1e3 * statistics.mean(times),
+                       "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(T * L.RESULT_DTYPE.itemsize)}
     out["config"] = workload_config(spec)
     return out
 

@@ -42,6 +42,8 @@ struct DevBuf {
 struct tcw_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of atom chunks, overlapped with the kernels
+    std::vector<cudaEvent_t> ev_up;
     cudaEvent_t ev_timer[2] = {nullptr, nullptr};
     cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // start, prep, table, loops end... finalize
     cudaEvent_t ev_fin = nullptr;
@@ -183,6 +185,7 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
         return fail(nullptr, TCW_E_CUDA, m);
     }
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto &ev : h->ev_timer) CUDA_TRY(nullptr, cudaEventCreate(&ev));
     for (auto &ev : h->ev_stage) CUDA_TRY(nullptr, cudaEventCreate(&ev));
     CUDA_TRY(nullptr, cudaEventCreate(&h->ev_fin));
@@ -244,6 +247,8 @@ extern "C" int tcw_destroy(tcw_handle *h) {
         if (ev) cudaEventDestroy(ev);
     if (h->ev_fin) cudaEventDestroy(h->ev_fin);
     for (auto ev : h->ev_sub) cudaEventDestroy(ev);
+    for (auto ev : h->ev_up) cudaEventDestroy(ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return TCW_OK;
@@ -300,8 +305,10 @@ extern "C" int tcw_flush_l2(tcw_handle *h) {
 // ---------------------------------------------------------------------------------------
 // upload
 // ---------------------------------------------------------------------------------------
-extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
-                                uint32_t atom_stride, uint32_t TAtom, int T, int numDet) {
+// Geometry of the batch + device buffers + the small per-vector arrays; the atoms themselves are
+// copied here (copy_atoms) or, chunk by chunk and overlapped with the kernels, by map_impl.
+static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                         uint32_t atom_stride, uint32_t TAtom, int T, int numDet, bool copy_atoms) {
     if (!h) return TCW_E_INVALID;
     if (!atoms || !n_atoms || T < 1 || numDet < 1 || atom_stride < 1 || TAtom < 1)
         return fail(h, TCW_E_INVALID, "tcw_upload_atoms: bad argument");
@@ -346,8 +353,9 @@ extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint
     if ((rc = ensure(h, h->d_atoms, n_vec * atom_stride * sizeof(tcw_atom)))) return rc;
     if ((rc = ensure(h, h->d_natoms, n_vec * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(h, h->d_meta, (size_t)T * sizeof(TplMeta)))) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_atoms.p, atoms, n_vec * atom_stride * sizeof(tcw_atom),
-                                cudaMemcpyHostToDevice, h->stream));
+    if (copy_atoms)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_atoms.p, atoms, n_vec * atom_stride * sizeof(tcw_atom),
+                                    cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_natoms.p, n_atoms, n_vec * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                 h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_meta.p, h->meta.data(), (size_t)T * sizeof(TplMeta),
@@ -357,6 +365,11 @@ extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->uploaded = true;
     return TCW_OK;
+}
+
+extern "C" int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                                uint32_t atom_stride, uint32_t TAtom, int T, int numDet) {
+    return upload_common(h, atoms, n_atoms, atom_stride, TAtom, T, numDet, true);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -437,7 +450,10 @@ static size_t subbatch_bytes() {
 // ---------------------------------------------------------------------------------------
 // the map
 // ---------------------------------------------------------------------------------------
-extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags) {
+// host_atoms == nullptr: the atoms are resident.  Otherwise they are still on the host (pinned
+// for real overlap): the batch is cut into chunks whose H2D copies run on a second stream while
+// the previous chunk is being computed.
+static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms) {
     if (!h) return TCW_E_INVALID;
     if (!win) return fail(h, TCW_E_INVALID, "tcw_map_resident: window range is NULL");
     if (!h->uploaded) return fail(h, TCW_E_STATE, "tcw_map_resident: no resident atoms (call tcw_upload_atoms)");
@@ -532,6 +548,7 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     int S = T;
     if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (pcells * 4)));
     S = std::min(S, 32768);
+    if (host_atoms && T >= 16) S = std::min(S, std::max(8, (T + 3) / 4));  // upload/compute overlap
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
     if (want_fmn) {
         if ((rc = ensure(h, h->d_Fmn, (size_t)T * pcells * sizeof(float)))) return rc;
@@ -556,15 +573,6 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
         CUDA_TRY(h, cudaMemsetAsync(h->d_rowsum.p, 0, (size_t)T * w.N_t0 * sizeof(double), st));
         CUDA_TRY(h, cudaMemsetAsync(h->d_colsum.p, 0, (size_t)T * w.N_tau * sizeof(double), st));
     }
-
-    // ---- stage 0: merge detectors, transpose to channels, FP64 prefix scan ----
-    tcw_prep_kernel<<<T, TCW_PREP_THREADS, 0, st>>>(
-        (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p,
-        h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, (float *)h->d_X8.p, h->xpad, (double *)h->d_P.p, h->ppad,
-        (uint32_t *)h->d_flags.p);
-    h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
 
     // ---- stage 1: exponential-window weight table (cached across calls) ----
     uint32_t exp_TM = 0, exp_TN = 0;
@@ -608,10 +616,35 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[2], st));
 
-    // ---- stage 2/3: map kernel (+ lnBtSG pass) per sub-batch ----
+    // ---- stage 0 + 2/3 per sub-batch: [H2D of the chunk on the copy stream] -> merge/scan ->
+    //      map kernel (+ lnBtSG pass).  Sub-batches double as upload chunks.
+    if (host_atoms) {
+        while ((int)h->ev_up.size() < n_sub) {
+            cudaEvent_t ev;
+            CUDA_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->ev_up.push_back(ev);
+        }
+        const size_t per_tpl = (size_t)h->numDet * h->stride;
+        for (int sb = 0; sb < n_sub; sb++) {
+            const int lo = sb * S, cnt = std::min(S, T - lo);
+            CUDA_TRY(h, cudaMemcpyAsync((tcw_atom *)h->d_atoms.p + (size_t)lo * per_tpl, host_atoms + (size_t)lo * per_tpl,
+                                        (size_t)cnt * per_tpl * sizeof(tcw_atom), cudaMemcpyHostToDevice,
+                                        h->copy_stream));
+            CUDA_TRY(h, cudaEventRecord(h->ev_up[sb], h->copy_stream));
+        }
+    }
     for (int sb = 0; sb < n_sub; sb++) {
         const int t_base = sb * S;
         const int cnt = std::min(S, T - t_base);
+        if (host_atoms) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_up[sb], 0));
+        // merge detectors, transpose to channels, FP64 prefix scan
+        tcw_prep_kernel<<<cnt, TCW_PREP_THREADS, 0, st>>>(
+            (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p, t_base,
+            h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, (float *)h->d_X8.p, h->xpad, (double *)h->d_P.p,
+            h->ppad, (uint32_t *)h->d_flags.p);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        if (sb == 0) CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
         float *fmn = fmn_full ? fmn_full + (size_t)t_base * pcells : fmn_scratch;
         CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 0], st));
         if (path == PATH_GENERIC) {
@@ -728,12 +761,18 @@ extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint
     return TCW_OK;
 }
 
+extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags) {
+    return map_impl(h, win, flags, nullptr);
+}
+
 extern "C" int tcw_last_stage_ms(tcw_handle *h, float ms[5]) {
     if (!h || !ms) return TCW_E_INVALID;
     if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_last_stage_ms: no map has been run");
     CUDA_TRY(h, cudaEventSynchronize(h->ev_fin));
-    CUDA_TRY(h, cudaEventElapsedTime(&ms[0], h->ev_stage[0], h->ev_stage[1]));
-    CUDA_TRY(h, cudaEventElapsedTime(&ms[1], h->ev_stage[1], h->ev_stage[2]));
+    // order on the stream: start [0] -> weight table [2] -> first sub-batch's merge/scan [1]
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[1], h->ev_stage[0], h->ev_stage[2]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[0], h->ev_stage[2], h->ev_stage[1]));
+    ms[0] *= (float)h->n_sub_last;  // merge/scan runs once per sub-batch; the first one is timed
     ms[2] = ms[3] = 0.0f;
     for (int sb = 0; sb < h->n_sub_last; sb++) {
         float a = 0, b = 0;
@@ -802,9 +841,9 @@ extern "C" int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_
     if (!results) return fail(h, TCW_E_INVALID, "tcw_map_batch: results is NULL");
     if ((flags & TCW_WANT_FMN) && !F_mn_out)
         return fail(h, TCW_E_INVALID, "tcw_map_batch: TCW_WANT_FMN needs F_mn_out");
-    int rc = tcw_upload_atoms(h, atoms, n_atoms, atom_stride, TAtom, T, numDet);
+    int rc = upload_common(h, atoms, n_atoms, atom_stride, TAtom, T, numDet, false);
     if (rc) return rc;
-    rc = tcw_map_resident(h, win, flags);
+    rc = map_impl(h, win, flags, atoms);
     if (rc) return rc;
     if (flags & TCW_WANT_FMN) {
         CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,

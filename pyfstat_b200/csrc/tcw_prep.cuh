@@ -22,10 +22,10 @@
 
 __global__ void __launch_bounds__(TCW_PREP_THREADS)
 tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__ n_atoms,
-                const TplMeta *__restrict__ meta, int numDet, uint32_t stride, uint32_t TAtom,
+                const TplMeta *__restrict__ meta, int t_base, int numDet, uint32_t stride, uint32_t TAtom,
                 MagicDiv md, float *__restrict__ X, float *__restrict__ X8, uint32_t xpad,
                 double *__restrict__ P, uint32_t ppad, uint32_t *__restrict__ flags) {
-    const int t = blockIdx.x;
+    const int t = t_base + blockIdx.x;
     const uint32_t N = meta[t].numAtoms;
     const uint32_t tMin = meta[t].t0_data;
     const int tid = threadIdx.x;

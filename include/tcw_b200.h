@@ -149,6 +149,17 @@ int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
                   const tcw_window_range *win, uint32_t flags, float *F_mn_out,
                   tcw_result *results);
 
+/* Same, with ONE WINDOW RANGE PER TEMPLATE (all of the same type and map shape, typically
+ * 1x1): the MCMC case, where every walker of a sampler step carries its own transient
+ * start time and duration and each likelihood call evaluates a single cell
+ * (pyfstat/mcmc_based_searches.py:3448-3466, 3511-3516: windowRange.t0 = int(tstart),
+ * windowRange.tau = int(tend - tstart), pyfstat/core.py:1447-1449).  Served by the generic
+ * kernels. */
+int tcw_map_batch_windows(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                          uint32_t atom_stride, uint32_t TAtom, int T, int numDet,
+                          const tcw_window_range *wins /* [T] */, uint32_t flags, float *F_mn_out,
+                          tcw_result *results);
+
 /* Device-resident variant used by batched search drivers and by bench.py's kernel-only
  * timing: upload once, then run any number of windows on the resident atoms. */
 int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,

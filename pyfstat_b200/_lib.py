@@ -31,7 +31,7 @@ E_INVALID, E_WINDOW, E_CUDA, E_NOMEM, E_DEGENERATE, E_STATE = -1, -2, -3, -4, -5
 
 EXPORTED_SYMBOLS = (
     "tcw_abi_version", "tcw_create", "tcw_destroy", "tcw_last_error", "tcw_device_name",
-    "tcw_map_dims", "tcw_map_batch", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
+    "tcw_map_dims", "tcw_map_batch", "tcw_map_batch_windows", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
     "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
     "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_host_alloc",
     "tcw_host_free", "tcw_cell_index_range",
@@ -118,6 +118,7 @@ def load_library(build_if_missing: bool = True):
     L.tcw_device_name.argtypes = [vp, C.c_char_p, i32]
     L.tcw_map_dims.argtypes = [C.POINTER(CWindowRange), C.POINTER(u32), C.POINTER(u32)]
     L.tcw_map_batch.argtypes = [vp, vp, vp, u32, u32, i32, i32, C.POINTER(CWindowRange), u32, vp, vp]
+    L.tcw_map_batch_windows.argtypes = [vp, vp, vp, u32, u32, i32, i32, vp, u32, vp, vp]
     L.tcw_upload_atoms.argtypes = [vp, vp, vp, u32, u32, i32, i32]
     L.tcw_map_resident.argtypes = [vp, C.POINTER(CWindowRange), u32]
     L.tcw_fetch_results.argtypes = [vp, vp]
@@ -234,6 +235,25 @@ class Handle:
         rc = self.L.tcw_map_batch(
             self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
             batch.T, batch.numDet, C.byref(cw), flags, F.ctypes.data if F is not None else None,
+            results.ctypes.data,
+        )
+        self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        return results, F
+
+    def map_batch_windows(self, batch: AtomBatch, windows, flags: int = 0, *, raise_on_degenerate: bool = True):
+        """``tcw_map_batch_windows``: one window range per template (same type and map shape)."""
+        ws = [TransientWindowRange.from_any(w) for w in windows]
+        if len(ws) != batch.T:
+            raise ValueError("need one window range per template")
+        for w in ws:
+            w.check_type()
+        N_t0, N_tau = ws[0].dims()
+        cws = (CWindowRange * batch.T)(*[CWindowRange(w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau) for w in ws])
+        results = np.zeros(batch.T, dtype=RESULT_DTYPE)
+        F = np.empty((batch.T, N_t0, N_tau), dtype=np.float32) if flags & WANT_FMN else None
+        rc = self.L.tcw_map_batch_windows(
+            self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
+            batch.T, batch.numDet, C.cast(cws, C.c_void_p), flags, F.ctypes.data if F is not None else None,
             results.ctypes.data,
         )
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)

@@ -62,7 +62,7 @@ struct tcw_handle {
     bool uniform = true;  // all templates share (t0_data, numAtoms)
     std::vector<TplMeta> meta;
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
-        d_flags, d_results, d_W, d_Kn, d_lut, d_flush;
+        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins;
 
     // last map
     bool have_fmn = false;
@@ -239,7 +239,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
-                      &h->d_Kn, &h->d_lut, &h->d_flush})
+                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -453,7 +453,8 @@ static size_t subbatch_bytes() {
 // host_atoms == nullptr: the atoms are resident.  Otherwise they are still on the host (pinned
 // for real overlap): the batch is cut into chunks whose H2D copies run on a second stream while
 // the previous chunk is being computed.
-static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms) {
+static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms,
+                    const tcw_window_range *per_template = nullptr) {
     if (!h) return TCW_E_INVALID;
     if (!win) return fail(h, TCW_E_INVALID, "tcw_map_resident: window range is NULL");
     if (!h->uploaded) return fail(h, TCW_E_STATE, "tcw_map_resident: no resident atoms (call tcw_upload_atoms)");
@@ -503,6 +504,31 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     g.md = make_magic(TAtom);
     g.ef = w.type == TCW_WINDOW_EXP ? TCW_EXP_EFOLDING : 1;
 
+    // ---- per-template window ranges: same type and map shape for all, generic kernels ----
+    const MapWindow *d_wins = nullptr;
+    if (per_template) {
+        if (none_window) return fail(h, TCW_E_INVALID, "per-template windows cannot be TRANSIENT_NONE");
+        std::vector<MapWindow> wins(T);
+        for (int t = 0; t < T; t++) {
+            const tcw_window_range &pw = per_template[t];
+            if (pw.type != win->type || pw.dt0 == 0 || pw.dtau == 0 || pw.t0Band / pw.dt0 + 1 != w.N_t0 ||
+                pw.tauBand / pw.dtau + 1 != w.N_tau)
+                return fail(h, TCW_E_INVALID, "per-template windows must share type and map shape (template " +
+                                                  std::to_string(t) + ")");
+            wins[t] = w;
+            wins[t].t0 = pw.t0;
+            wins[t].dt0 = pw.dt0;
+            wins[t].tau = pw.tau;
+            wins[t].dtau = pw.dtau;
+            wins[t].t0Band = pw.t0Band;
+            wins[t].tauBand = pw.tauBand;
+        }
+        int rcw = ensure(h, h->d_wins, (size_t)T * sizeof(MapWindow));
+        if (rcw) return rcw;
+        CUDA_TRY(h, cudaMemcpy(h->d_wins.p, wins.data(), (size_t)T * sizeof(MapWindow), cudaMemcpyHostToDevice));
+        d_wins = (const MapWindow *)h->d_wins.p;
+    }
+
     // ---- choose the kernels ----
     enum { PATH_GENERIC = 0, PATH_FAST = 1 };
     int path = PATH_GENERIC;
@@ -511,7 +537,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     const bool rect_track = !want_btsg;  // see LAUNCH_RECT
     bool rect_staged = false;
     ExpPlan ep;
-    if (!(flags & TCW_FORCE_GENERIC) && !none_window) {
+    if (!(flags & TCW_FORCE_GENERIC) && !none_window && !per_template) {
         if (w.type == TCW_WINDOW_RECT) {
             rect_R = (w.dt0 == w.dtau) ? 4 : 1;
             bool ok = true;
@@ -651,7 +677,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             dim3 grid((unsigned)((cells + TCW_GENERIC_THREADS - 1) / TCW_GENERIC_THREADS), 1, cnt);
 #define LAUNCH_GENERIC(WT, EX)                                                                         \
     tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                              \
-        (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, (int)none_window, g, \
+        (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins, (int)none_window, g, \
         (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
             if (w.type == TCW_WINDOW_RECT) LAUNCH_GENERIC(TCW_WINDOW_RECT, false);
             else if (exact) LAUNCH_GENERIC(TCW_WINDOW_EXP, true);
@@ -747,7 +773,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     // ---- stage 4: one result record per template ----
     tcw_finalize_kernel<<<T, TCW_FIN_THREADS, 0, st>>>(
         (const unsigned long long *)h->d_maxkey.p, (const uint32_t *)h->d_flags.p, (const double *)h->d_rowsum.p,
-        (const double *)h->d_colsum.p, (const TplMeta *)h->d_meta.p, w, (int)none_window, TAtom, (int)want_btsg,
+        (const double *)h->d_colsum.p, (const TplMeta *)h->d_meta.p, w, d_wins, (int)none_window, TAtom, (int)want_btsg,
         (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)path, (tcw_result *)h->d_results.p);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -844,6 +870,26 @@ extern "C" int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_
     int rc = upload_common(h, atoms, n_atoms, atom_stride, TAtom, T, numDet, false);
     if (rc) return rc;
     rc = map_impl(h, win, flags, atoms);
+    if (rc) return rc;
+    if (flags & TCW_WANT_FMN) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,
+                                      (size_t)h->last_pitch * sizeof(float), (size_t)h->last_N_tau * sizeof(float),
+                                      (size_t)T * h->last_N_t0, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return tcw_fetch_results(h, results);
+}
+
+extern "C" int tcw_map_batch_windows(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+                                     uint32_t atom_stride, uint32_t TAtom, int T, int numDet,
+                                     const tcw_window_range *wins, uint32_t flags, float *F_mn_out,
+                                     tcw_result *results) {
+    if (!h) return TCW_E_INVALID;
+    if (!results || !wins) return fail(h, TCW_E_INVALID, "tcw_map_batch_windows: results / wins is NULL");
+    if ((flags & TCW_WANT_FMN) && !F_mn_out)
+        return fail(h, TCW_E_INVALID, "tcw_map_batch_windows: TCW_WANT_FMN needs F_mn_out");
+    int rc = upload_common(h, atoms, n_atoms, atom_stride, TAtom, T, numDet, false);
+    if (rc) return rc;
+    rc = map_impl(h, &wins[0], flags, atoms, wins);
     if (rc) return rc;
     if (flags & TCW_WANT_FMN) {
         CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,

@@ -198,9 +198,11 @@ __device__ __forceinline__ void block_sum_argmax(const double *__restrict__ v, u
 __global__ void __launch_bounds__(TCW_FIN_THREADS)
 tcw_finalize_kernel(const unsigned long long *__restrict__ maxkey, const uint32_t *__restrict__ flags,
                     const double *__restrict__ rowsum, const double *__restrict__ colsum,
-                    const TplMeta *__restrict__ meta, MapWindow w, int none_window, uint32_t TAtom,
+                    const TplMeta *__restrict__ meta, MapWindow w, const MapWindow *__restrict__ wins, int none_window,
+                    uint32_t TAtom,
                     int want_btsg, int allow_degenerate, uint32_t path, tcw_result *__restrict__ results) {
     const int t = blockIdx.x;
+    if (wins) w = wins[t];
     __shared__ double s_tot, s_tot2;
     __shared__ uint32_t s_mMP, s_nMP;
     if (want_btsg) {

@@ -26,13 +26,16 @@ __device__ __forceinline__ double fast_neg_exp_lut(double mx, const double *__re
 template <int WTYPE, bool EXACT_EXP>
 __global__ void __launch_bounds__(TCW_GENERIC_THREADS)
 tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
-                       int t_base, MapWindow w, int none_window, IndexGeom g,
-                       const double *__restrict__ lut,
+                       int t_base, MapWindow w, const MapWindow *__restrict__ wins, int none_window,
+                       IndexGeom g, const double *__restrict__ lut,
                        float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
                        uint32_t *__restrict__ flags) {
     __shared__ unsigned long long red[TCW_GENERIC_THREADS / 32];
     const int tz = blockIdx.z;
     const int t = t_base + tz;
+    // per-template window ranges (all of one type and shape): the MCMC case, where every
+    // walker carries its own (t0, tau) (mcmc_based_searches.py:3511-3516, core.py:1447-1449)
+    if (wins) w = wins[t];
     const uint32_t numAtoms = meta[t].numAtoms;
     const uint32_t t0_data = meta[t].t0_data;
     const size_t cells = (size_t)w.N_t0 * w.N_tau;

@@ -419,3 +419,40 @@ def test_full_size_oracle_parity_rect_30d(gpu, oracle):
     assert rel.max() <= RTOL
     assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
     assert_records_match(res, 0, o, w)
+
+
+# ---- per-template windows: the MCMC case (BASELINE config 5) ---------------------------------
+
+
+@pytest.mark.parametrize("win", ["rect", "exp"])
+def test_per_template_windows_mcmc_step(gpu, oracle, win):
+    """256 walkers, each its own (tstart, duration): one tcw_map_batch_windows call == 256
+    single-cell oracle maps, bit for bit (generic kernels), incl. lnBtSG = ln 70 + F."""
+    from pyfstat_b200.mcmc import transient_detstat_batch
+
+    n, T = 480, 256
+    b = synth_atoms(T, n, ("H1", "L1"), seed=131)
+    rng = np.random.default_rng(7)
+    tstart = 10**9 + rng.uniform(0, 0.5 * n * 1800, T)
+    dur = rng.uniform(4 * 1800, 0.45 * n * 1800, T)
+    wins = [TransientWindowRange(WINDOW_T[win], int(tstart[i]), 0, 1800, int(dur[i]), 0, 1800) for i in range(T)]
+    res, F = gpu.map_batch_windows(b, wins, L.WANT_FMN | L.WANT_BTSG | L.ALLOW_DEGENERATE)
+    assert F.shape == (T, 1, 1)
+    for t in range(0, T, 7):
+        o = oracle.compute_map(b.template(t), 1800, wins[t], allow_degenerate=True)
+        assert F[t, 0, 0] == np.float32(o["F_mn"][0, 0])
+        assert float(res["lnBtSG"][t]) == pytest.approx(math.log(70.0) + o["maxF"], abs=1e-9)
+        assert (int(res["t0_ML"][t]), int(res["tau_ML"][t])) == (wins[t].t0, wins[t].tau)
+    # the sampler-facing helper: -inf beyond maxStartTime, 2F otherwise
+    maxStart = 10**9 + 0.8 * n * 1800
+    det, rec = transient_detstat_batch(b, tstart, tstart + dur, win, maxStartTime=maxStart)
+    bad = tstart + dur > maxStart
+    assert bad.any() and np.all(np.isinf(det[bad])) and np.all(np.isfinite(det[~bad]))
+    assert np.allclose(det[~bad], 2.0 * F[~bad, 0, 0], rtol=0, atol=0)
+    # mixed shapes are rejected
+    wins[3] = TransientWindowRange(WINDOW_T[win], int(tstart[3]), 1800, 1800, int(dur[3]), 0, 1800)
+    with pytest.raises(L.TcwError):
+        gpu.map_batch_windows(b, wins, 0)
+
+
+WINDOW_T = {"rect": 1, "exp": 2}

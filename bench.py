@@ -414,6 +414,7 @@ def run_gpu(args):
         }
         if not args.no_secondary and args.workload == "exp30":
             line["rect"] = secondary_rect(h, L, hbm_peak, hbm_src)
+            line["mcmc"] = secondary_mcmc(h, L)
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_single_thread(spec)
         sys.stdout.flush()
@@ -462,6 +463,32 @@ def secondary_rect(h, L, hbm_peak, hbm_src):
     out["e2e_btsg"] = {"cells_per_s": T * spec["cells"] / statistics.mean(times), "ms_per_step": 1e3 * statistics.mean(times),
                        "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(T * L.RESULT_DTYPE.itemsize)}
     out["config"] = workload_config(spec)
+    return out
+
+
+def secondary_mcmc(h, L):
+    """BASELINE configs[4] shape: one sampler step = 256 walkers, each a 1x1 map with its own
+    (tstart, duration) on 30 d of H1+L1 atoms, through tcw_map_batch_windows (host atoms in,
+    records out).  Reports per-step latency and templates/s for both windows."""
+    from pyfstat_b200.atoms import synth_atoms
+    from pyfstat_b200.window import TransientWindowRange
+
+    T, n = 256, 1440
+    alloc = L.pinned_atoms_alloc()
+    batch = synth_atoms(T, n, ("H1", "L1"), seed=5000, t0_data=T0_DATA, TAtom=TATOM, pinned_alloc=alloc)
+    rng = np.random.default_rng(5)
+    tstart = T0_DATA + rng.uniform(0, 0.5 * n * TATOM, T)
+    dur = rng.uniform(4 * TATOM, 0.45 * n * TATOM, T)
+    out = {"walkers_per_step": T, "atoms_per_detector": n, "api": "tcw_map_batch_windows (C ABI), pinned host atoms"}
+    for name, wt in (("rect", 1), ("exp", 2)):
+        wins = [TransientWindowRange(wt, int(tstart[i]), 0, TATOM, int(dur[i]), 0, TATOM) for i in range(T)]
+        times = []
+        for i in range(13):
+            t0 = time.perf_counter()
+            h.map_batch_windows(batch, wins, L.ALLOW_DEGENERATE)
+            if i >= 3:
+                times.append(time.perf_counter() - t0)
+        out[name] = {"ms_per_step": 1e3 * statistics.mean(times), "templates_per_s": T / statistics.mean(times)}
     return out
 
 

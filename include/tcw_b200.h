@@ -192,6 +192,8 @@ int tcw_flush_l2(tcw_handle *h);
 /* FP32-FMA / FP64-add peak microbenchmarks on this device (TFLOP/s, counting FMA = 2 flop,
  * DADD = 1 flop): the roofline denominators MEASURED_PEAKS.json does not carry. */
 int tcw_microbench(tcw_handle *h, double *ffma_tflops, double *dadd_tflops);
+/* Same for Blackwell's packed FP32 FMA (fma.rn.f32x2 / SASS FFMA2), counting 4 flop per lane-instruction. */
+int tcw_microbench_ffma2(tcw_handle *h, double *ffma2_tflops);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void *tcw_host_alloc(uint64_t bytes);
 void tcw_host_free(void *p);

@@ -33,7 +33,8 @@ EXPORTED_SYMBOLS = (
     "tcw_abi_version", "tcw_create", "tcw_destroy", "tcw_last_error", "tcw_device_name",
     "tcw_map_dims", "tcw_map_batch", "tcw_map_batch_windows", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
     "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
-    "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_host_alloc",
+    "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
+    "tcw_host_alloc",
     "tcw_host_free", "tcw_cell_index_range",
 )
 
@@ -132,6 +133,7 @@ def load_library(build_if_missing: bool = True):
     L.tcw_launch_count.restype = C.c_uint64
     L.tcw_flush_l2.argtypes = [vp]
     L.tcw_microbench.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tcw_microbench_ffma2.argtypes = [vp, C.POINTER(C.c_double)]
     L.tcw_host_alloc.argtypes = [C.c_uint64]
     L.tcw_host_alloc.restype = vp
     L.tcw_host_free.argtypes = [vp]
@@ -315,7 +317,9 @@ class Handle:
     def microbench(self):
         a, b = C.c_double(), C.c_double()
         self._check(self.L.tcw_microbench(self._h, C.byref(a), C.byref(b)))
-        return {"ffma_tflops": a.value, "dadd_tflops": b.value}
+        c = C.c_double()
+        self._check(self.L.tcw_microbench_ffma2(self._h, C.byref(c)))
+        return {"ffma_tflops": a.value, "dadd_tflops": b.value, "ffma2_tflops": c.value}
 
 
 def pinned_atoms_alloc():

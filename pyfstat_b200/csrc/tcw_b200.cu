@@ -935,6 +935,43 @@ __global__ void tcw_dadd_peak_kernel(double *out, int iters) {
     if (s == 123.456) out[0] = s;
 }
 
+// packed FP32 (Blackwell FFMA2: two FMAs per lane per instruction)
+__global__ void tcw_ffma2_peak_kernel(float *out, int iters) {
+    float2 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f + i);
+    const float2 b = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-7f, -1e-7f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __ffma2_rn(a[i], b, c);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i].x + a[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+
+extern "C" int tcw_microbench_ffma2(tcw_handle *h, double *ffma2_tflops) {
+    if (!h || !ffma2_tflops) return TCW_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure(h, h->d_scratch, 1024);
+    if (rc) return rc;
+    const int blocks = h->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float ms = 0;
+    for (int rep = 0; rep < 2; rep++) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[0], h->stream));
+        tcw_ffma2_peak_kernel<<<blocks, threads, 0, h->stream>>>((float *)h->d_scratch.p, iters);
+        CUDA_TRY(h, cudaEventRecord(h->ev_timer[1], h->stream));
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_timer[1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]));
+    }
+    *ffma2_tflops = 4.0 * 64.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    h->launches += 2;
+    return TCW_OK;
+}
+
 extern "C" int tcw_microbench(tcw_handle *h, double *ffma_tflops, double *dadd_tflops) {
     if (!h || !ffma_tflops || !dadd_tflops) return TCW_E_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));

@@ -129,13 +129,15 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         for (int c = 0; c < TCW_EXP_STAGES - 1 && c < nchunks; c++) issue(c);
     }
 
-    float acc[TCW_NCH][RM][RN];
+    // accumulators are pairs of adjacent tau columns: one FFMA2 (fma.rn.f32x2, Blackwell packed
+    // FP32) updates two cells, halving the issue slots of the inner loop
+    float2 acc[TCW_NCH][RM][RN / 2];
 #pragma unroll
     for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
         for (int r = 0; r < RM; r++)
 #pragma unroll
-            for (int j = 0; j < RN; j++) acc[c][r][j] = 0.0f;
+            for (int j = 0; j < RN / 2; j++) acc[c][r][j] = make_float2(0.0f, 0.0f);
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
         // refill the stage consumed in the previous iteration (all threads passed its sync)
@@ -166,24 +168,25 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
                     xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
                     xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
                 }
-                float w1[RN], w2[RN];
+                float2 w1[RN / 2], w2[RN / 2];
                 if (RN == 4) {
                     const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
-                    w1[0] = wv.x; w1[1] = wv.y; w1[RN - 2] = wv.z; w1[RN - 1] = wv.w;
+                    w1[0] = make_float2(wv.x, wv.y);
+                    w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
                 } else {
-                    const float2 wv = *reinterpret_cast<const float2 *>(wrow + k * TN);
-                    w1[0] = wv.x; w1[1] = wv.y;
+                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
                 }
 #pragma unroll
-                for (int j = 0; j < RN; j++) w2[j] = w1[j] * w1[j];
+                for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
 #pragma unroll
                 for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
                     for (int r = 0; r < RM; r++) {
                         const float xv = xr[c][(u + r) & 3];
+                        const float2 xx = make_float2(xv, xv);
 #pragma unroll
-                        for (int j = 0; j < RN; j++)
-                            acc[c][r][j] = fmaf(xv, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
+                        for (int j = 0; j < RN / 2; j++)
+                            acc[c][r][j] = __ffma2_rn(xx, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
                     }
             }
         }
@@ -202,8 +205,9 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         for (int j = 0; j < RN; j++) {
             const uint32_t n = n0 + tn * RN + j;
             if (m < w.N_t0 && n < w.N_tau) {
-                const float F = fstat_fast(acc[0][r][j], acc[1][r][j], acc[2][r][j], acc[3][r][j],
-                                           acc[4][r][j], acc[5][r][j], acc[6][r][j]);
+#define ACC(c_) ((j & 1) ? acc[c_][r][j >> 1].y : acc[c_][r][j >> 1].x)
+                const float F = fstat_fast(ACC(0), ACC(1), ACC(2), ACC(3), ACC(4), ACC(5), ACC(6));
+#undef ACC
                 const uint32_t flat = m * w.N_tau + n;
                 if (Ft) Ft[(size_t)m * w.pitch + n] = F;
                 if (F > best) {

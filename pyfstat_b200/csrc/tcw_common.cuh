@@ -228,4 +228,69 @@ __device__ __forceinline__ float fstat_fast(float Ad, float Bd, float Cd, float 
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdet) : "f"(det));
     return ok ? num * rdet : 2.0f;
 }
+
+// ---------------------------------------------------------------------------------------
+// Blackwell packed FP32 (add/mul/fma.rn.f32x2 -> SASS FADD2/FMUL2/FFMA2: two results per issue
+// slot).  Pairs are kept in 64-bit registers through inline PTX: with the float2 intrinsics
+// nvcc re-assembles loop-invariant pairs from scalar registers before every use (2 MOVs per
+// packed instruction in the rect kernel's hot loop).
+// ---------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// fstat_fast for TWO cells at once (the rectangular-window kernel is instruction-issue-bound):
+// 16 packed instructions + 2 MUFU.RCP + 2 compares/selects per pair.
+struct FstatConst2 {
+    f32x2 neg_kappa, neg_two, neg_one;
+};
+__device__ __forceinline__ FstatConst2 fstat_const2() {
+    constexpr float kK = 9999.0f / 10001.0f;
+    constexpr float kKappa = (1.0f - kK * kK) * 0.25f;
+    FstatConst2 k;
+    k.neg_kappa = pack2(-kKappa, -kKappa);
+    k.neg_two = pack2(-2.0f, -2.0f);
+    k.neg_one = pack2(-1.0f, -1.0f);
+    return k;
+}
+__device__ __forceinline__ void fstat_fast2(const FstatConst2 &k, f32x2 Ad, f32x2 Bd, f32x2 Cd, f32x2 Fa_re,
+                                            f32x2 Fa_im, f32x2 Fb_re, f32x2 Fb_im, float &F0, float &F1) {
+    const f32x2 sumAB = add2(Ad, Bd);
+    const f32x2 det = fma2(mul2(Cd, k.neg_one), Cd, mul2(Ad, Bd));     // AB - C^2
+    const f32x2 margin = fma2(mul2(sumAB, k.neg_kappa), sumAB, det);    // det - kappa s^2
+    const f32x2 fa2 = fma2(Fa_re, Fa_re, mul2(Fa_im, Fa_im));
+    const f32x2 fb2 = fma2(Fb_re, Fb_re, mul2(Fb_im, Fb_im));
+    const f32x2 re = fma2(Fa_re, Fb_re, mul2(Fa_im, Fb_im));
+    const f32x2 num = fma2(Bd, fa2, fma2(mul2(Cd, re), k.neg_two, mul2(Ad, fb2)));
+    float d0, d1, m0, m1, r0, r1;
+    unpack2(det, d0, d1);
+    unpack2(margin, m0, m1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    float f0, f1;
+    unpack2(mul2(num, pack2(r0, r1)), f0, f1);
+    F0 = m0 > 0.0f ? f0 : 2.0f;
+    F1 = m1 > 0.0f ? f1 : 2.0f;
+}
 #endif  // __CUDACC__

@@ -55,7 +55,7 @@
 #define TCW_RECT_SMEM_E (TCW_RECT_UCAP * 4)
 #define TCW_RECT_SMEM_S (TCW_RECT_MAXROWS * 4)
 #define TCW_RECT_SMEM_R (TCW_RECT_MAXROWS * 8 * 4)
-#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_Q + TCW_RECT_SMEM_E + TCW_RECT_SMEM_S + TCW_RECT_SMEM_R)
+#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_E + TCW_RECT_SMEM_S + TCW_RECT_SMEM_R)
 
 // Fast body of one warp: R rows x (32 * n_j) values of d, split-point FP32 sums.
 //   CHECKED = false: every (row, d) is a valid cell (off-diagonal tiles have no degenerate cell).
@@ -63,10 +63,11 @@
 //             locates the first cell equal to the final max), saving 2 instructions per cell.
 template <int R, bool CHECKED, bool STORE, bool TRACK>
 __device__ __forceinline__ void rect_rows_fp32(
-    const float *__restrict__ sQ, const uint32_t *__restrict__ sE, const float (&Rs)[R][TCW_NCH],
+    const f32x2 *__restrict__ sQ2, const uint32_t *__restrict__ sE, const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH],
     float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int j_begin, int j_end,
     uint32_t lane, uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0,
     uint32_t t0_data, uint32_t numAtoms, const IndexGeom g, float (&best)[R], uint32_t (&best_d)[R]) {
+    const FstatConst2 kc = fstat_const2();
 #pragma unroll 4
     for (int j = j_begin; j < j_end; j++) {
         const uint32_t d = d0 + lane + 32u * j;
@@ -78,13 +79,33 @@ __device__ __forceinline__ void rect_rows_fp32(
             idx = min(index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1 - a0,
                       (uint32_t)(TCW_RECT_ECAP - 1));
         }
-        float Q[TCW_NCH];
+        f32x2 Q2[TCW_NCH];  // {q, q}: stored duplicated so that the packed adds need no register shuffling
 #pragma unroll
-        for (int c = 0; c < TCW_NCH; c++) Q[c] = sQ[c * TCW_RECT_ECAP + idx];
+        for (int c = 0; c < TCW_NCH; c++) Q2[c] = sQ2[c * TCW_RECT_ECAP + idx];
+        // rows in pairs: both cells share Q (same end index), so every FP32 operation of the
+        // pair is one packed instruction (FADD2 with Q broadcast, then fstat_fast2)
+        float Fr[R];
+        if (R % 2 == 0) {
+#pragma unroll
+            for (int rp = 0; rp < R / 2; rp++) {
+                f32x2 S[TCW_NCH];
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++) S[c] = add2(Q2[c], Rs2[rp][c]);
+                fstat_fast2(kc, S[0], S[1], S[2], S[3], S[4], S[5], S[6], Fr[2 * rp], Fr[2 * rp + (R > 1 ? 1 : 0)]);
+            }
+        } else {
+            float lo[TCW_NCH], q[TCW_NCH], hi;
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) {
+                unpack2(Rs2[0][c], lo[c], hi);
+                unpack2(Q2[c], q[c], hi);
+            }
+            Fr[0] = fstat_fast(q[0] + lo[0], q[1] + lo[1], q[2] + lo[2], q[3] + lo[3], q[4] + lo[4], q[5] + lo[5],
+                               q[6] + lo[6]);
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float F = fstat_fast(Q[0] + Rs[r][0], Q[1] + Rs[r][1], Q[2] + Rs[r][2], Q[3] + Rs[r][3],
-                                       Q[4] + Rs[r][4], Q[5] + Rs[r][5], Q[6] + Rs[r][6]);
+            const float F = Fr[r];
             bool valid = true;
             if (CHECKED) valid = rowok[r] && (d - r) < N_tau;  // d - r wraps for d < r
             if (valid) {
@@ -160,14 +181,13 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
     unsigned char *sp = tcw_rect_smem;
     double *sP = reinterpret_cast<double *>(sp);        // [7][ECAP]  staged FP64 end prefixes
+    f32x2 *sQ2 = reinterpret_cast<f32x2 *>(sp);         // [7][ECAP]  {q, q}, q = fl32(P[i] - P[rho]): IN PLACE over sP
     sp += TCW_RECT_SMEM_P;
-    float *sQ = reinterpret_cast<float *>(sp);          // [7][ECAP]  fl32(P[i] - P[rho])
-    sp += TCW_RECT_SMEM_Q;
     uint32_t *sE = reinterpret_cast<uint32_t *>(sp);    // [UCAP]     end index (rel. to slice) per u
     sp += TCW_RECT_SMEM_E;
     uint32_t *sS = reinterpret_cast<uint32_t *>(sp);    // [ROWS]     start index i_t0 per row
     sp += TCW_RECT_SMEM_S;
-    float *sR = reinterpret_cast<float *>(sp);          // [ROWS][8]  fl32(P[rho] - P[s]) per row
+    float *sR = reinterpret_cast<float *>(sp);          // [ROWS/2][8][2]  fl32(P[rho] - P[s]), row pairs interleaved
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long red[TCW_RECT_WARPS];
 
@@ -228,19 +248,26 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     __syncthreads();  // sE, sS visible; mbarrier init visible to all waiters
     if (STAGED) mbar_wait(&bar, 0);
     if (offdiag) {
-        // sQ[c][i] = fl32(P_c[a0+i] - P_c[rho]) for the staged slice (7 channels of an entry per thread)
+        // off-diagonal tiles no longer need the FP64 slice itself: convert it IN PLACE to
+        // {q, q} pairs, q = fl32(P_c[a0+i] - P_c[rho]) (each thread rewrites only the 8-byte slots
+        // it read), after everyone has fetched P[rho] and the per-row terms fl32(P[rho] - P[s])
         double pref[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) pref[c] = sP[c * TCW_RECT_ECAP];
-        for (uint32_t i = threadIdx.x; i < cnt; i += TCW_RECT_THREADS) {
-#pragma unroll
-            for (int c = 0; c < TCW_NCH; c++)
-                sQ[c * TCW_RECT_ECAP + i] = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]);
-        }
-        // sR[row][c] = fl32(P_c[rho] - P_c[s_row])
         for (uint32_t i = threadIdx.x; i < ROWS * 8; i += TCW_RECT_THREADS) {
             const uint32_t row = i >> 3, c = i & 7;
-            if (c < TCW_NCH) sR[i] = (float)(sP[c * TCW_RECT_ECAP] - __ldg(Pt + (size_t)c * ppad + sS[row]));
+            // stored as row PAIRS {row 2p, row 2p+1} per channel: a 64-bit load yields a packed operand
+            if (c < TCW_NCH)
+                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] =
+                    (float)(sP[c * TCW_RECT_ECAP] - __ldg(Pt + (size_t)c * ppad + sS[row]));
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += TCW_RECT_THREADS) {
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) {
+                const float q = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]);
+                sQ2[c * TCW_RECT_ECAP + i] = pack2(q, q);
+            }
         }
         __syncthreads();
     }
@@ -272,16 +299,23 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
             rowp[r] = Ft ? Ft + ((size_t)mc * w.pitch + d0 + lane) - r : nullptr;
         }
         if (offdiag) {
-            float Rs[R][TCW_NCH];
+            f32x2 Rs2[(R + 1) / 2][TCW_NCH];  // {row 2rp, row 2rp+1} pairs of fl32(P[rho] - P[s])
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const float4 lo = *reinterpret_cast<const float4 *>(sR + (grow + r) * 8);
-                const float4 hi = *reinterpret_cast<const float4 *>(sR + (grow + r) * 8 + 4);
-                Rs[r][0] = lo.x; Rs[r][1] = lo.y; Rs[r][2] = lo.z; Rs[r][3] = lo.w;
-                Rs[r][4] = hi.x; Rs[r][5] = hi.y; Rs[r][6] = hi.z;
+            for (int rp = 0; rp < (R + 1) / 2; rp++) {
+                const f32x2 *pr = reinterpret_cast<const f32x2 *>(sR) + ((grow >> 1) + rp) * 8;
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++) Rs2[rp][c] = pr[c];
+                if (R == 1 && (grow & 1)) {  // odd single row: its value sits in the high half
+#pragma unroll
+                    for (int c = 0; c < TCW_NCH; c++) {
+                        float lo, hi;
+                        unpack2(Rs2[rp][c], lo, hi);
+                        Rs2[rp][c] = pack2(hi, hi);
+                    }
+                }
             }
 #define RECT_FAST(CHK_, STORE_, J0_, J1_)                                                                       \
-    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ, sE, Rs, rowp, rowok, u_off, d0, J0_, J1_, lane, w.N_tau, d_total, \
+    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ2, sE, Rs2, rowp, rowok, u_off, d0, J0_, J1_, lane, w.N_tau, d_total, \
                                            t1_lane, t1_step, a0, t0_data, numAtoms, g, best, best_d)
             if (edge_rows) {
                 if (Ft) RECT_FAST(true, true, 0, n_j);

@@ -710,13 +710,15 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             }
             const uint32_t DD = rect_DD;
             const uint32_t d_total = w.N_tau + rect_R - 1;
+            // regular tiles: as few as the staging capacity allows, evenly sized (multiple of 32)
             const uint32_t n_reg = d_total > DD ? (d_total - DD + TCW_RECT_DT - 1) / TCW_RECT_DT : 0;
+            const uint32_t DT = n_reg ? (((d_total - DD + n_reg - 1) / n_reg) + 31u) & ~31u : 32u;
             dim3 grid(1 + n_reg, n_gy, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
 #define LAUNCH_RECT(RR, STG, TRK)                                                                   \
     tcw_rect_map_kernel<RR, STG, TRK><<<grid, TCW_RECT_THREADS, smem, st>>>(                        \
-        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, fmn,     \
+        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, fmn, \
         (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
             // with a following lnBtSG pass the map kernel only tracks max VALUES; the pass
             // locates the first cell attaining the final max while it re-reads F_mn anyway

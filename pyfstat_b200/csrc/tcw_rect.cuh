@@ -44,8 +44,8 @@
 
 #define TCW_RECT_THREADS 256
 #define TCW_RECT_WARPS (TCW_RECT_THREADS / 32)
-#define TCW_RECT_DT 512    // d values per regular tile (16 per lane)
-#define TCW_RECT_ECAP 640  // staged end-prefix entries per channel (even)
+#define TCW_RECT_DT 1024   // max d values per regular tile (the launch picks DT <= this, a multiple of 32)
+#define TCW_RECT_ECAP 1100 // staged end-prefix entries per channel (even)
 #define TCW_RECT_G 2       // row groups per warp (a tile has 8 warps x G groups x R rows)
 #define TCW_RECT_ROWS(R) (TCW_RECT_WARPS * TCW_RECT_G * (R))
 #define TCW_RECT_MAXROWS (TCW_RECT_WARPS * TCW_RECT_G * 4)
@@ -169,14 +169,15 @@ __device__ __noinline__ RectRowResult rect_row_fp64(
     return out;
 }
 
-// grid: x = d tiles: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT)
+// grid: x = d tiles: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT),
+//           DT chosen by the host so that the regular tiles divide the map evenly
 //       y = tiles of 8 warps x G row groups, z = template in sub-batch
 // TRACK = false (only with a following lnBtSG pass over a stored F_mn): publish max values
 // only; tcw_btsg_kernel completes the key with the first flat index that attains the max.
 template <int R, bool STAGED, bool TRACK>
 __global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
 tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
-                    int t_base, MapWindow w, IndexGeom g, uint32_t DD, float *__restrict__ Fmn,
+                    int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, float *__restrict__ Fmn,
                     unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
     unsigned char *sp = tcw_rect_smem;
@@ -202,8 +203,8 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const uint32_t d_total = w.N_tau + R - 1;
     const uint32_t m0 = blockIdx.y * ROWS;
     const uint32_t m_last = min(m0 + ROWS, w.N_t0) - 1;
-    const uint32_t d0 = blockIdx.x == 0 ? 0u : DD + (blockIdx.x - 1) * TCW_RECT_DT;
-    const uint32_t d_cnt = blockIdx.x == 0 ? DD : (uint32_t)TCW_RECT_DT;
+    const uint32_t d0 = blockIdx.x == 0 ? 0u : DD + (blockIdx.x - 1) * DT;
+    const uint32_t d_cnt = blockIdx.x == 0 ? DD : DT;
     const uint32_t d_last = min(d0 + d_cnt, d_total) - 1;
     const bool edge_rows = (d0 < (uint32_t)(R - 1)) || (m0 + ROWS > w.N_t0);  // head strip / bottom row tile
 
@@ -239,6 +240,18 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
         const uint32_t m = min(m0 + threadIdx.x, w.N_t0 - 1);
         sS[threadIdx.x] = index_t0(w.t0 + m * w.dt0, t0_data, numAtoms, g);
     }
+    // start prefixes P_c[s_row] for the per-row terms: fetched now, while the bulk copies fly
+    double ps_early[(ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS];
+#pragma unroll
+    for (int k = 0; k < (int)((ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS); k++) {
+        const uint32_t i = threadIdx.x + k * TCW_RECT_THREADS;
+        const uint32_t row = i >> 3, c = i & 7;
+        ps_early[k] = 0.0;
+        if (i < ROWS * 8 && c < TCW_NCH) {
+            const uint32_t m = min(m0 + row, w.N_t0 - 1);
+            ps_early[k] = __ldg(Pt + (size_t)c * ppad + index_t0(w.t0 + m * w.dt0, t0_data, numAtoms, g));
+        }
+    }
     const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, t0_data, numAtoms, g);
     // off-diagonal: the split point rho = a0 lies strictly inside every window of the tile,
     // s < rho <= e + 1 with e > s (so no cell of the tile is degenerate): rho >= s_hi + 2
@@ -254,12 +267,13 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
         double pref[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) pref[c] = sP[c * TCW_RECT_ECAP];
-        for (uint32_t i = threadIdx.x; i < ROWS * 8; i += TCW_RECT_THREADS) {
+#pragma unroll
+        for (int k = 0; k < (int)((ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS); k++) {
+            const uint32_t i = threadIdx.x + k * TCW_RECT_THREADS;
             const uint32_t row = i >> 3, c = i & 7;
             // stored as row PAIRS {row 2p, row 2p+1} per channel: a 64-bit load yields a packed operand
-            if (c < TCW_NCH)
-                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] =
-                    (float)(sP[c * TCW_RECT_ECAP] - __ldg(Pt + (size_t)c * ppad + sS[row]));
+            if (i < ROWS * 8 && c < TCW_NCH)
+                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] = (float)(sP[c * TCW_RECT_ECAP] - ps_early[k]);
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < cnt; i += TCW_RECT_THREADS) {

@@ -71,6 +71,19 @@ def workload_spec(name):
     return spec
 
 
+def measured_traffic(name, T):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if it was
+    taken at this launch shape (profiles/r01_traffic.json); else None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(p)).get(name)
+        if d and d["templates_per_launch"] == T:
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -372,7 +385,7 @@ def run_gpu(args):
             roofline = {
                 "bound": "fp32", "kernel": "tcw_exp_map_kernel", "achieved": achieved,
                 "peak": peaks["ffma_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["ffma_tflops"],
-                "traffic": None,
+                "traffic": measured_traffic(spec["name"], T),
                 "peak_source": ("FFMA microbenchmark run by this bench on this GPU (tcw_microbench; nominal 74.4 = "
                                 "148 SM x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json carries no FP32 SIMT peak. "
                                 "Not HBM- or tensor-bound: SURVEY 8(d) puts the exponential window on the FP32 FMA pipe"),
@@ -451,7 +464,9 @@ def secondary_rect(h, L, hbm_peak, hbm_src):
         }
         if flags & L.WANT_FMN:
             out[name]["roofline"] = {"bound": "hbm", "kernel": "tcw_rect_map_kernel", "achieved": gbs, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                     "unit": "GB/s", "frac": gbs / hbm_peak,
+                                     "traffic": measured_traffic("rect60", T) if name == "fmn" else None,
+                                     "peak_source": hbm_src,
                                      "algorithmic_bytes_per_template": spec["alg_bytes"]}
     # end to end through tcw_map_batch (pinned host atoms -> records), lnBtSG on, no F_mn copy
     times = []

@@ -557,8 +557,11 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     // ---- buffers ----
     int rc;
     if ((rc = ensure(h, h->d_X, (size_t)T * TCW_NCH * h->xpad * sizeof(float)))) return rc;
-    if ((rc = ensure(h, h->d_X8, (size_t)T * 8 * h->xpad * sizeof(float)))) return rc;
-    if ((rc = ensure(h, h->d_P, (size_t)T * TCW_NCH * h->ppad * sizeof(double)))) return rc;
+    // the atom-interleaved copy only feeds the tiled exp kernel, the prefix sums only the tiled rect kernel
+    const bool need_X8 = path == PATH_FAST && w.type == TCW_WINDOW_EXP;
+    const bool need_P = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
+    if (need_X8 && (rc = ensure(h, h->d_X8, (size_t)T * 8 * h->xpad * sizeof(float)))) return rc;
+    if (need_P && (rc = ensure(h, h->d_P, (size_t)T * TCW_NCH * h->ppad * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->d_maxkey, (size_t)T * sizeof(unsigned long long)))) return rc;
     if ((rc = ensure(h, h->d_flags, (size_t)T * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(h, h->d_results, (size_t)T * sizeof(tcw_result)))) return rc;
@@ -666,8 +669,8 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         // merge detectors, transpose to channels, FP64 prefix scan
         tcw_prep_kernel<<<cnt, TCW_PREP_THREADS, 0, st>>>(
             (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p, t_base,
-            h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, (float *)h->d_X8.p, h->xpad, (double *)h->d_P.p,
-            h->ppad, (uint32_t *)h->d_flags.p);
+            h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, need_X8 ? (float *)h->d_X8.p : nullptr, h->xpad,
+            need_P ? (double *)h->d_P.p : nullptr, h->ppad, (uint32_t *)h->d_flags.p);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
         if (sb == 0) CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));

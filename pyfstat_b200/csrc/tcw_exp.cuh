@@ -30,7 +30,7 @@
 #include "tcw_generic.cuh"
 #include "tcw_prep.cuh"
 
-#define TCW_EXP_KC 32      // k-steps per staged chunk
+#define TCW_EXP_KC 32      // k-steps per staged chunk (64: -2% at 30 d with FFMA2)
 #define TCW_EXP_STAGES 3
 #define TCW_EXP_TNT 16     // threads along tau per CTA (fixed); a warp = 2 (t0) x 16 (tau) threads
 

@@ -8,7 +8,7 @@
 // floor((t_Xi - tMin)/TAtom); the 7 quantities are summed in float32 in detector order;
 // empty bins stay zero.  One CTA per template.
 //
-// Outputs (both zero padded):
+// Outputs (zero padded; X8 and P are optional -- nullptr skips them):
 //   X[t][c][xpad] float32  merged channel c (SoA)  -- generic kernels, tcw_fetch_merged
 //   X8[t][xpad][8] float32 merged atoms, channel-interleaved (7 + pad) -- exp window kernel
 //   P[t][c][ppad] float64  exclusive prefix: P[i] = sum_{j<i} X[j], P[0] = 0, i <= numAtoms
@@ -30,7 +30,7 @@ tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__
     const uint32_t tMin = meta[t].t0_data;
     const int tid = threadIdx.x;
     float *Xt = X + (size_t)t * TCW_NCH * xpad;
-    double *Pt = P + (size_t)t * TCW_NCH * ppad;
+    double *Pt = P ? P + (size_t)t * TCW_NCH * ppad : nullptr;
     const tcw_atom *At = atoms + (size_t)t * numDet * stride;
     const uint32_t *nt = n_atoms + (size_t)t * numDet;
 
@@ -78,10 +78,13 @@ tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) Xt[(size_t)c * xpad + j] = s[c];
         // atom-interleaved copy for the exponential-window kernel: one 32-byte record per atom
-        float4 *x8 = reinterpret_cast<float4 *>(X8 + ((size_t)t * xpad + j) * 8);
-        x8[0] = make_float4(s[0], s[1], s[2], s[3]);
-        x8[1] = make_float4(s[4], s[5], s[6], 0.0f);
+        if (X8) {
+            float4 *x8 = reinterpret_cast<float4 *>(X8 + ((size_t)t * xpad + j) * 8);
+            x8[0] = make_float4(s[0], s[1], s[2], s[3]);
+            x8[1] = make_float4(s[4], s[5], s[6], 0.0f);
+        }
     }
+    if (!P) return;  // prefix sums are only needed by the rectangular-window kernel
     __syncthreads();
 
     // FP64 exclusive prefix scan per channel: each thread owns a contiguous chunk, chunk

@@ -62,7 +62,7 @@ struct tcw_handle {
     bool uniform = true;  // all templates share (t0_data, numAtoms)
     std::vector<TplMeta> meta;
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
-        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins;
+        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins, d_tilemax;
 
     // last map
     bool have_fmn = false;
@@ -202,17 +202,15 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     }
     CUDA_TRY(nullptr, cudaMemcpy(h->d_lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
     // opt in to large dynamic shared memory once
-#define RECT_ATTR(RR, STG, TRK)                                                                     \
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<RR, STG, TRK>,                        \
+#define RECT_ATTR(RR, STG)                                                                              \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<RR, STG>,                                 \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_RECT_SMEM)); \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_locate_kernel<RR, STG>,                              \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, TCW_RECT_SMEM))
-    RECT_ATTR(4, true, true);
-    RECT_ATTR(4, true, false);
-    RECT_ATTR(4, false, true);
-    RECT_ATTR(4, false, false);
-    RECT_ATTR(1, true, true);
-    RECT_ATTR(1, true, false);
-    RECT_ATTR(1, false, true);
-    RECT_ATTR(1, false, false);
+    RECT_ATTR(4, true);
+    RECT_ATTR(4, false);
+    RECT_ATTR(1, true);
+    RECT_ATTR(1, false);
 #undef RECT_ATTR
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ExpCfgA::kSmem));
@@ -239,7 +237,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
-                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins})
+                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins, &h->d_tilemax})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -533,20 +531,46 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     enum { PATH_GENERIC = 0, PATH_FAST = 1 };
     int path = PATH_GENERIC;
     int rect_R = 1;
-    uint32_t rect_DD = 32;
-    const bool rect_track = !want_btsg;  // see LAUNCH_RECT
+    uint32_t rect_DD = 32, rect_G = 1, rect_DTcap = 32;
     bool rect_staged = false;
     ExpPlan ep;
     if (!(flags & TCW_FORCE_GENERIC) && !none_window && !per_template) {
         if (w.type == TCW_WINDOW_RECT) {
-            rect_R = (w.dt0 == w.dtau) ? 4 : 1;
+            // R = 4 rows per thread share an end index when dt0 == dtau; the diagonal tiles' per-group
+            // split point (tcw_rect.cuh) additionally wants windows at least one row step long
+            rect_R = (w.dt0 == w.dtau && w.tau >= w.dtau) ? 4 : 1;
             bool ok = true;
             for (int t = 0; t < T && ok; t++) ok = no_wrap(w, 1, rect_R - 1, h->meta[t], TAtom);
             if (ok) {
                 path = PATH_FAST;
-                const uint64_t span = ((uint64_t)(TCW_RECT_WARPS * TCW_RECT_G * rect_R - 1) * w.dt0 +
-                                       (uint64_t)(TCW_RECT_DT - 1) * w.dtau) / TAtom + 6;
-                rect_staged = span <= TCW_RECT_ECAP;
+                // row groups per warp: tall tiles amortise the per-tile staging, but a small batch
+                // needs enough tiles to fill the GPU
+                const uint64_t rows1 = (uint64_t)TCW_RECT_WARPS * rect_R;
+                rect_G = 1;
+                if (const char *env = getenv("TCW_RECT_G")) {
+                    rect_G = (uint32_t)std::min(std::max(atoi(env), 1), rect_R == 4 ? TCW_RECT_GMAX : 2);
+                } else {
+                    const uint32_t g_max = rect_R == 4 ? TCW_RECT_GMAX : 2;
+                    const uint64_t slots = (uint64_t)h->prop.multiProcessorCount * 3 * 4;  // >= 4 waves
+                    for (uint32_t gc = g_max; gc >= 1; gc /= 2) {
+                        rect_G = gc;
+                        const uint64_t tiles = (uint64_t)T * ((w.N_t0 + rows1 * gc - 1) / (rows1 * gc)) *
+                                               ((w.N_tau + TCW_RECT_DT - 1) / TCW_RECT_DT + 1);
+                        if (tiles >= slots) break;
+                    }
+                }
+                // widest regular tile whose end indices still fit the staged slice
+                const uint64_t rows = rows1 * rect_G;
+                rect_staged = false;
+                for (uint32_t dt = TCW_RECT_DT; dt >= 64; dt -= 32) {
+                    const uint64_t span = ((rows - 1) * w.dt0 + (uint64_t)(dt - 1) * w.dtau) / TAtom + 6;
+                    if (span <= TCW_RECT_ECAP) {
+                        rect_staged = true;
+                        rect_DTcap = dt;
+                        break;
+                    }
+                }
+                if (!rect_staged) rect_DTcap = TCW_RECT_DT;
             }
         } else {
             ep = plan_exp(h, w);
@@ -687,7 +711,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);
 #undef LAUNCH_GENERIC
         } else if (w.type == TCW_WINDOW_RECT) {
-            const uint32_t rows_per_tile = TCW_RECT_WARPS * TCW_RECT_G * rect_R;
+            const uint32_t rows_per_tile = TCW_RECT_WARPS * rect_G * rect_R;
             const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
             // width DD of the head strip: the smallest multiple of 32 such that every tile
             // starting at d = DD is off-diagonal (split point inside all its windows, see
@@ -695,7 +719,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             if (sb == 0) {
                 rect_DD = 32;
                 const TplMeta &mt0 = h->meta[0];
-                for (uint32_t cand = 32; rect_staged && cand <= TCW_RECT_DT; cand += 32) {
+                for (uint32_t cand = 32; rect_staged && cand <= rect_DTcap; cand += 32) {
                     bool all_off = true;
                     for (uint32_t gy = 0; gy < n_gy && all_off; gy++) {
                         const uint32_t m0 = gy * rows_per_tile;
@@ -714,28 +738,36 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             const uint32_t DD = rect_DD;
             const uint32_t d_total = w.N_tau + rect_R - 1;
             // regular tiles: as few as the staging capacity allows, evenly sized (multiple of 32)
-            const uint32_t n_reg = d_total > DD ? (d_total - DD + TCW_RECT_DT - 1) / TCW_RECT_DT : 0;
+            const uint32_t n_reg = d_total > DD ? (d_total - DD + rect_DTcap - 1) / rect_DTcap : 0;
             const uint32_t DT = n_reg ? (((d_total - DD + n_reg - 1) / n_reg) + 31u) & ~31u : 32u;
             dim3 grid(1 + n_reg, n_gy, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
-#define LAUNCH_RECT(RR, STG, TRK)                                                                   \
-    tcw_rect_map_kernel<RR, STG, TRK><<<grid, TCW_RECT_THREADS, smem, st>>>(                        \
-        (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, fmn, \
-        (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
-            // with a following lnBtSG pass the map kernel only tracks max VALUES; the pass
-            // locates the first cell attaining the final max while it re-reads F_mn anyway
-            if (rect_track) {
-                if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true, true);
-                else if (rect_R == 4) LAUNCH_RECT(4, false, true);
-                else if (rect_staged) LAUNCH_RECT(1, true, true);
-                else LAUNCH_RECT(1, false, true);
-            } else {
-                if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true, false);
-                else if (rect_R == 4) LAUNCH_RECT(4, false, false);
-                else if (rect_staged) LAUNCH_RECT(1, true, false);
-                else LAUNCH_RECT(1, false, false);
+            // The map kernel tracks max VALUES only.  The argmax is completed by the lnBtSG pass
+            // (which re-reads F_mn anyway) or, without it, by the locate kernel: only the tile(s)
+            // whose maximum equals the template maximum are re-evaluated with index tracking.
+            uint32_t *tilemax = nullptr;
+            if (!want_btsg) {
+                if ((rc = ensure(h, h->d_tilemax, (size_t)S * n_gy * (1 + n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX * sizeof(uint32_t)))) return rc;
+                tilemax = (uint32_t *)h->d_tilemax.p;
             }
+#define LAUNCH_RECT(RR, STG)                                                                               \
+    do {                                                                                                   \
+        tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                                \
+            (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, rect_G, \
+            fmn, (unsigned long long *)h->d_maxkey.p, tilemax, (uint32_t *)h->d_flags.p);                  \
+        if (tilemax) {                                                                                     \
+            h->launches++;                                                                                 \
+            CUDA_TRY(h, cudaGetLastError());                                                               \
+            tcw_rect_locate_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                         \
+                (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
+                rect_G, (unsigned long long *)h->d_maxkey.p, tilemax, (uint32_t *)h->d_flags.p);           \
+        }                                                                                                  \
+    } while (0)
+            if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);
+            else if (rect_R == 4) LAUNCH_RECT(4, false);
+            else if (rect_staged) LAUNCH_RECT(1, true);
+            else LAUNCH_RECT(1, false);
 #undef LAUNCH_RECT
         } else {
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, (w.N_t0 + exp_TM - 1) / exp_TM, cnt);
@@ -757,7 +789,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             dim3 grid((w.N_tau + TCW_BTSG_COLS - 1) / TCW_BTSG_COLS, (w.N_t0 + TCW_BTSG_ROWS - 1) / TCW_BTSG_ROWS,
                       cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the lnBtSG pass");
-            const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT && !rect_track;
+            const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
 #define LAUNCH_BTSG(EX, LOC)                                                                          \
     tcw_btsg_kernel<EX, LOC><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(                          \
         fmn, t_base, w.N_t0, w.N_tau, w.pitch, (unsigned long long *)h->d_maxkey.p,                    \

@@ -126,6 +126,22 @@ __device__ __forceinline__ void block_atomic_max_key(unsigned long long key,
     }
 }
 
+// block-wide max of a packed key; the result is valid in warp 0
+template <int NWARPS>
+__device__ __forceinline__ unsigned long long block_max_key(unsigned long long key,
+                                                            unsigned long long *smem_scratch) {
+    key = warp_max_u64(key);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem_scratch[warp] = key;
+    __syncthreads();
+    unsigned long long v = 0ull;
+    if (warp == 0) {
+        v = lane < NWARPS ? smem_scratch[lane] : 0ull;
+        v = warp_max_u64(v);
+    }
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // TMA bulk copy (1-D cp.async.bulk -> SASS UBLKCP) + mbarrier helpers
 // ---------------------------------------------------------------------------------------
@@ -260,37 +276,51 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
-// fstat_fast for TWO cells at once (the rectangular-window kernel is instruction-issue-bound):
-// 16 packed instructions + 2 MUFU.RCP + 2 compares/selects per pair.
+// 3-input max / NaN-propagating min (sm_100: one FMNMX3 each)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3_nan(float a, float b, float c) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// fstat_fast for TWO cells at once (the rectangular-window kernel is instruction-issue-bound),
+// UNGUARDED: returns F = num / det and the conditioning margin det - kappa s^2 of both cells; the
+// caller selects F = 2 where the margin is not positive.  The ab sums come in as Cp = -2 C:
+//   det = A B - Cp^2 / 4,   num = B |Fa|^2 + A |Fb|^2 + Cp Re(Fa conj Fb)
+// 15 packed instructions + 2 MUFU.RCP + 2 FMUL per pair.
 struct FstatConst2 {
-    f32x2 neg_kappa, neg_two, neg_one;
+    f32x2 neg_kappa, neg_quarter;
 };
 __device__ __forceinline__ FstatConst2 fstat_const2() {
     constexpr float kK = 9999.0f / 10001.0f;
     constexpr float kKappa = (1.0f - kK * kK) * 0.25f;
     FstatConst2 k;
     k.neg_kappa = pack2(-kKappa, -kKappa);
-    k.neg_two = pack2(-2.0f, -2.0f);
-    k.neg_one = pack2(-1.0f, -1.0f);
+    k.neg_quarter = pack2(-0.25f, -0.25f);
     return k;
 }
-__device__ __forceinline__ void fstat_fast2(const FstatConst2 &k, f32x2 Ad, f32x2 Bd, f32x2 Cd, f32x2 Fa_re,
-                                            f32x2 Fa_im, f32x2 Fb_re, f32x2 Fb_im, float &F0, float &F1) {
+__device__ __forceinline__ void fstat_core2(const FstatConst2 &k, f32x2 Ad, f32x2 Bd, f32x2 Cp, f32x2 Fa_re,
+                                            f32x2 Fa_im, f32x2 Fb_re, f32x2 Fb_im, float &F0, float &F1,
+                                            float &M0, float &M1) {
     const f32x2 sumAB = add2(Ad, Bd);
-    const f32x2 det = fma2(mul2(Cd, k.neg_one), Cd, mul2(Ad, Bd));     // AB - C^2
+    const f32x2 det = fma2(mul2(Cp, k.neg_quarter), Cp, mul2(Ad, Bd));  // AB - C^2
     const f32x2 margin = fma2(mul2(sumAB, k.neg_kappa), sumAB, det);    // det - kappa s^2
     const f32x2 fa2 = fma2(Fa_re, Fa_re, mul2(Fa_im, Fa_im));
     const f32x2 fb2 = fma2(Fb_re, Fb_re, mul2(Fb_im, Fb_im));
     const f32x2 re = fma2(Fa_re, Fb_re, mul2(Fa_im, Fb_im));
-    const f32x2 num = fma2(Bd, fa2, fma2(mul2(Cd, re), k.neg_two, mul2(Ad, fb2)));
-    float d0, d1, m0, m1, r0, r1;
+    const f32x2 num = fma2(Bd, fa2, fma2(Cp, re, mul2(Ad, fb2)));
+    float d0, d1, n0, n1, r0, r1;
     unpack2(det, d0, d1);
-    unpack2(margin, m0, m1);
+    unpack2(num, n0, n1);
+    unpack2(margin, M0, M1);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
-    float f0, f1;
-    unpack2(mul2(num, pack2(r0, r1)), f0, f1);
-    F0 = m0 > 0.0f ? f0 : 2.0f;
-    F1 = m1 > 0.0f ? f1 : 2.0f;
+    F0 = n0 * r0;
+    F1 = n1 * r1;
 }
 #endif  // __CUDACC__

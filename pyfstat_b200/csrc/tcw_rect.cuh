@@ -21,23 +21,34 @@
 // instead of once per cell).
 //
 // Precision modes (measured: FP64->FP32 conversions issue on the XU pipe at 16/clk/SM, so 7
-// conversions per cell cap the kernel at ~2 cells/clk/SM):
-//   * off-diagonal tiles -- every window of the tile contains the tile's first staged end
-//     index rho -- split the difference at rho:
+// conversions per cell cap the kernel at ~2 cells/clk/SM).  Every cell is evaluated as
 //         S = fl32(P[e+1] - P[rho])  +  fl32(P[rho] - P[s])
-//     The first term is tabulated once per tile (FP64 subtract + convert, ~0.25 per cell), the
-//     second lives in registers per row, so a cell costs ONE FADD per channel.  Both terms are
-//     sub-window sums of the cell's own window: for a2, b2 they are non-negative (no
-//     cancellation), for the signed channels the error is that of a two-term float32
-//     summation -- tighter than the reference's sequential float32 running sums.
-//   * tiles touching the diagonal (short windows, where a common split point does not
-//     exist) keep the FP64 difference + conversion per cell.  The launch gives the diagonal
-//     its own narrow strip of d (host-chosen width DD), ~1 % of the cells, processed one
-//     row at a time to keep the kernel's register footprint at 3 CTAs/SM.
+// with a split point rho chosen so that both terms are (close to) sub-window sums of the cell's
+// own window -- for a2, b2 no cancellation, for the signed channels the error of a two-term
+// float32 summation, tighter than the reference's sequential float32 running sums:
+//   * off-diagonal tiles -- every window of the tile contains the tile's first staged end
+//     index -- use ONE rho per tile: the first term is tabulated once per tile (FP64 subtract +
+//     convert, ~0.15 per cell), the second lives in registers per row, so a cell costs ONE
+//     packed FADD per channel and row pair;
+//   * tiles touching the diagonal (short windows, where a tile-wide split point does not
+//     exist; ~4 % of the cells) use one rho per GROUP of R rows, rho = 1 + the group's last
+//     start index: the first term is built per (group, d) on the fly (7 FP64 subtracts +
+//     conversions per R cells).  Windows shorter than the group's span see a negative first
+//     term; its magnitude is at most R-1 row steps, so with tau_min >= dtau (host-checked,
+//     otherwise R = 1) the cancellation costs a few ulp;
+//   * R == 1 or unstaged diagonal tiles keep the FP64 difference + conversion per cell.
 //
-// Fused epilogue: per-row running (max F, first d), combined per CTA and published with one
-// 64-bit atomicMax per CTA; F_mn is stored only if the caller (or the lnBtSG pass) needs it.
-// Tiles without a map edge run a branch-free body.
+// The ab channel is carried as C' = -2 * sum(ab) (exact scaling applied when the FP32 terms are
+// formed): det = A B - C'^2/4 and num = B|Fa|^2 + A|Fb|^2 + C' Re(Fa conj Fb) need one packed
+// instruction and one constant less.
+//
+// Fused epilogue: the map kernel tracks max VALUES only (one 3-input FMNMX per two cells); the
+// per-tile maxima go to a small table and the argmax is completed afterwards, either by the
+// lnBtSG pass (which re-reads F_mn anyway) or by tcw_rect_locate_kernel, which re-evaluates
+// only the tile(s) whose maximum equals the template maximum, with first-occurrence tracking.
+// Conditioning guard: interior chunks run 4 x R cells per lane unguarded while folding the
+// margins into one NaN-propagating 3-input minimum; a chunk with any non-positive margin is
+// re-evaluated with the per-cell select (F = 2 fallback of the reference).
 #pragma once
 #include "tcw_common.cuh"
 #include "tcw_prep.cuh"
@@ -46,86 +57,175 @@
 #define TCW_RECT_WARPS (TCW_RECT_THREADS / 32)
 #define TCW_RECT_DT 1024   // max d values per regular tile (the launch picks DT <= this, a multiple of 32)
 #define TCW_RECT_ECAP 1100 // staged end-prefix entries per channel (even)
-#define TCW_RECT_G 2       // row groups per warp (a tile has 8 warps x G groups x R rows)
-#define TCW_RECT_ROWS(R) (TCW_RECT_WARPS * TCW_RECT_G * (R))
-#define TCW_RECT_MAXROWS (TCW_RECT_WARPS * TCW_RECT_G * 4)
+#define TCW_RECT_GMAX 4    // max row groups per warp (a tile has 8 warps x G groups x R rows; G is a launch parameter)
+#define TCW_RECT_MAXROWS (TCW_RECT_WARPS * TCW_RECT_GMAX * 4)
 #define TCW_RECT_UCAP (TCW_RECT_DT + TCW_RECT_MAXROWS)  // end-index table entries
+#define TCW_RECT_JB 4      // d chunks (of 32) per guarded block of the interior loop
 #define TCW_RECT_SMEM_P (TCW_NCH * TCW_RECT_ECAP * 8)
-#define TCW_RECT_SMEM_Q (TCW_NCH * TCW_RECT_ECAP * 4)
 #define TCW_RECT_SMEM_E (TCW_RECT_UCAP * 4)
 #define TCW_RECT_SMEM_S (TCW_RECT_MAXROWS * 4)
 #define TCW_RECT_SMEM_R (TCW_RECT_MAXROWS * 8 * 4)
-#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_E + TCW_RECT_SMEM_S + TCW_RECT_SMEM_R)
+#define TCW_RECT_SMEM_G (TCW_RECT_MAXROWS / 4 * 8 * 8)
+#define TCW_RECT_SMEM (TCW_RECT_SMEM_P + TCW_RECT_SMEM_E + TCW_RECT_SMEM_S + TCW_RECT_SMEM_R + TCW_RECT_SMEM_G)
 
-// Fast body of one warp: R rows x (32 * n_j) values of d, split-point FP32 sums.
-//   CHECKED = false: every (row, d) is a valid cell (off-diagonal tiles have no degenerate cell).
-//   TRACK   = false: only the running max value is kept (the lnBtSG pass re-reads F_mn and
-//             locates the first cell equal to the final max), saving 2 instructions per cell.
-template <int R, bool CHECKED, bool STORE, bool TRACK>
-__device__ __forceinline__ void rect_rows_fp32(
-    const f32x2 *__restrict__ sQ2, const uint32_t *__restrict__ sE, const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH],
-    float *const (&rowp)[R], const bool (&rowok)[R], uint32_t u_off, uint32_t d0, int j_begin, int j_end,
-    uint32_t lane, uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0,
-    uint32_t t0_data, uint32_t numAtoms, const IndexGeom g, float (&best)[R], uint32_t (&best_d)[R]) {
-    const FstatConst2 kc = fstat_const2();
-#pragma unroll 4
-    for (int j = j_begin; j < j_end; j++) {
-        const uint32_t d = d0 + lane + 32u * j;
-        if (CHECKED && d >= d_total) break;
-        uint32_t idx;  // index of P[e+1] relative to the staged slice
-        if (R > 1) {
-            idx = sE[u_off + lane + 32u * j];
+// exact power-of-two scaling of channel c when the FP32 terms are formed: ab is carried as -2 ab
+__device__ __forceinline__ float rect_chan_scale(int c) { return c == 2 ? -2.0f : 1.0f; }
+
+// The R cells that share one end index (one lane, one d): window sums S = Q + R-term per row,
+// then F = num / det and the conditioning margin, both UNGUARDED (the caller applies the guard).
+//   DIAG = false: Q comes from the per-tile table of {q, q} pairs;
+//   DIAG = true : Q is built here from the staged FP64 slice and the group's P[rho].
+template <int R, bool DIAG>
+__device__ __forceinline__ void rect_eval(const f32x2 *__restrict__ sQ2, const double *__restrict__ sP,
+                                          const double *__restrict__ sGg, uint32_t idx,
+                                          const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH], const FstatConst2 &kc,
+                                          float (&F)[R], float (&mg)[R]) {
+    f32x2 Q2[TCW_NCH];  // {q, q}: duplicated so that the packed adds need no register shuffling
+#pragma unroll
+    for (int c = 0; c < TCW_NCH; c++) {
+        if (DIAG) {
+            const float q = (float)(sP[c * TCW_RECT_ECAP + idx] - sGg[c]) * rect_chan_scale(c);
+            Q2[c] = pack2(q, q);
         } else {
-            idx = min(index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1 - a0,
-                      (uint32_t)(TCW_RECT_ECAP - 1));
+            Q2[c] = sQ2[c * TCW_RECT_ECAP + idx];
         }
-        f32x2 Q2[TCW_NCH];  // {q, q}: stored duplicated so that the packed adds need no register shuffling
+    }
+    // rows in pairs: both cells share Q (same end index), so every FP32 operation of the pair is
+    // one packed instruction.  An odd R evaluates its last row in both halves of a pair.
 #pragma unroll
-        for (int c = 0; c < TCW_NCH; c++) Q2[c] = sQ2[c * TCW_RECT_ECAP + idx];
-        // rows in pairs: both cells share Q (same end index), so every FP32 operation of the
-        // pair is one packed instruction (FADD2 with Q broadcast, then fstat_fast2)
-        float Fr[R];
-        if (R % 2 == 0) {
+    for (int rp = 0; rp < (R + 1) / 2; rp++) {
+        f32x2 S[TCW_NCH];
 #pragma unroll
-            for (int rp = 0; rp < R / 2; rp++) {
-                f32x2 S[TCW_NCH];
-#pragma unroll
-                for (int c = 0; c < TCW_NCH; c++) S[c] = add2(Q2[c], Rs2[rp][c]);
-                fstat_fast2(kc, S[0], S[1], S[2], S[3], S[4], S[5], S[6], Fr[2 * rp], Fr[2 * rp + (R > 1 ? 1 : 0)]);
-            }
-        } else {
-            float lo[TCW_NCH], q[TCW_NCH], hi;
-#pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) {
-                unpack2(Rs2[0][c], lo[c], hi);
-                unpack2(Q2[c], q[c], hi);
-            }
-            Fr[0] = fstat_fast(q[0] + lo[0], q[1] + lo[1], q[2] + lo[2], q[3] + lo[3], q[4] + lo[4], q[5] + lo[5],
-                               q[6] + lo[6]);
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float F = Fr[r];
-            bool valid = true;
-            if (CHECKED) valid = rowok[r] && (d - r) < N_tau;  // d - r wraps for d < r
-            if (valid) {
-                if (STORE) rowp[r][32 * j] = F;
-                if (TRACK) {
-                    if (F > best[r]) {
-                        best[r] = F;
-                        best_d[r] = d;
-                    }
-                } else {
-                    best[r] = fmaxf(best[r], F);  // NaN-safe: fmaxf returns the non-NaN operand
-                }
-            }
+        for (int c = 0; c < TCW_NCH; c++) S[c] = add2(Q2[c], Rs2[rp][c]);
+        float f0, f1, m0, m1;
+        fstat_core2(kc, S[0], S[1], S[2], S[3], S[4], S[5], S[6], f0, f1, m0, m1);
+        F[2 * rp] = f0;
+        mg[2 * rp] = m0;
+        if (2 * rp + 1 < R) {
+            F[2 * rp + 1] = f1;
+            mg[2 * rp + 1] = m1;
         }
     }
 }
 
-// Precise body (tiles touching the diagonal, or unstaged): FP64 difference per cell, ONE row
-// per call (its start prefix in registers), every cell bounds- and degeneracy-checked.  Scalar
-// in/out on purpose: the hot path's per-row state must stay in registers.
+// One cell straight from the FP64 prefixes (start prefix from global memory): the few cells of a
+// diagonal group whose window ends before the group's split point.
+__device__ __noinline__ float rect_cell_fp64(const double *__restrict__ sP, uint32_t idx,
+                                             const double *__restrict__ Pt, uint32_t ppad, uint32_t s_row) {
+    float S[TCW_NCH];
+#pragma unroll
+    for (int c = 0; c < TCW_NCH; c++)
+        S[c] = (float)(sP[c * TCW_RECT_ECAP + idx] - __ldg(Pt + (size_t)c * ppad + s_row));
+    return fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+}
+
+// Per-row running state of a group.  TRACK = false keeps one max VALUE for the whole group.
+template <int R>
+struct RectBest {
+    float v[R];
+    uint32_t d[R];
+};
+
+// One chunk (32 d, one per lane) of a group with the per-cell guard, bounds checks (CHECKED),
+// degenerate-cell detection (DIAG) and first-occurrence tracking (TRACK).
+template <int R, bool DIAG, bool CHECKED, bool STORE, bool TRACK>
+__device__ __forceinline__ void rect_chunk_careful(
+    const f32x2 *__restrict__ sQ2, const double *__restrict__ sP, const double *__restrict__ sGg, uint32_t idx,
+    const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH], const FstatConst2 &kc, float *const (&rowp)[R], const bool (&rowok)[R],
+    const uint32_t (&srow)[R], uint32_t e_abs, uint32_t d, int j, uint32_t N_tau, const double *__restrict__ Pt,
+    uint32_t ppad, RectBest<R> &best, float &vmax, uint32_t &degenerate) {
+    float F[R], mg[R];
+    rect_eval<R, DIAG>(sQ2, sP, sGg, idx, Rs2, kc, F, mg);
+    // DIAG: a window ending before the group's split point rho = srow[R-1] + 1 would see
+    // cancellation between the two terms -> evaluate those few cells exactly
+    const bool before_rho = DIAG && e_abs < srow[R - 1];  // e + 1 < rho
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float Fr = mg[r] > 0.0f ? F[r] : 2.0f;  // NaN margin -> fallback, as the reference's cond test
+        bool valid = true;
+        if (CHECKED) valid = rowok[r] && (d - r) < N_tau;  // d - r wraps for d < r
+        if (DIAG && before_rho && valid) Fr = rect_cell_fp64(sP, idx, Pt, ppad, srow[r]);
+        if (valid) {
+            if (STORE) rowp[r][32 * j] = Fr;
+            if (TRACK) {
+                if (Fr > best.v[r]) {
+                    best.v[r] = Fr;
+                    best.d[r] = d;
+                }
+            } else {
+                vmax = fmaxf(vmax, Fr);  // NaN-safe: fmaxf returns the non-NaN operand
+            }
+            if (DIAG && e_abs == srow[r]) degenerate = 1;  // i_t1 == i_t0
+        }
+    }
+}
+
+// All chunks [j_begin, j_end) of one group.
+//   CHECKED = false: every (row, d) is a valid cell; with TRACK = false the chunks run in blocks
+//   of TCW_RECT_JB with the guard folded into one minimum per block (see the header).
+template <int R, bool DIAG, bool CHECKED, bool STORE, bool TRACK>
+__device__ __forceinline__ void rect_rows(
+    const f32x2 *__restrict__ sQ2, const double *__restrict__ sP, const double *__restrict__ sGg,
+    const uint32_t *__restrict__ sE, const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH], float *const (&rowp)[R],
+    const bool (&rowok)[R], const uint32_t (&srow)[R], uint32_t u_off, uint32_t d0, int j_begin, int j_end,
+    uint32_t lane, uint32_t N_tau, uint32_t d_total, uint32_t t1_lane, uint32_t t1_step, uint32_t a0,
+    uint32_t t0_data, uint32_t numAtoms, const IndexGeom g, const double *__restrict__ Pt, uint32_t ppad,
+    RectBest<R> &best, float &vmax, uint32_t &degenerate) {
+    const FstatConst2 kc = fstat_const2();
+    auto end_index = [&](int j) -> uint32_t {  // index of P[e+1] relative to the staged slice
+        if (R > 1) return sE[u_off + lane + 32u * j];
+        return min(index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1 - a0,
+                   (uint32_t)(TCW_RECT_ECAP - 1));
+    };
+    int j = j_begin;
+    if (!CHECKED && !TRACK && !DIAG) {
+#pragma unroll 1
+        for (; j + TCW_RECT_JB <= j_end; j += TCW_RECT_JB) {
+            const float vmax_in = vmax;
+            float mmin = 1.0f;
+#pragma unroll
+            for (int u = 0; u < TCW_RECT_JB; u++) {
+                float F[R], mg[R];
+                rect_eval<R, false>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, F, mg);
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (STORE) rowp[r][32 * (j + u)] = F[r];
+                if (R % 2 == 0) {
+#pragma unroll
+                    for (int r = 0; r < R; r += 2) {
+                        vmax = fmax3(vmax, F[r], F[r + 1]);
+                        mmin = fmin3_nan(mmin, mg[r], mg[r + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        vmax = fmaxf(vmax, F[r]);
+                        mmin = fmin3_nan(mmin, mg[r], mg[r]);
+                    }
+                }
+            }
+            if (!(mmin > 0.0f)) {  // rare: some cell of the block needs the F = 2 fallback -> redo guarded
+                vmax = vmax_in;
+#pragma unroll 1
+                for (int u = 0; u < TCW_RECT_JB; u++)
+                    rect_chunk_careful<R, false, false, STORE, false>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, rowp,
+                                                                      rowok, srow, 0u, 0u, j + u, N_tau, Pt, ppad, best,
+                                                                      vmax, degenerate);
+            }
+        }
+    }
+#pragma unroll 1
+    for (; j < j_end; j++) {
+        const uint32_t d = d0 + lane + 32u * j;
+        if (CHECKED && d >= d_total) break;
+        const uint32_t idx = end_index(j);
+        rect_chunk_careful<R, DIAG, CHECKED, STORE, TRACK>(sQ2, sP, sGg, idx, Rs2, kc, rowp, rowok, srow,
+                                                            idx + a0 - 1u, d, j, N_tau, Pt, ppad, best, vmax, degenerate);
+    }
+}
+
+// Precise body (R == 1 or unstaged tiles touching the diagonal): FP64 difference per cell, ONE
+// row per call (its start prefix in registers), every cell bounds- and degeneracy-checked.
 struct RectRowResult {
     float best;
     uint32_t best_d;
@@ -169,18 +269,18 @@ __device__ __noinline__ RectRowResult rect_row_fp64(
     return out;
 }
 
-// grid: x = d tiles: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT),
-//           DT chosen by the host so that the regular tiles divide the map evenly
-//       y = tiles of 8 warps x G row groups, z = template in sub-batch
-// TRACK = false (only with a following lnBtSG pass over a stored F_mn): publish max values
-// only; tcw_btsg_kernel completes the key with the first flat index that attains the max.
+// One tile.  bx = d tile: 0 = head strip [0, DD) holding the diagonal; b >= 1 = [DD + (b-1) DT, +DT),
+//                DT chosen by the host so that the regular tiles divide the map evenly
+//            by = tile of 8 warps x G row groups x R rows, tz = template in sub-batch
+// TRACK = false: returns the tile's max VALUE in the high half of the key (index part 0).
+// TRACK = true : full key (value, first flat index); nothing is stored.
 template <int R, bool STAGED, bool TRACK>
-__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
-tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
-                    int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, float *__restrict__ Fmn,
-                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
-    unsigned char *sp = tcw_rect_smem;
+__device__ __forceinline__ unsigned long long rect_tile(
+    const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta, int t, int tz, uint32_t bx,
+    uint32_t by, const MapWindow &w, const IndexGeom &g, uint32_t DD, uint32_t DT, uint32_t G,
+    float *__restrict__ Fmn, uint32_t *__restrict__ flags, uint32_t *__restrict__ gmax, uint32_t top,
+    unsigned char *smem, uint64_t *bar, unsigned long long *red) {
+    unsigned char *sp = smem;
     double *sP = reinterpret_cast<double *>(sp);        // [7][ECAP]  staged FP64 end prefixes
     f32x2 *sQ2 = reinterpret_cast<f32x2 *>(sp);         // [7][ECAP]  {q, q}, q = fl32(P[i] - P[rho]): IN PLACE over sP
     sp += TCW_RECT_SMEM_P;
@@ -189,24 +289,21 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     uint32_t *sS = reinterpret_cast<uint32_t *>(sp);    // [ROWS]     start index i_t0 per row
     sp += TCW_RECT_SMEM_S;
     float *sR = reinterpret_cast<float *>(sp);          // [ROWS/2][8][2]  fl32(P[rho] - P[s]), row pairs interleaved
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned long long red[TCW_RECT_WARPS];
+    sp += TCW_RECT_SMEM_R;
+    double *sG = reinterpret_cast<double *>(sp);        // [ROWS/R][8]  P[rho] of each row group (diagonal tiles)
 
-    const int tz = blockIdx.z;
-    const int t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
     const uint32_t t0_data = meta[t].t0_data;
     const double *Pt = P + (size_t)t * TCW_NCH * ppad;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    constexpr uint32_t ROWS = TCW_RECT_ROWS(R);  // rows per tile
+    const uint32_t ROWS = TCW_RECT_WARPS * G * R;  // rows per tile
     const uint32_t d_total = w.N_tau + R - 1;
-    const uint32_t m0 = blockIdx.y * ROWS;
+    const uint32_t m0 = by * ROWS;
     const uint32_t m_last = min(m0 + ROWS, w.N_t0) - 1;
-    const uint32_t d0 = blockIdx.x == 0 ? 0u : DD + (blockIdx.x - 1) * DT;
-    const uint32_t d_cnt = blockIdx.x == 0 ? DD : DT;
+    const uint32_t d0 = bx == 0 ? 0u : DD + (bx - 1) * DT;
+    const uint32_t d_cnt = bx == 0 ? DD : DT;
     const uint32_t d_last = min(d0 + d_cnt, d_total) - 1;
-    const bool edge_rows = (d0 < (uint32_t)(R - 1)) || (m0 + ROWS > w.N_t0);  // head strip / bottom row tile
 
     // end time of (row group, d): rows of a group differ by dt0 == dtau (R > 1), absorbed into d
     const uint32_t t1_tile = w.t0 + w.tau + m0 * w.dt0 + d0 * w.dtau;
@@ -218,12 +315,12 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
                                        numAtoms, g);
         cnt = min((e_hi + 1 - a0 + 1 + 1) & ~1u, (uint32_t)TCW_RECT_ECAP);  // even; <= ECAP by the host check
         if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
+            mbar_init(bar, 1);
             mbar_fence_init();
-            mbar_arrive_expect_tx(&bar, TCW_NCH * cnt * (uint32_t)sizeof(double));
+            mbar_arrive_expect_tx(bar, TCW_NCH * cnt * (uint32_t)sizeof(double));
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++)
-                bulk_g2s(sP + c * TCW_RECT_ECAP, Pt + (size_t)c * ppad + a0, cnt * (uint32_t)sizeof(double), &bar);
+                bulk_g2s(sP + c * TCW_RECT_ECAP, Pt + (size_t)c * ppad + a0, cnt * (uint32_t)sizeof(double), bar);
         }
     }
     // per-tile index tables, computed cooperatively while the bulk copies are in flight:
@@ -241,9 +338,10 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
         sS[threadIdx.x] = index_t0(w.t0 + m * w.dt0, t0_data, numAtoms, g);
     }
     // start prefixes P_c[s_row] for the per-row terms: fetched now, while the bulk copies fly
-    double ps_early[(ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS];
+    constexpr int KPS = (TCW_RECT_MAXROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS;
+    double ps_early[KPS];
 #pragma unroll
-    for (int k = 0; k < (int)((ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS); k++) {
+    for (int k = 0; k < KPS; k++) {
         const uint32_t i = threadIdx.x + k * TCW_RECT_THREADS;
         const uint32_t row = i >> 3, c = i & 7;
         ps_early[k] = 0.0;
@@ -256,10 +354,26 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     // off-diagonal: the split point rho = a0 lies strictly inside every window of the tile,
     // s < rho <= e + 1 with e > s (so no cell of the tile is degenerate): rho >= s_hi + 2
     const bool offdiag = STAGED && (a0 >= s_hi + 2);
+    const bool groupsplit = STAGED && R > 1 && !offdiag;
     float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
 
     __syncthreads();  // sE, sS visible; mbarrier init visible to all waiters
-    if (STAGED) mbar_wait(&bar, 0);
+    if (groupsplit) {
+        // diagonal tile: rho of a group = 1 + start index of its last row; sR = fl32(P[rho] - P[s]),
+        // sG = P[rho] (global loads issued before waiting for the slice)
+#pragma unroll
+        for (int k = 0; k < KPS; k++) {
+            const uint32_t i = threadIdx.x + k * TCW_RECT_THREADS;
+            const uint32_t row = i >> 3, c = i & 7;
+            if (i < ROWS * 8 && c < TCW_NCH) {
+                const uint32_t rho = sS[row / R * R + R - 1] + 1;  // <= numAtoms: P has numAtoms + 1 entries
+                const double prho = __ldg(Pt + (size_t)c * ppad + rho);
+                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] = (float)(prho - ps_early[k]) * rect_chan_scale(c);
+                if (row % R == 0) sG[(row / R) * 8 + c] = prho;
+            }
+        }
+    }
+    if (STAGED) mbar_wait(bar, 0);
     if (offdiag) {
         // off-diagonal tiles no longer need the FP64 slice itself: convert it IN PLACE to
         // {q, q} pairs, q = fl32(P_c[a0+i] - P_c[rho]) (each thread rewrites only the 8-byte slots
@@ -268,51 +382,62 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) pref[c] = sP[c * TCW_RECT_ECAP];
 #pragma unroll
-        for (int k = 0; k < (int)((ROWS * 8 + TCW_RECT_THREADS - 1) / TCW_RECT_THREADS); k++) {
+        for (int k = 0; k < KPS; k++) {
             const uint32_t i = threadIdx.x + k * TCW_RECT_THREADS;
             const uint32_t row = i >> 3, c = i & 7;
             // stored as row PAIRS {row 2p, row 2p+1} per channel: a 64-bit load yields a packed operand
             if (i < ROWS * 8 && c < TCW_NCH)
-                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] = (float)(sP[c * TCW_RECT_ECAP] - ps_early[k]);
+                sR[(((row >> 1) * 8 + c) << 1) + (row & 1)] =
+                    (float)(sP[c * TCW_RECT_ECAP] - ps_early[k]) * rect_chan_scale(c);
         }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < cnt; i += TCW_RECT_THREADS) {
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++) {
-                const float q = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]);
+                const float q = (float)(sP[c * TCW_RECT_ECAP + i] - pref[c]) * rect_chan_scale(c);
                 sQ2[c * TCW_RECT_ECAP + i] = pack2(q, q);
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     const uint32_t t1_step = 32u * w.dtau;
     const int n_j = (int)(d_cnt / 32);
     const int j_full = w.N_tau > d0 ? (int)min((w.N_tau - d0) / 32u, (uint32_t)n_j) : 0;  // fully valid chunks
     unsigned long long key = 0ull;
+    float vmax = -1.0f;
     uint32_t degenerate = 0;
-    // each warp walks TCW_RECT_G row groups of R rows: the tile's staging cost is shared
+    // each warp walks G row groups of R rows: the tile's staging cost is shared
 #pragma unroll 1
-    for (uint32_t gi = 0; gi < TCW_RECT_G; gi++) {
+    for (uint32_t gi = 0; gi < G; gi++) {
         const uint32_t grow = (gi * TCW_RECT_WARPS + warp) * R;  // first row of the group, relative to m0
-        if (m0 + grow >= w.N_t0) break;
+        uint32_t *gslot = gmax ? gmax + gi * TCW_RECT_WARPS + warp : nullptr;  // this group's max value
+        if (m0 + grow >= w.N_t0) {
+            if (!TRACK && gslot && lane == 0) *gslot = 0u;
+            continue;
+        }
+        if (TRACK && *gslot != top) continue;  // locate pass: only the groups that attain the template max
+        float vgrp = -1.0f;  // maxF starts at -1, strict > (tcw:135-139)
         const uint32_t u_off = grow;
         const uint32_t t1_lane = t1_tile + grow * w.dt0 + lane * w.dtau;  // used by R == 1 only
-        float best[R];
-        uint32_t best_d[R];
+        RectBest<R> best;
         float *rowp[R];
         bool rowok[R];
+        uint32_t srow[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const uint32_t m = m0 + grow + r;
-            best[r] = -1.0f;  // maxF starts at -1, strict > (tcw:135-139)
-            best_d[r] = r;
+            best.v[r] = -1.0f;
+            best.d[r] = r;
             rowok[r] = m < w.N_t0;
             const uint32_t mc = rowok[r] ? m : 0u;
+            srow[r] = 0u;
             // cell (m, n = d - r) with d = d0 + lane + 32 j  ->  rowp[r][32 j]
             rowp[r] = Ft ? Ft + ((size_t)mc * w.pitch + d0 + lane) - r : nullptr;
         }
-        if (offdiag) {
+        // a group is an edge group if some (row, d) of its full chunks is not a cell of the map
+        const bool edge = (d0 < (uint32_t)(R - 1)) || (m0 + grow + R > w.N_t0);
+        if (offdiag || groupsplit) {
             f32x2 Rs2[(R + 1) / 2][TCW_NCH];  // {row 2rp, row 2rp+1} pairs of fl32(P[rho] - P[s])
 #pragma unroll
             for (int rp = 0; rp < (R + 1) / 2; rp++) {
@@ -328,49 +453,109 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
                     }
                 }
             }
-#define RECT_FAST(CHK_, STORE_, J0_, J1_)                                                                       \
-    rect_rows_fp32<R, CHK_, STORE_, TRACK>(sQ2, sE, Rs2, rowp, rowok, u_off, d0, J0_, J1_, lane, w.N_tau, d_total, \
-                                           t1_lane, t1_step, a0, t0_data, numAtoms, g, best, best_d)
-            if (edge_rows) {
-                if (Ft) RECT_FAST(true, true, 0, n_j);
-                else RECT_FAST(true, false, 0, n_j);
+            const double *sGg = sG + (grow / R) * 8;
+#define RECT_ROWS(DIAG_, CHK_, STORE_, J0_, J1_)                                                                     \
+    rect_rows<R, DIAG_, CHK_, STORE_, TRACK>(sQ2, sP, sGg, sE, Rs2, rowp, rowok, srow, u_off, d0, J0_, J1_, lane,   \
+                                             w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g, Pt, ppad, \
+                                             best, vgrp, degenerate)
+            if (groupsplit) {
+#pragma unroll
+                for (int r = 0; r < R; r++) srow[r] = sS[min(grow + r, ROWS - 1)];
+                if (Ft && !TRACK) RECT_ROWS(true, true, true, 0, n_j);
+                else RECT_ROWS(true, true, false, 0, n_j);
+            } else if (edge) {
+                if (Ft && !TRACK) RECT_ROWS(false, true, true, 0, n_j);
+                else RECT_ROWS(false, true, false, 0, n_j);
             } else {
                 // chunks of 32 d that are valid for every lane and row run unchecked; only the
                 // chunk(s) straddling the map's right edge are bounds-checked
-                if (Ft) {
-                    RECT_FAST(false, true, 0, j_full);
-                    if (j_full < n_j) RECT_FAST(true, true, j_full, n_j);
+                if (Ft && !TRACK) {
+                    RECT_ROWS(false, false, true, 0, j_full);
+                    if (j_full < n_j) RECT_ROWS(false, true, true, j_full, n_j);
                 } else {
-                    RECT_FAST(false, false, 0, j_full);
-                    if (j_full < n_j) RECT_FAST(true, false, j_full, n_j);
+                    RECT_ROWS(false, false, false, 0, j_full);
+                    if (j_full < n_j) RECT_ROWS(false, true, false, j_full, n_j);
                 }
             }
-#undef RECT_FAST
+#undef RECT_ROWS
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (!rowok[r]) continue;
                 const uint32_t s_row = sS[grow + r];
                 const RectRowResult rr =
-                    Ft ? rect_row_fp64<R, STAGED, true>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
-                                                        w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g)
-                       : rect_row_fp64<R, STAGED, false>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
-                                                         w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g);
-                best[r] = rr.best;
-                best_d[r] = rr.best_d;
+                    (Ft && !TRACK)
+                        ? rect_row_fp64<R, STAGED, true>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
+                                                         w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g)
+                        : rect_row_fp64<R, STAGED, false>(sP, sE, Pt, ppad, s_row, rowp[r], r, u_off, d0, n_j, lane,
+                                                          w.N_tau, d_total, t1_lane, t1_step, a0, t0_data, numAtoms, g);
+                best.v[r] = rr.best;
+                best.d[r] = rr.best_d;
+                vgrp = fmaxf(vgrp, rr.best);
                 degenerate |= rr.degenerate;
             }
         }
+        if (!TRACK) {
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (best[r] > -1.0f) {
-                // TRACK == false: index part 0 (flat = 0xFFFFFFFF), completed by the lnBtSG pass
-                const uint32_t flat = TRACK ? (m0 + grow + r) * w.N_tau + (best_d[r] - r) : 0xFFFFFFFFu;
-                const unsigned long long k = pack_key(best[r], flat);
-                key = k > key ? k : key;
+            for (int o = 16; o > 0; o >>= 1) vgrp = fmaxf(vgrp, __shfl_xor_sync(0xffffffffu, vgrp, o));
+            if (gslot && lane == 0) *gslot = vgrp > -1.0f ? float_orderable(vgrp) : 0u;
+            vmax = fmaxf(vmax, vgrp);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (best.v[r] > -1.0f) {
+                    const unsigned long long k =
+                        pack_key(best.v[r], (m0 + grow + r) * w.N_tau + (best.d[r] - r));
+                    key = k > key ? k : key;
+                }
             }
         }
     }
+    if (!TRACK && vmax > -1.0f) key = pack_key(vmax, 0xFFFFFFFFu);  // index part 0: completed later
     if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
-    block_atomic_max_key<TCW_RECT_WARPS>(key, &maxkey[t], red);
+    return block_max_key<TCW_RECT_WARPS>(key, red);
+}
+
+// grid: x = d tiles, y = row tiles, z = template in sub-batch.  Publishes the max VALUE per
+// template (atomicMax on the packed key, index part 0) and per row group (groupmax: 8 x GMAX
+// entries per tile, for the locate pass).
+template <int R, bool STAGED>
+__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
+tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
+                    int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G,
+                    float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
+                    uint32_t *__restrict__ groupmax, uint32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned long long red[TCW_RECT_WARPS];
+    const int tz = blockIdx.z, t = t_base + tz;
+    const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    uint32_t *gmax = groupmax ? groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX) : nullptr;
+    const unsigned long long key = rect_tile<R, STAGED, false>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
+                                                               DT, G, Fmn, flags, gmax, 0u, tcw_rect_smem, &bar, red);
+    if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
+}
+
+// Same grid.  A CTA holding row groups whose maximum equals the template maximum re-evaluates
+// those groups with first-occurrence tracking (identical arithmetic, nothing stored) and
+// completes the key.
+template <int R, bool STAGED>
+__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
+tcw_rect_locate_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
+                       int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G,
+                       unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ groupmax,
+                       uint32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned long long red[TCW_RECT_WARPS];
+    const int tz = blockIdx.z, t = t_base + tz;
+    const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    uint32_t *gmax = groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX);
+    const uint32_t top = (uint32_t)(maxkey[t] >> 32);  // final: the map kernel has completed (stream order)
+    int mine = 0;
+    if (top != 0u && threadIdx.x < TCW_RECT_WARPS * G) mine = gmax[threadIdx.x] == top;
+    if (!__syncthreads_or(mine)) return;
+    const unsigned long long key = rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
+                                                              DT, G, nullptr, flags, gmax, top, tcw_rect_smem, &bar, red);
+    if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
 }

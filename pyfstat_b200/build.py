@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build pyfstat_b200/libtcw_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB,
+    extra = os.environ.get("TCW_NVCC_EXTRA", "").split()  # development: e.g. -DTCW_RECT_MINB=2
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB,
            os.path.join(CSRC, "tcw_b200.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

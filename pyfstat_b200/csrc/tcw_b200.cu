@@ -438,6 +438,85 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     return p;
 }
 
+// Tile shape of the rectangular-window kernel for one launch (tcw_rect.cuh): G row groups per
+// warp (ROWS = 8 G R rows per tile), the head strip width DD (smallest multiple of 32 such that
+// every tile starting at d = DD is off-diagonal; the device re-checks per tile, so DD only affects
+// speed) and n_reg regular tiles of DT values of d.  Candidates are ranked by a small cost model:
+// work per SM slot (cells + staging, which scales with ROWS + DT) plus half a tile as the
+// expected tail -- tall, wide tiles for big batches, small ones when few templates must still
+// fill the GPU.  TCW_RECT_G / TCW_RECT_NREG override (development).
+struct RectPlan {
+    uint32_t G = 1, DD = 32, DT = 32, n_reg = 0;
+    bool staged = false;
+};
+
+static RectPlan plan_rect(const tcw_handle *h, const MapWindow &w, int S, uint32_t R, uint32_t TAtom,
+                          const IndexGeom &g) {
+    const TplMeta &mt0 = h->meta[0];
+    const uint32_t d_total = w.N_tau + R - 1;
+    const double slots = (double)h->prop.multiProcessorCount * TCW_RECT_MINB;
+    const uint32_t g_max = R == 4 ? TCW_RECT_GMAX : 2;
+    const char *env_g = getenv("TCW_RECT_G"), *env_n = getenv("TCW_RECT_NREG");
+    RectPlan best;
+    double best_cost = -1.0;
+    for (uint32_t G = g_max; G >= 1; G /= 2) {
+        if (env_g && (uint32_t)atoi(env_g) != G) continue;
+        const uint32_t rows = TCW_RECT_WARPS * G * R;
+        const uint32_t n_gy = (w.N_t0 + rows - 1) / rows;
+        // widest regular tile whose end indices still fit the staged slice
+        uint32_t dt_cap = 0;
+        for (uint32_t dt = TCW_RECT_DT; dt >= 64; dt -= 32) {
+            const uint64_t span = ((uint64_t)(rows - 1) * w.dt0 + (uint64_t)(dt - 1) * w.dtau) / TAtom + 6;
+            if (span <= TCW_RECT_ECAP) {
+                dt_cap = dt;
+                break;
+            }
+        }
+        RectPlan p;
+        p.G = G;
+        p.staged = dt_cap != 0;
+        if (!p.staged) dt_cap = 1024;
+        p.DD = 32;
+        for (uint32_t cand = 32; p.staged && cand <= dt_cap; cand += 32) {
+            bool all_off = true;
+            for (uint32_t gy = 0; gy < n_gy && all_off; gy++) {
+                const uint32_t m0 = gy * rows;
+                const uint32_t m_last = std::min(m0 + rows, w.N_t0) - 1;
+                const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + cand * w.dtau, mt0.t0_data, mt0.numAtoms, g);
+                const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, mt0.t0_data, mt0.numAtoms, g);
+                all_off = ((e_lo + 1) & ~1u) >= s_hi + 2;
+            }
+            if (all_off) {
+                p.DD = cand;
+                break;
+            }
+        }
+        const uint32_t rest = d_total > p.DD ? d_total - p.DD : 0;
+        const uint32_t n_min = (rest + dt_cap - 1) / dt_cap;
+        for (uint32_t n_reg = n_min; n_reg <= n_min + 3; n_reg++) {
+            if (env_n && (uint32_t)atoi(env_n) != n_reg && n_min <= (uint32_t)atoi(env_n)) continue;
+            p.n_reg = n_reg;
+            p.DT = 32;
+            if (n_reg) {
+                const uint32_t even = (rest + n_reg - 1) / n_reg;
+                p.DT = (even + 127u) & ~127u;  // whole guarded blocks (TCW_RECT_JB chunks of 32)
+                if (p.DT > dt_cap) p.DT = (even + 31u) & ~31u;
+            }
+            const double c_setup = 12.0;  // staging cost per staged entry, in cell evaluations (measured ~10 %)
+            const double head = 2.0 * rows * p.DD + c_setup * (rows + p.DD);
+            const double reg = (double)rows * p.DT + c_setup * (rows + p.DT);
+            const double work = (double)S * n_gy * (head + n_reg * reg);
+            const double cost = work / slots + 0.5 * std::max(head, n_reg ? reg : 0.0);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = p;
+            }
+            if (!n_reg) break;
+        }
+    }
+    return best;
+}
+
 static size_t subbatch_bytes() {
     const char *env = getenv("TCW_SUBBATCH_MB");
     size_t mb = env ? (size_t)atol(env) : 2048;
@@ -531,8 +610,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     enum { PATH_GENERIC = 0, PATH_FAST = 1 };
     int path = PATH_GENERIC;
     int rect_R = 1;
-    uint32_t rect_DD = 32, rect_G = 1, rect_DTcap = 32;
-    bool rect_staged = false;
+    RectPlan rp;
     ExpPlan ep;
     if (!(flags & TCW_FORCE_GENERIC) && !none_window && !per_template) {
         if (w.type == TCW_WINDOW_RECT) {
@@ -541,37 +619,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             rect_R = (w.dt0 == w.dtau && w.tau >= w.dtau) ? 4 : 1;
             bool ok = true;
             for (int t = 0; t < T && ok; t++) ok = no_wrap(w, 1, rect_R - 1, h->meta[t], TAtom);
-            if (ok) {
-                path = PATH_FAST;
-                // row groups per warp: tall tiles amortise the per-tile staging, but a small batch
-                // needs enough tiles to fill the GPU
-                const uint64_t rows1 = (uint64_t)TCW_RECT_WARPS * rect_R;
-                rect_G = 1;
-                if (const char *env = getenv("TCW_RECT_G")) {
-                    rect_G = (uint32_t)std::min(std::max(atoi(env), 1), rect_R == 4 ? TCW_RECT_GMAX : 2);
-                } else {
-                    const uint32_t g_max = rect_R == 4 ? TCW_RECT_GMAX : 2;
-                    const uint64_t slots = (uint64_t)h->prop.multiProcessorCount * 3 * 4;  // >= 4 waves
-                    for (uint32_t gc = g_max; gc >= 1; gc /= 2) {
-                        rect_G = gc;
-                        const uint64_t tiles = (uint64_t)T * ((w.N_t0 + rows1 * gc - 1) / (rows1 * gc)) *
-                                               ((w.N_tau + TCW_RECT_DT - 1) / TCW_RECT_DT + 1);
-                        if (tiles >= slots) break;
-                    }
-                }
-                // widest regular tile whose end indices still fit the staged slice
-                const uint64_t rows = rows1 * rect_G;
-                rect_staged = false;
-                for (uint32_t dt = TCW_RECT_DT; dt >= 64; dt -= 32) {
-                    const uint64_t span = ((rows - 1) * w.dt0 + (uint64_t)(dt - 1) * w.dtau) / TAtom + 6;
-                    if (span <= TCW_RECT_ECAP) {
-                        rect_staged = true;
-                        rect_DTcap = dt;
-                        break;
-                    }
-                }
-                if (!rect_staged) rect_DTcap = TCW_RECT_DT;
-            }
+            if (ok) path = PATH_FAST;
         } else {
             ep = plan_exp(h, w);
             if (ep.ok) path = PATH_FAST;
@@ -711,57 +759,35 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);
 #undef LAUNCH_GENERIC
         } else if (w.type == TCW_WINDOW_RECT) {
+            if (sb == 0) rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
+            const uint32_t rect_G = rp.G, DD = rp.DD, DT = rp.DT, n_reg = rp.n_reg;
+            const bool rect_staged = rp.staged;
             const uint32_t rows_per_tile = TCW_RECT_WARPS * rect_G * rect_R;
             const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
-            // width DD of the head strip: the smallest multiple of 32 such that every tile
-            // starting at d = DD is off-diagonal (split point inside all its windows, see
-            // tcw_rect.cuh); the device re-checks per tile, so this only affects speed
-            if (sb == 0) {
-                rect_DD = 32;
-                const TplMeta &mt0 = h->meta[0];
-                for (uint32_t cand = 32; rect_staged && cand <= rect_DTcap; cand += 32) {
-                    bool all_off = true;
-                    for (uint32_t gy = 0; gy < n_gy && all_off; gy++) {
-                        const uint32_t m0 = gy * rows_per_tile;
-                        const uint32_t m_last = std::min(m0 + rows_per_tile, w.N_t0) - 1;
-                        const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + cand * w.dtau, mt0.t0_data,
-                                                       mt0.numAtoms, g);
-                        const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, mt0.t0_data, mt0.numAtoms, g);
-                        all_off = ((e_lo + 1) & ~1u) >= s_hi + 2;
-                    }
-                    if (all_off) {
-                        rect_DD = cand;
-                        break;
-                    }
-                }
-            }
-            const uint32_t DD = rect_DD;
-            const uint32_t d_total = w.N_tau + rect_R - 1;
-            // regular tiles: as few as the staging capacity allows, evenly sized (multiple of 32)
-            const uint32_t n_reg = d_total > DD ? (d_total - DD + rect_DTcap - 1) / rect_DTcap : 0;
-            const uint32_t DT = n_reg ? (((d_total - DD + n_reg - 1) / n_reg) + 31u) & ~31u : 32u;
             dim3 grid(1 + n_reg, n_gy, cnt);
             if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
             // The map kernel tracks max VALUES only.  The argmax is completed by the lnBtSG pass
-            // (which re-reads F_mn anyway) or, without it, by the locate kernel: only the tile(s)
-            // whose maximum equals the template maximum are re-evaluated with index tracking.
-            uint32_t *tilemax = nullptr;
+            // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
+            // template re-evaluates only the row groups whose maximum equals the template maximum.
+            uint32_t *groupmax = nullptr;
             if (!want_btsg) {
-                if ((rc = ensure(h, h->d_tilemax, (size_t)S * n_gy * (1 + n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX * sizeof(uint32_t)))) return rc;
-                tilemax = (uint32_t *)h->d_tilemax.p;
+                const size_t n_entries = (size_t)S * n_gy * (1 + n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX;
+                if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
+                groupmax = (uint32_t *)h->d_tilemax.p;
             }
 #define LAUNCH_RECT(RR, STG)                                                                               \
     do {                                                                                                   \
         tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                                \
             (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, rect_G, \
-            fmn, (unsigned long long *)h->d_maxkey.p, tilemax, (uint32_t *)h->d_flags.p);                  \
-        if (tilemax) {                                                                                     \
+            fmn, (unsigned long long *)h->d_maxkey.p, groupmax, (uint32_t *)h->d_flags.p);                 \
+        if (groupmax) {                                                                                    \
             h->launches++;                                                                                 \
             CUDA_TRY(h, cudaGetLastError());                                                               \
-            tcw_rect_locate_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                         \
+            tcw_rect_locate_kernel<RR, STG><<<cnt, TCW_RECT_THREADS, smem, st>>>(                          \
                 (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
-                rect_G, (unsigned long long *)h->d_maxkey.p, tilemax, (uint32_t *)h->d_flags.p);           \
+                rect_G, grid.x, grid.y, (unsigned long long *)h->d_maxkey.p, groupmax,                     \
+                (uint32_t *)h->d_flags.p);                                                                 \
         }                                                                                                  \
     } while (0)
             if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);

@@ -54,9 +54,14 @@
 #include "tcw_prep.cuh"
 
 #define TCW_RECT_THREADS 256
+#ifndef TCW_RECT_MINB
+#define TCW_RECT_MINB 2  // CTAs per SM the register allocation targets (measured: 128 registers, no spills, beat 3 x 80)
+#endif
 #define TCW_RECT_WARPS (TCW_RECT_THREADS / 32)
-#define TCW_RECT_DT 1024   // max d values per regular tile (the launch picks DT <= this, a multiple of 32)
-#define TCW_RECT_ECAP 1100 // staged end-prefix entries per channel (even)
+#ifndef TCW_RECT_DT
+#define TCW_RECT_DT 1472   // max d values per regular tile (the launch picks DT <= this, a multiple of 32)
+#define TCW_RECT_ECAP 1608 // staged end-prefix entries per channel (even)
+#endif
 #define TCW_RECT_GMAX 4    // max row groups per warp (a tile has 8 warps x G groups x R rows; G is a launch parameter)
 #define TCW_RECT_MAXROWS (TCW_RECT_WARPS * TCW_RECT_GMAX * 4)
 #define TCW_RECT_UCAP (TCW_RECT_DT + TCW_RECT_MAXROWS)  // end-index table entries
@@ -177,16 +182,30 @@ __device__ __forceinline__ void rect_rows(
         return min(index_t1(t1_lane + (uint32_t)j * t1_step, t0_data, numAtoms, g) + 1 - a0,
                    (uint32_t)(TCW_RECT_ECAP - 1));
     };
+    // A run of chunks is "plain" if every (row, d) in it is a cell of the map whose window ends
+    // at or after the group's split point (so it is neither degenerate nor in need of the exact
+    // evaluation): such runs take the unguarded block path.  All conditions are warp-uniform.
+    constexpr int JBX = DIAG ? 1 : TCW_RECT_JB;
+    bool allrows = true;
+#pragma unroll
+    for (int r = 0; r < R; r++) allrows = allrows && rowok[r];
+    auto plain = [&](int j) -> bool {
+        if (!CHECKED) return true;
+        const uint32_t d_lo = d0 + 32u * j;
+        bool ok = allrows && d_lo >= (uint32_t)(R - 1) && d_lo + 32u * JBX <= N_tau;
+        if (DIAG && ok) ok = sE[u_off + 32u * j] + a0 - 1u > srow[R - 1];  // lane 0's end index: the smallest
+        return ok;
+    };
     int j = j_begin;
-    if (!CHECKED && !TRACK && !DIAG) {
 #pragma unroll 1
-        for (; j + TCW_RECT_JB <= j_end; j += TCW_RECT_JB) {
+    while (j < j_end) {
+        if (!TRACK && j + JBX <= j_end && plain(j)) {
             const float vmax_in = vmax;
             float mmin = 1.0f;
 #pragma unroll
-            for (int u = 0; u < TCW_RECT_JB; u++) {
+            for (int u = 0; u < JBX; u++) {
                 float F[R], mg[R];
-                rect_eval<R, false>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, F, mg);
+                rect_eval<R, DIAG>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, F, mg);
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     if (STORE) rowp[r][32 * (j + u)] = F[r];
@@ -207,20 +226,24 @@ __device__ __forceinline__ void rect_rows(
             if (!(mmin > 0.0f)) {  // rare: some cell of the block needs the F = 2 fallback -> redo guarded
                 vmax = vmax_in;
 #pragma unroll 1
-                for (int u = 0; u < TCW_RECT_JB; u++)
-                    rect_chunk_careful<R, false, false, STORE, false>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, rowp,
-                                                                      rowok, srow, 0u, 0u, j + u, N_tau, Pt, ppad, best,
-                                                                      vmax, degenerate);
+                for (int u = 0; u < JBX; u++) {
+                    const uint32_t idx = end_index(j + u);
+                    rect_chunk_careful<R, DIAG, false, STORE, false>(sQ2, sP, sGg, idx, Rs2, kc, rowp, rowok, srow,
+                                                                     idx + a0 - 1u, 0u, j + u, N_tau, Pt, ppad, best,
+                                                                     vmax, degenerate);
+                }
             }
+            j += JBX;
+        } else {
+            const uint32_t d = d0 + lane + 32u * j;
+            if (!CHECKED || d < d_total) {
+                const uint32_t idx = end_index(j);
+                rect_chunk_careful<R, DIAG, CHECKED, STORE, TRACK>(sQ2, sP, sGg, idx, Rs2, kc, rowp, rowok, srow,
+                                                                    idx + a0 - 1u, d, j, N_tau, Pt, ppad, best, vmax,
+                                                                    degenerate);
+            }
+            j++;
         }
-    }
-#pragma unroll 1
-    for (; j < j_end; j++) {
-        const uint32_t d = d0 + lane + 32u * j;
-        if (CHECKED && d >= d_total) break;
-        const uint32_t idx = end_index(j);
-        rect_chunk_careful<R, DIAG, CHECKED, STORE, TRACK>(sQ2, sP, sGg, idx, Rs2, kc, rowp, rowok, srow,
-                                                            idx + a0 - 1u, d, j, N_tau, Pt, ppad, best, vmax, degenerate);
     }
 }
 
@@ -279,7 +302,7 @@ __device__ __forceinline__ unsigned long long rect_tile(
     const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta, int t, int tz, uint32_t bx,
     uint32_t by, const MapWindow &w, const IndexGeom &g, uint32_t DD, uint32_t DT, uint32_t G,
     float *__restrict__ Fmn, uint32_t *__restrict__ flags, uint32_t *__restrict__ gmax, uint32_t top,
-    unsigned char *smem, uint64_t *bar, unsigned long long *red) {
+    unsigned char *smem, uint64_t *bar, uint32_t phase, unsigned long long *red) {
     unsigned char *sp = smem;
     double *sP = reinterpret_cast<double *>(sp);        // [7][ECAP]  staged FP64 end prefixes
     f32x2 *sQ2 = reinterpret_cast<f32x2 *>(sp);         // [7][ECAP]  {q, q}, q = fl32(P[i] - P[rho]): IN PLACE over sP
@@ -314,9 +337,7 @@ __device__ __forceinline__ unsigned long long rect_tile(
         const uint32_t e_hi = index_t1(t1_tile + ((m_last - m0) / R * R) * w.dt0 + (d_last - d0) * w.dtau, t0_data,
                                        numAtoms, g);
         cnt = min((e_hi + 1 - a0 + 1 + 1) & ~1u, (uint32_t)TCW_RECT_ECAP);  // even; <= ECAP by the host check
-        if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            mbar_fence_init();
+        if (threadIdx.x == 0) {  // the barrier was initialised by the kernel (one phase per tile)
             mbar_arrive_expect_tx(bar, TCW_NCH * cnt * (uint32_t)sizeof(double));
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++)
@@ -373,7 +394,7 @@ __device__ __forceinline__ unsigned long long rect_tile(
             }
         }
     }
-    if (STAGED) mbar_wait(bar, 0);
+    if (STAGED) mbar_wait(bar, phase);
     if (offdiag) {
         // off-diagonal tiles no longer need the FP64 slice itself: convert it IN PLACE to
         // {q, q} pairs, q = fl32(P_c[a0+i] - P_c[rho]) (each thread rewrites only the 8-byte slots
@@ -407,11 +428,16 @@ __device__ __forceinline__ unsigned long long rect_tile(
     unsigned long long key = 0ull;
     float vmax = -1.0f;
     uint32_t degenerate = 0;
-    // each warp walks G row groups of R rows: the tile's staging cost is shared
+    // each warp walks G row groups of R rows: the tile's staging cost is shared.  The locate
+    // pass (TRACK) visits every group slot of the tile with ALL warps, which share the chunks
+    // of a group that attains the template max.
+    const uint32_t n_it = TRACK ? G * TCW_RECT_WARPS : G;
 #pragma unroll 1
-    for (uint32_t gi = 0; gi < G; gi++) {
-        const uint32_t grow = (gi * TCW_RECT_WARPS + warp) * R;  // first row of the group, relative to m0
-        uint32_t *gslot = gmax ? gmax + gi * TCW_RECT_WARPS + warp : nullptr;  // this group's max value
+    for (uint32_t it = 0; it < n_it; it++) {
+        const uint32_t gi = TRACK ? it / TCW_RECT_WARPS : it;
+        const uint32_t wsel = TRACK ? it % TCW_RECT_WARPS : warp;  // the warp that owned the group in the map pass
+        const uint32_t grow = (gi * TCW_RECT_WARPS + wsel) * R;  // first row of the group, relative to m0
+        uint32_t *gslot = gmax ? gmax + gi * TCW_RECT_WARPS + wsel : nullptr;  // this group's max value
         if (m0 + grow >= w.N_t0) {
             if (!TRACK && gslot && lane == 0) *gslot = 0u;
             continue;
@@ -436,7 +462,7 @@ __device__ __forceinline__ unsigned long long rect_tile(
             rowp[r] = Ft ? Ft + ((size_t)mc * w.pitch + d0 + lane) - r : nullptr;
         }
         // a group is an edge group if some (row, d) of its full chunks is not a cell of the map
-        const bool edge = (d0 < (uint32_t)(R - 1)) || (m0 + grow + R > w.N_t0);
+        const bool edge = TRACK || (d0 < (uint32_t)(R - 1)) || (m0 + grow + R > w.N_t0);
         if (offdiag || groupsplit) {
             f32x2 Rs2[(R + 1) / 2][TCW_NCH];  // {row 2rp, row 2rp+1} pairs of fl32(P[rho] - P[s])
 #pragma unroll
@@ -461,27 +487,35 @@ __device__ __forceinline__ unsigned long long rect_tile(
             if (groupsplit) {
 #pragma unroll
                 for (int r = 0; r < R; r++) srow[r] = sS[min(grow + r, ROWS - 1)];
-                if (Ft && !TRACK) RECT_ROWS(true, true, true, 0, n_j);
-                else RECT_ROWS(true, true, false, 0, n_j);
-            } else if (edge) {
-                if (Ft && !TRACK) RECT_ROWS(false, true, true, 0, n_j);
-                else RECT_ROWS(false, true, false, 0, n_j);
-            } else {
-                // chunks of 32 d that are valid for every lane and row run unchecked; only the
-                // chunk(s) straddling the map's right edge are bounds-checked
-                if (Ft && !TRACK) {
-                    RECT_ROWS(false, false, true, 0, j_full);
-                    if (j_full < n_j) RECT_ROWS(false, true, true, j_full, n_j);
+            }
+            // map pass: one call over all chunks; locate pass: this warp's share of the chunks
+            const int jstep = TRACK ? TCW_RECT_WARPS : n_j;
+#pragma unroll 1
+            for (int jj = TRACK ? (int)warp : 0; jj < n_j; jj += jstep) {
+                const int J0 = jj, J1 = TRACK ? jj + 1 : n_j;
+                if (groupsplit) {
+                    if (Ft && !TRACK) RECT_ROWS(true, true, true, J0, J1);
+                    else RECT_ROWS(true, true, false, J0, J1);
+                } else if (edge) {
+                    if (Ft && !TRACK) RECT_ROWS(false, true, true, J0, J1);
+                    else RECT_ROWS(false, true, false, J0, J1);
                 } else {
-                    RECT_ROWS(false, false, false, 0, j_full);
-                    if (j_full < n_j) RECT_ROWS(false, true, false, j_full, n_j);
+                    // chunks of 32 d that are valid for every lane and row run unchecked; only the
+                    // chunk(s) straddling the map's right edge are bounds-checked
+                    if (Ft) {
+                        RECT_ROWS(false, false, true, 0, j_full);
+                        if (j_full < n_j) RECT_ROWS(false, true, true, j_full, n_j);
+                    } else {
+                        RECT_ROWS(false, false, false, 0, j_full);
+                        if (j_full < n_j) RECT_ROWS(false, true, false, j_full, n_j);
+                    }
                 }
             }
 #undef RECT_ROWS
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (!rowok[r]) continue;
+                if (!rowok[r] || (TRACK && warp != wsel)) continue;
                 const uint32_t s_row = sS[grow + r];
                 const RectRowResult rr =
                     (Ft && !TRACK)
@@ -516,11 +550,60 @@ __device__ __forceinline__ unsigned long long rect_tile(
     return block_max_key<TCW_RECT_WARPS>(key, red);
 }
 
-// grid: x = d tiles, y = row tiles, z = template in sub-batch.  Publishes the max VALUE per
-// template (atomicMax on the packed key, index part 0) and per row group (groupmax: 8 x GMAX
-// entries per tile, for the locate pass).
+// Completes the argmax of template t without a stored F_mn: finds the row groups whose maximum
+// equals the template maximum (normally one) and re-evaluates their tiles with first-occurrence
+// tracking (identical arithmetic, nothing stored).  Run by one whole CTA; (gx, gy) = tile grid.
+#define TCW_RECT_HITWORDS 256
 template <int R, bool STAGED>
-__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
+__device__ __forceinline__ void rect_locate(const double *__restrict__ P, uint32_t ppad,
+                                            const TplMeta *__restrict__ meta, int t, int tz, const MapWindow &w,
+                                            const IndexGeom &g, uint32_t DD, uint32_t DT, uint32_t G, uint32_t gx,
+                                            uint32_t gy, unsigned long long *__restrict__ maxkey,
+                                            uint32_t *__restrict__ groupmax, uint32_t *__restrict__ flags,
+                                            unsigned char *smem, uint64_t *bar, uint32_t phase,
+                                            unsigned long long *red, uint32_t *hit) {
+    const uint32_t top = (uint32_t)(*(volatile unsigned long long *)&maxkey[t] >> 32);
+    if (top == 0u) return;
+    constexpr uint32_t GE = TCW_RECT_WARPS * TCW_RECT_GMAX;  // table entries per tile
+    const uint32_t n_tiles = gx * gy;
+    uint32_t *gm = groupmax + (size_t)tz * n_tiles * GE;
+    for (uint32_t base = 0; base < n_tiles; base += TCW_RECT_HITWORDS * 32) {
+        const uint32_t n_here = min(n_tiles - base, (uint32_t)(TCW_RECT_HITWORDS * 32));
+        for (uint32_t i = threadIdx.x; i < TCW_RECT_HITWORDS; i += TCW_RECT_THREADS) hit[i] = 0u;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < n_here * GE; e += TCW_RECT_THREADS) {
+            const uint32_t tl = e / GE;
+            if ((e % GE) < TCW_RECT_WARPS * G && __ldcg(gm + (size_t)base * GE + e) == top)
+                atomicOr(&hit[tl >> 5], 1u << (tl & 31));
+        }
+        __syncthreads();
+        for (uint32_t wd = 0; wd < (n_here + 31) / 32; wd++) {
+            uint32_t bits = hit[wd];  // uniform across the CTA
+            while (bits) {
+                const uint32_t tile = base + wd * 32 + (uint32_t)(__ffs(bits) - 1);
+                bits &= bits - 1;
+                const unsigned long long key =
+                    rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, tile % gx, tile / gx, w, g, DD, DT, G, nullptr,
+                                               flags, gm + (size_t)tile * GE, top, smem, bar, phase, red);
+                if (STAGED) phase ^= 1u;
+                if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
+                __syncthreads();  // red[] and the staged slice are reused by the next tile
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// grid: x = d tiles, y = row tiles, z = template in sub-batch.  Publishes the max VALUE per
+// template (atomicMax on the packed key, index part 0) and, when the argmax has to be completed
+// by tcw_rect_locate_kernel (groupmax != nullptr: no lnBtSG pass follows), per row group:
+// 8 x GMAX entries per tile.
+// Natural dispatch order (x fastest): the cheap head-strip tiles are interleaved with the regular
+// ones, which keeps the CTAs sharing an SM out of phase (one stages while the other computes).
+// Measured: running all regular tiles first and the head tiles last is 7 % slower; so is running
+// the locate step inside this kernel (last CTA of a template) instead of a second small launch.
+template <int R, bool STAGED>
+__global__ void __launch_bounds__(TCW_RECT_THREADS, TCW_RECT_MINB)
 tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
                     int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G,
                     float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
@@ -531,31 +614,34 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const int tz = blockIdx.z, t = t_base + tz;
     const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     uint32_t *gmax = groupmax ? groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX) : nullptr;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
     const unsigned long long key = rect_tile<R, STAGED, false>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
-                                                               DT, G, Fmn, flags, gmax, 0u, tcw_rect_smem, &bar, red);
+                                                               DT, G, Fmn, flags, gmax, 0u, tcw_rect_smem, &bar, 0u,
+                                                               red);
     if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
 }
 
-// Same grid.  A CTA holding row groups whose maximum equals the template maximum re-evaluates
-// those groups with first-occurrence tracking (identical arithmetic, nothing stored) and
-// completes the key.
+// One CTA per template of the sub-batch, launched after the map kernel (stream order makes the
+// template maxima and the group table final): completes the argmax, see rect_locate.
 template <int R, bool STAGED>
-__global__ void __launch_bounds__(TCW_RECT_THREADS, 3)
+__global__ void __launch_bounds__(TCW_RECT_THREADS, TCW_RECT_MINB)
 tcw_rect_locate_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
-                       int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G,
-                       unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ groupmax,
+                       int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G, uint32_t gx,
+                       uint32_t gy, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ groupmax,
                        uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long red[TCW_RECT_WARPS];
-    const int tz = blockIdx.z, t = t_base + tz;
-    const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    uint32_t *gmax = groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX);
-    const uint32_t top = (uint32_t)(maxkey[t] >> 32);  // final: the map kernel has completed (stream order)
-    int mine = 0;
-    if (top != 0u && threadIdx.x < TCW_RECT_WARPS * G) mine = gmax[threadIdx.x] == top;
-    if (!__syncthreads_or(mine)) return;
-    const unsigned long long key = rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
-                                                              DT, G, nullptr, flags, gmax, top, tcw_rect_smem, &bar, red);
-    if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
+    __shared__ uint32_t hit[TCW_RECT_HITWORDS];  // bitmap of tiles holding a group with the top value
+    const int tz = blockIdx.x, t = t_base + tz;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    rect_locate<R, STAGED>(P, ppad, meta, t, tz, w, g, DD, DT, G, gx, gy, maxkey, groupmax, flags, tcw_rect_smem, &bar,
+                           0u, red, hit);
 }

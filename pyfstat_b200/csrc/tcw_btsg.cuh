@@ -30,8 +30,11 @@ template <bool EXACT_EXP>
 __device__ __forceinline__ double btsg_term(double maxF, float F, const double *__restrict__ slut) {
     const double dF = maxF - (double)F;  // >= 0
     if (EXACT_EXP) return exp(-dF);
-    // LUT[(UINT4)(dF*100 + 0.5)], 0 beyond 20 (also catches NaN-free huge values)
-    const uint32_t i0 = __double2uint_rz(__dadd_rn(__dmul_rn(dF, (double)TCW_LUT_LEN / TCW_LUT_XMAX), 0.5));
+    // LUT[(UINT4)(dF*100 + 0.5)], 0 beyond 20.  The product and the sum round separately, as in
+    // lalpulsar; the truncation to UINT4 is done on the FP64 pipe (add 2^52 rounding toward zero
+    // leaves the integer part in the low mantissa word) instead of an XU-pipe F2I conversion.
+    const double v = __dadd_rn(__dmul_rn(dF, (double)TCW_LUT_LEN / TCW_LUT_XMAX), 0.5);  // >= 0.5
+    const uint32_t i0 = (uint32_t)__double2loint(__dadd_rz(v, 4503599627370496.0));
     return dF > TCW_LUT_XMAX ? 0.0 : slut[min(i0, (uint32_t)TCW_LUT_LEN)];
 }
 
@@ -47,7 +50,7 @@ __device__ __forceinline__ double btsg_term(double maxF, float F, const double *
 // LOCATE: the rect map kernel published max VALUES only (key index part 0); complete the key
 // with the smallest flat index whose F equals the max (first occurrence, np.argmax order).
 template <bool EXACT_EXP, bool LOCATE>
-__global__ void __launch_bounds__(TCW_BTSG_THREADS)
+__global__ void __launch_bounds__(TCW_BTSG_THREADS, 4)
 tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32_t N_tau, uint32_t pitch,
                 unsigned long long *__restrict__ maxkey, const double *__restrict__ lut,
                 double *__restrict__ rowsum, double *__restrict__ colsum) {
@@ -63,24 +66,33 @@ tcw_btsg_kernel(const float *__restrict__ Fmn, int t_base, uint32_t N_t0, uint32
     const float *Ft = Fmn + (size_t)tz * N_t0 * pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t m0 = blockIdx.y * TCW_BTSG_ROWS + warp * TCW_BTSG_RPW, n0 = blockIdx.x * TCW_BTSG_COLS;
-    if (!EXACT_EXP) {
-        for (int i = threadIdx.x; i <= TCW_LUT_LEN; i += TCW_BTSG_THREADS) slut[i] = __ldg(lut + i);
-        __syncthreads();
-    }
     // this lane's columns: n0 + 128*jv + 4*lane + q, jv = 0,1, q = 0..3  (accumulator j = 4*jv + q)
     double colacc[TCW_BTSG_CPL];
 #pragma unroll
     for (int j = 0; j < TCW_BTSG_CPL; j++) colacc[j] = 0.0;
     const bool full = (m0 + TCW_BTSG_RPW <= N_t0) && (n0 + TCW_BTSG_COLS <= N_tau);
+    const float4 *p = reinterpret_cast<const float4 *>(Ft + (size_t)m0 * pitch + n0) + lane;
+    // the first rows' loads are issued BEFORE the table copy and its barrier, so that the two
+    // round trips to L2/HBM overlap (the CTA is short-lived: 64 cells per thread)
+    constexpr int kPre = 4;
+    float4 pre[kPre][2];
     if (full) {
-        const float4 *p = reinterpret_cast<const float4 *>(Ft + (size_t)m0 * pitch + n0) + lane;
-        constexpr int kRowUnroll = EXACT_EXP ? 1 : 4;
-#pragma unroll kRowUnroll
+#pragma unroll
+        for (int i = 0; i < kPre; i++)
+#pragma unroll
+            for (int jv = 0; jv < 2; jv++) pre[i][jv] = __ldg(p + (size_t)i * (pitch / 4) + 32 * jv);
+    }
+    if (!EXACT_EXP) {
+        for (int i = threadIdx.x; i <= TCW_LUT_LEN; i += TCW_BTSG_THREADS) slut[i] = __ldg(lut + i);
+        __syncthreads();
+    }
+    if (full) {
+#pragma unroll
         for (int i = 0; i < TCW_BTSG_RPW; i++) {
             float f[TCW_BTSG_CPL];
 #pragma unroll
             for (int jv = 0; jv < 2; jv++) {
-                const float4 v = __ldg(p + (size_t)i * (pitch / 4) + 32 * jv);
+                const float4 v = i < kPre ? pre[i < kPre ? i : 0][jv] : __ldg(p + (size_t)i * (pitch / 4) + 32 * jv);
                 f[4 * jv + 0] = v.x; f[4 * jv + 1] = v.y; f[4 * jv + 2] = v.z; f[4 * jv + 3] = v.w;
             }
             double ra = 0.0;

@@ -22,6 +22,7 @@ from .backend import (
     register,
     unregister,
 )
+from . import semicoherent
 from .window import (
     TRANSIENT_EXPONENTIAL,
     TRANSIENT_LAST,
@@ -34,7 +35,7 @@ from .window import (
 __all__ = [
     "ATOM_DTYPE", "AtomBatch", "batch_from_detector_lists", "from_multi_fstat_atoms", "synth_atoms",
     "BACKEND_NAME", "b200_compute_transient_fstat_map", "backend_available", "fstat_map_class",
-    "get_handle", "register", "unregister",
+    "get_handle", "register", "unregister", "semicoherent",
     "TRANSIENT_NONE", "TRANSIENT_RECTANGULAR", "TRANSIENT_EXPONENTIAL", "TRANSIENT_LAST",
     "TransientWindowRange", "canonical_window",
 ]

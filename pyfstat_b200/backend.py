@@ -84,6 +84,79 @@ def _base_class(tcw_module=None):
     return getattr(tcw_module, "pyTransientFstatMap", object) if tcw_module else object
 
 
+class LazyFmn:
+    """What ``FstatMap.F_mn`` returns before the map has been copied to the host.
+
+    ``F_mn[m, n]`` with two integers -- the one access pattern of the transient BSGL
+    (``FXstatMap.F_mn[idx_maxTwoF]``, core.py:1541) -- evaluates that single cell on the GPU
+    (a 1x1 map) instead of computing, copying and caching the whole ``[N_t0, N_tau]`` array.
+    Any other use (slicing, ``np.asarray``, iteration, arithmetic, attributes such as ``.max()``)
+    materialises the array once and behaves like it.
+    """
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def _array(self):
+        return self._owner._materialise()
+
+    @property
+    def shape(self):
+        return self._owner.shape
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    @property
+    def ndim(self):
+        return 2
+
+    def __len__(self):
+        return self._owner.shape[0]
+
+    def __getitem__(self, idx):
+        if (
+            isinstance(idx, tuple)
+            and len(idx) == 2
+            and all(isinstance(i, (int, np.integer)) and not isinstance(i, (bool, np.bool_)) for i in idx)
+            and self._owner._F_mn is None
+        ):
+            N_t0, N_tau = self._owner.shape
+            m, n = int(idx[0]), int(idx[1])
+            if not (-N_t0 <= m < N_t0 and -N_tau <= n < N_tau):
+                raise IndexError(f"index {idx} is out of bounds for F_mn of shape {(N_t0, N_tau)}")
+            return np.float32(self._owner.F_at(m % N_t0, n % N_tau))
+        return self._array()[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._array()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __iter__(self):
+        return iter(self._array())
+
+    def __getattr__(self, name):  # everything else: behave like the ndarray
+        return getattr(self._array(), name)
+
+    def __repr__(self):
+        return f"LazyFmn(shape={self.shape}, materialised={self._owner._F_mn is not None})"
+
+
+def _lazy_binop(name):
+    def op(self, *args):
+        return getattr(self._array(), name)(*args)
+
+    op.__name__ = name
+    return op
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
+           "__neg__", "__eq__", "__ne__", "__lt__", "__le__", "__gt__", "__ge__"):
+    setattr(LazyFmn, _n, _lazy_binop(_n))
+LazyFmn.__hash__ = None
+
+
 _class_cache = {}
 
 
@@ -124,6 +197,11 @@ def fstat_map_class(tcw_module=None):
         # ---- lazy F_mn --------------------------------------------------------------
         @property
         def F_mn(self):
+            """The ``[N_t0, N_tau]`` float32 array once materialised; before that a
+            :class:`LazyFmn` that serves single-cell reads without materialising."""
+            return self._F_mn if self._F_mn is not None else LazyFmn(self)
+
+        def _materialise(self):
             if self._F_mn is None:
                 h = get_handle(self._device)
                 _, F = h.map_batch(

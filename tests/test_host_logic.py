@@ -275,6 +275,10 @@ class OracleBackedHandle:
             Fs.append(r["F_mn"].astype(np.float32))
         return res, (np.stack(Fs) if flags & _lib.WANT_FMN else None)
 
+    def map_batch_windows(self, batch, windows, flags=0, raise_on_degenerate=True):
+        recs = [self.map_batch(batch[t], w, flags, raise_on_degenerate)[0] for t, w in enumerate(windows)]
+        return np.concatenate(recs), None
+
     def close(self):
         pass
 
@@ -305,12 +309,23 @@ def test_plugin_through_real_reference_dispatcher(ref_tcw, oracle, monkeypatch, 
         assert fm.get_tau_max_posterior(w) == pytest.approx(o["tau_MP"])
         assert len(fake.calls) == n_calls, "fused results must not trigger another device call"
         assert fm._F_mn is None, "F_mn must stay lazy until it is read"
-        # single cell as core.py:1541 reads it, full map as tcw:311 / the tests read it
+        # single cell as core.py:1541 reads it: one 1x1 map, the full map is NOT materialised
         F = fm.F_mn
-        assert F.shape == (47, 49) and F.dtype == np.float32
+        assert F.shape == (47, 49) and F.dtype == np.float32 and len(F) == 47
         assert F[fm.get_maxF_idx()] == np.float32(fm.maxF)
-        assert len(fake.calls) == n_calls + 1 and fake.calls[-1] & _lib.WANT_FMN
-        assert fm.F_at(3, 4) == F[3, 4]
+        assert len(fake.calls) == n_calls + 1 and not (fake.calls[-1] & _lib.WANT_FMN)
+        assert fm._F_mn is None
+        with pytest.raises(IndexError):
+            F[47, 0]
+        # full map as tcw:311 / the tests read it: materialised once, then a plain ndarray
+        Fa = np.asarray(F)
+        assert len(fake.calls) == n_calls + 2 and fake.calls[-1] & _lib.WANT_FMN
+        assert isinstance(fm.F_mn, np.ndarray) and np.shares_memory(fm.F_mn, Fa)
+        assert F[3, 4] == Fa[3, 4] and F[-1, -1] == Fa[46, 48] and F[3].shape == (49,)
+        assert float(F.max()) == fm.maxF and (2 * F)[1, 2] == 2 * Fa[1, 2]
+        assert len(fake.calls) == n_calls + 2
+        assert fm.F_at(3, 4) == Fa[3, 4]
+        F = Fa
         # the reference's own writer/reader on our object (tcw:289-317, 159-184)
         path = tmp_path / "map.dat"
         fm.write_F_mn_to_file(str(path), w, header=["hello"])
@@ -333,3 +348,89 @@ def test_plugin_through_real_reference_dispatcher(ref_tcw, oracle, monkeypatch, 
         assert fm3.F_mn[0, 0] == F[0, -1]
     finally:
         pyfstat_b200.unregister(ref_tcw)
+
+
+def test_semicoherent_and_bsgl_helpers(oracle, monkeypatch):
+    """per-segment 2F (core.py:2282-2289), per-detector sums with the NaN
+    rule (core.py:2236-2260), per-detector 2F at the multi-detector argmax (core.py:1527-1541)
+    and the cumulative 2F (core.py:1648-1665) -- host logic against the oracle (test double)."""
+    from pyfstat_b200 import batch as B
+    from pyfstat_b200 import semicoherent as SC
+
+    fake = OracleBackedHandle(oracle)
+    monkeypatch.setattr(backend, "get_handle", lambda device=-1: fake)
+    monkeypatch.setattr(SC, "get_handle", lambda device=-1: fake)
+    monkeypatch.setattr(B, "get_handle", lambda device=-1: fake)
+    n, TAtom, t0 = 96, 1800, 10**9
+    b = synth_atoms(2, n, ("H1", "L1"), seed=31)
+    nsegs = 8
+    tb = np.linspace(t0, t0 + n * TAtom, nsegs + 1)
+    w = SC.semicoherent_window_range(tb, tb[1] - tb[0])
+    assert (w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau) == (1, t0, (nsegs - 1) * 12 * TAtom, 12 * TAtom,
+                                                                       12 * TAtom, 0, 1)
+    assert w.dims() == (nsegs, 1)
+    twoF = SC.per_segment_twoF(b, w)
+    assert twoF.shape == (2, nsegs)
+    for t in range(2):
+        o = oracle.compute_map(b.template(t), TAtom, w)
+        assert np.array_equal(twoF[t], 2.0 * o["F_mn"][:, 0].astype(np.float32).astype(np.float64))
+    twoFX, per_seg = SC.single_IFO_twoFs(b, w)
+    assert twoFX.shape == (2, 2) and per_seg.shape == (2, 2, nsegs)
+    o = oracle.compute_map([b.template(1)[1]], TAtom, w)
+    assert np.array_equal(per_seg[1, 1], 2.0 * o["F_mn"][:, 0].astype(np.float32).astype(np.float64))
+    assert twoFX[1, 1] == per_seg[1, 1].sum()
+    with pytest.raises(ValueError):
+        SC.single_detector_batch(b, 2)
+    # transient BSGL ingredient: per-detector 2F at the multi-detector argmax cell
+    wt = canonical_window("rect", t0, n)
+    rec, _ = B.map_batch(b, wt)
+    tx = SC.twoFX_at_maxTwoF(b, wt, rec)
+    for t in range(2):
+        for X in range(2):
+            oX = oracle.compute_map([b.template(t)[X]], TAtom, wt, allow_degenerate=True)
+            assert tx[t, X] == 2.0 * float(np.float32(oX["F_mn"][int(rec["m_ML"][t]), int(rec["n_ML"][t])]))
+    # cumulative 2F: equally spaced durations -> one 1 x N_tau map; otherwise one call each
+    durs = SC.cumulative_durations(t0, t0 + n * TAtom, TAtom, 48)
+    assert durs[0] == 2 * TAtom and durs[-1] == n * TAtom
+    n_calls = len(fake.calls)
+    cum = SC.twoF_cumulative(b, t0, durs)
+    assert cum.shape == (2, 48) and len(fake.calls) == n_calls + 1
+    for k in (0, 17, 47):
+        o1 = oracle.compute_map(b.template(0), TAtom, TransientWindowRange(1, t0, 0, 1, int(durs[k]), 0, 1))
+        assert cum[0, k] == 2.0 * float(np.float32(o1["maxF"]))
+    cum2 = SC.twoF_cumulative(b, t0, [2 * TAtom, 5 * TAtom, 6 * TAtom])
+    assert cum2.shape == (2, 3) and cum2[0, 0] == cum[0, 0]
+
+    # install(): the two SemiCoherentSearch methods, attributes as in the reference
+    class FakeResults:
+        numDetectors = 2
+
+        def __init__(self, multi):
+            self.multiFatoms = [multi]
+
+    class SemiCoherentSearch:
+        singleFstats = True
+
+        def _get_per_segment_twoF(self):
+            raise AssertionError("must be replaced")
+
+        def get_semicoherent_single_IFO_twoFs(self, record_segments=False):
+            raise AssertionError("must be replaced")
+
+    class FakeCore:
+        pass
+
+    FakeCore.SemiCoherentSearch = SemiCoherentSearch
+    SC.install(FakeCore)
+    s = SemiCoherentSearch()
+    s.FstatResults = FakeResults(FakeMulti(b[0]))
+    s.semicoherentWindowRange = w
+    s.twoFX = np.zeros(3)
+    s.twoFX_per_segment = np.zeros((3, nsegs))
+    assert np.array_equal(s._get_per_segment_twoF(), twoF[0])
+    out = s.get_semicoherent_single_IFO_twoFs(record_segments=True)
+    assert out[0] == twoFX[0, 0] and out[1] == twoFX[0, 1] and out[2] == 0
+    assert np.array_equal(s.twoFX_per_segment[1], per_seg[0, 1])
+    SC.uninstall(FakeCore)
+    with pytest.raises(AssertionError):
+        SemiCoherentSearch()._get_per_segment_twoF()

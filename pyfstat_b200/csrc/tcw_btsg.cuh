@@ -43,9 +43,14 @@ __device__ __forceinline__ double btsg_term(double maxF, float F, const double *
 // partials stay in registers over the warp's rows, row partials are combined through shared
 // memory; one FP64 atomicAdd per row / column per CTA.
 // Measured alternatives (60 d rect, T=64, pass time): scalar loads 0.70 ms; 128-bit loads
-// 0.66 ms (this version); cp.async.4 staging 1.29 ms; persistent CTAs with all 16 loads of a
-// thread issued up front (126 registers, 2 CTAs/SM) 0.95 ms -- occupancy beats per-thread
-// memory-level parallelism here.
+// 0.66 ms; + first rows' loads issued before the table-copy barrier and the UINT4 truncation
+// on the FP64 pipe 0.625 ms (this version); cp.async.4 staging 1.29 ms; persistent CTAs with
+// all 16 loads of a thread issued up front (126 registers, 2 CTAs/SM) 0.95 ms; warp-private
+// rings of 1-KB TMA bulk copies (band of 256 columns x 256 rows per CTA) 0.96 ms -- ~100 cycles
+// of TMA service per copy, serialised per SM, 2.2 M copies; persistent warp-autonomous units
+// of 32 rows x 256 columns with the column partials flushed by FP64 atomics 0.82 ms (1.7e7
+// atomics).  Many short-lived CTAs at high occupancy beat every "smarter" streaming scheme
+// tried here.
 //
 // LOCATE: the rect map kernel published max VALUES only (key index part 0); complete the key
 // with the smallest flat index whose F equals the max (first occurrence, np.argmax order).

@@ -55,7 +55,9 @@
 
 #define TCW_RECT_THREADS 256
 #ifndef TCW_RECT_MINB
-#define TCW_RECT_MINB 2  // CTAs per SM the register allocation targets (measured: 128 registers, no spills, beat 3 x 80)
+#define TCW_RECT_MINB 2  // CTAs per SM the register allocation targets.  Measured (60 d, T=64, F_mn stored): R=4 at
+                         // 2 CTAs/SM x 128 registers 0.64 ms; R=4 at 3 x 80 (spills) 0.67; R=2 rows per thread at
+                         // 3 x 80 0.67, at 4 x 64 0.74: occupancy does not buy back the shared Q fetches
 #endif
 #define TCW_RECT_WARPS (TCW_RECT_THREADS / 32)
 #ifndef TCW_RECT_DT

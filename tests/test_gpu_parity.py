@@ -511,3 +511,31 @@ def test_semicoherent_cumulative_and_bsgl_helpers(gpu, oracle, monkeypatch):
     full = np.asarray(fm.F_mn)
     assert full.shape == (n - 1, n + 1) and float(full[idx]) == fm.maxF
     assert float(cell) == pytest.approx(fm.maxF, rel=RTOL)  # generic 1x1 map vs tiled kernel
+
+
+@pytest.mark.gpu
+def test_full_size_exp_120d_config4_shape(gpu, oracle):
+    """BASELINE configs[3] shape: 120 d, H1+L1, exponential window, map 5759 x 5761 (3.3e7 cells,
+    8.5e10 atom visits -- minutes per template for the CPU oracle).  Size-independent checks:
+    fused argmax == np.argmax of the materialised map, lnBtSG == the oracle's Bstat of that map,
+    and a sample of cells (corners, the argmax, random ones) against single-cell oracle maps."""
+    n = 5760
+    b = synth_atoms(1, n, ("H1", "L1"), seed=151)
+    w = canonical_window("exp", 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    assert F.shape == (1, n - 1, n + 1) and int(res["status"][0]) == 0 and int(res["path"][0]) == 1
+    flat = int(np.argmax(F[0]))
+    assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, n + 1)
+    assert float(res["maxF"][0]) == float(F[0].max())
+    again = oracle.bstat(F[0].astype(np.float64), float(res["maxF"][0]), w, use_lut=True)
+    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=1e-10)
+    assert (int(res["m_MP"][0]), int(res["n_MP"][0])) == (again["m_MP"], again["n_MP"])
+    rng = np.random.default_rng(5)
+    cells = [(0, 0), (0, n), (n - 2, 0), (n - 2, n), divmod(flat, n + 1)]
+    cells += [(int(rng.integers(0, n - 1)), int(rng.integers(0, n + 1))) for _ in range(40)]
+    tpl = b.template(0)
+    for m, nn in cells:
+        one = TransientWindowRange(2, w.t0 + m * w.dt0, 0, w.dt0, w.tau + nn * w.dtau, 0, w.dtau)
+        o = oracle.compute_map(tpl, 1800, one, allow_degenerate=True)
+        ref = float(o["F_mn"][0, 0])
+        assert abs(float(F[0, m, nn]) - ref) <= RTOL * abs(ref), (m, nn, float(F[0, m, nn]), ref)

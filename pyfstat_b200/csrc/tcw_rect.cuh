@@ -304,7 +304,7 @@ __device__ __forceinline__ unsigned long long rect_tile(
     const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta, int t, int tz, uint32_t bx,
     uint32_t by, const MapWindow &w, const IndexGeom &g, uint32_t DD, uint32_t DT, uint32_t G,
     float *__restrict__ Fmn, uint32_t *__restrict__ flags, uint32_t *__restrict__ gmax, uint32_t top,
-    unsigned char *smem, uint64_t *bar, uint32_t phase, unsigned long long *red) {
+    unsigned char *smem, uint64_t *bar, uint32_t phase, bool init_bar, unsigned long long *red) {
     unsigned char *sp = smem;
     double *sP = reinterpret_cast<double *>(sp);        // [7][ECAP]  staged FP64 end prefixes
     f32x2 *sQ2 = reinterpret_cast<f32x2 *>(sp);         // [7][ECAP]  {q, q}, q = fl32(P[i] - P[rho]): IN PLACE over sP
@@ -339,7 +339,11 @@ __device__ __forceinline__ unsigned long long rect_tile(
         const uint32_t e_hi = index_t1(t1_tile + ((m_last - m0) / R * R) * w.dt0 + (d_last - d0) * w.dtau, t0_data,
                                        numAtoms, g);
         cnt = min((e_hi + 1 - a0 + 1 + 1) & ~1u, (uint32_t)TCW_RECT_ECAP);  // even; <= ECAP by the host check
-        if (threadIdx.x == 0) {  // the barrier was initialised by the kernel (one phase per tile)
+        if (threadIdx.x == 0) {  // one barrier phase per tile; initialised with the CTA's first tile
+            if (init_bar) {
+                mbar_init(bar, 1);
+                mbar_fence_init();
+            }
             mbar_arrive_expect_tx(bar, TCW_NCH * cnt * (uint32_t)sizeof(double));
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++)
@@ -586,8 +590,9 @@ __device__ __forceinline__ void rect_locate(const double *__restrict__ P, uint32
                 bits &= bits - 1;
                 const unsigned long long key =
                     rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, tile % gx, tile / gx, w, g, DD, DT, G, nullptr,
-                                               flags, gm + (size_t)tile * GE, top, smem, bar, phase, red);
-                if (STAGED) phase ^= 1u;
+                                               flags, gm + (size_t)tile * GE, top, smem, bar, phase & 1u, phase == 0u,
+                                               red);
+                phase++;
                 if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
                 __syncthreads();  // red[] and the staged slice are reused by the next tile
             }
@@ -616,13 +621,9 @@ tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *
     const int tz = blockIdx.z, t = t_base + tz;
     const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     uint32_t *gmax = groupmax ? groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX) : nullptr;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-    }
     const unsigned long long key = rect_tile<R, STAGED, false>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
                                                                DT, G, Fmn, flags, gmax, 0u, tcw_rect_smem, &bar, 0u,
-                                                               red);
+                                                               true, red);
     if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
 }
 
@@ -639,11 +640,6 @@ tcw_rect_locate_kernel(const double *__restrict__ P, uint32_t ppad, const TplMet
     __shared__ unsigned long long red[TCW_RECT_WARPS];
     __shared__ uint32_t hit[TCW_RECT_HITWORDS];  // bitmap of tiles holding a group with the top value
     const int tz = blockIdx.x, t = t_base + tz;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
     rect_locate<R, STAGED>(P, ppad, meta, t, tz, w, g, DD, DT, G, gx, gy, maxkey, groupmax, flags, tcw_rect_smem, &bar,
                            0u, red, hit);
 }

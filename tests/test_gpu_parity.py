@@ -539,3 +539,37 @@ def test_full_size_exp_120d_config4_shape(gpu, oracle):
         o = oracle.compute_map(tpl, 1800, one, allow_degenerate=True)
         ref = float(o["F_mn"][0, 0])
         assert abs(float(F[0, m, nn]) - ref) <= RTOL * abs(ref), (m, nn, float(F[0, m, nn]), ref)
+
+
+@pytest.mark.gpu
+def test_rect_locate_pass_ties_across_tiles(gpu):
+    """The rect map kernel tracks max VALUES only; without a lnBtSG pass the locate kernel must
+    return np.argmax's first occurrence -- also when many tiles / row groups tie, and on the
+    dt0 != dtau (one row per thread) variant."""
+    n = 1440
+    zero = np.zeros(n, dtype=ATOM_DTYPE)
+    zero["timestamp"] = 10**9 + 1800 * np.arange(n)
+    const = zero.copy()
+    const["a2_alpha"], const["b2_alpha"], const["ab_alpha"] = 0.5, 0.25, 0.125
+    const["Fa_re"], const["Fa_im"], const["Fb_re"], const["Fb_im"] = 1.0, 0.5, -0.25, 0.75
+    noise = synth_atoms(1, n, ("H1", "L1"), seed=161).template(0)
+    w = canonical_window("rect", 10**9, n)
+    w1 = TransientWindowRange(1, 10**9, 700 * 1800, 1800, 2 * 1800, 900 * 1800, 2 * 1800)  # dt0 != dtau -> R = 1
+    for tpl in ([zero], [const], noise):
+        b = batch_from_detector_lists([tpl], 1800)
+        for win in (w, w1):
+            _, F = run_gpu(gpu, b, win, 0, btsg=False, fmn=True)
+            flat = int(np.argmax(F[0]))
+            for btsg in (False, True):  # locate kernel / lnBtSG pass
+                res, none = run_gpu(gpu, b, win, 0, btsg=btsg, fmn=False)
+                assert none is None and int(res["path"][0]) == 1
+                assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, F.shape[2]), (btsg, win)
+                assert float(res["maxF"][0]) == float(F[0].max())
+    # a batch mixing the three: every template gets its own argmax
+    b3 = batch_from_detector_lists([[zero, zero], [const, const], noise], 1800)
+    res, F = run_gpu(gpu, b3, w, 0, btsg=False, fmn=True)
+    r2, _ = run_gpu(gpu, b3, w, 0, btsg=False, fmn=False)
+    for t in range(3):
+        flat = int(np.argmax(F[t]))
+        assert (int(r2["m_ML"][t]), int(r2["n_ML"][t])) == divmod(flat, F.shape[2])
+        assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])

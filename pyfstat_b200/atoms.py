@@ -126,25 +126,59 @@ def from_multi_fstat_atoms(multiFstatAtoms) -> AtomBatch:
         if int(vec.TAtom) != TAtom:
             raise ValueError("all detectors must share TAtom (XLALmergeMultiFstatAtomsBinned)")
         n = int(vec.length)
-        out = np.zeros(n, dtype=ATOM_DTYPE)
-        data = vec.data
-        # Per-atom attribute reads, like reshape_FstatAtomsVector (tcw:627-632).  A zero-copy
-        # view of the SWIG buffer is the SURVEY 8(f)-2 "next" row; it cannot be validated
-        # without lalpulsar, so the verified slow loop is what ships.
-        for i in range(n):
-            atom = data[i]
-            out["timestamp"][i] = atom.timestamp
-            out["a2_alpha"][i] = atom.a2_alpha
-            out["b2_alpha"][i] = atom.b2_alpha
-            out["ab_alpha"][i] = atom.ab_alpha
-            Fa = complex(atom.Fa_alpha)
-            Fb = complex(atom.Fb_alpha)
-            out["Fa_re"][i] = Fa.real
-            out["Fa_im"][i] = Fa.imag
-            out["Fb_re"][i] = Fb.real
-            out["Fb_im"][i] = Fb.imag
+        out = _view_swig_atoms(vec.data, n) if n >= 2 and _zero_copy_enabled() else None
+        if out is None:
+            out = np.zeros(n, dtype=ATOM_DTYPE)
+            data = vec.data
+            # per-atom attribute reads, like reshape_FstatAtomsVector (tcw:627-632)
+            for i in range(n):
+                out[i] = _read_atom(data[i])
         per_det.append(out)
     return batch_from_detector_lists([per_det], TAtom)
+
+
+def _read_atom(atom):
+    """One ``FstatAtom`` through its attributes (tcw:610-617), as an ATOM_DTYPE scalar tuple."""
+    Fa = complex(atom.Fa_alpha)
+    Fb = complex(atom.Fb_alpha)
+    return (atom.timestamp, atom.a2_alpha, atom.b2_alpha, atom.ab_alpha, Fa.real, Fa.imag, Fb.real, Fb.imag)
+
+
+def _zero_copy_enabled() -> bool:
+    import os
+
+    return os.environ.get("PYFSTAT_B200_ZERO_COPY", "1") not in ("0", "")
+
+
+def _view_swig_atoms(data, n: int):
+    """read lal's ``FstatAtom[n]`` as ONE block instead of ``6 n`` SWIG attribute reads.
+
+    lalpulsar's ``FstatAtom`` is ``{UINT4 timestamp; REAL4 a2_alpha, b2_alpha, ab_alpha; COMPLEX8
+    Fa_alpha, Fb_alpha}`` = the 32-byte ``tcw_atom`` record, and a SWIG element wrapper exposes
+    its C address as ``int(element.this)``.  Neither fact can be checked against lalpulsar in
+    the build container, so the view is VERIFIED at run time: the address stride between
+    elements 0 and 1 must be 32 bytes, and the first, second and last records must equal what
+    the attribute path reads.  Any doubt (no ``.this``, other stride, mismatch, exception)
+    returns None and the caller falls back to the per-atom loop.  The result is a copy; the
+    caller's memory is never aliased or written.
+    """
+    import ctypes
+
+    try:
+        first, second = data[0], data[1]
+        a0, a1 = int(first.this), int(second.this)
+        if a0 <= 0 or a1 - a0 != ATOM_DTYPE.itemsize:
+            return None
+        raw = (ctypes.c_char * (n * ATOM_DTYPE.itemsize)).from_address(a0)
+        out = np.frombuffer(raw, dtype=ATOM_DTYPE, count=n).copy()
+        for i in (0, 1, n - 1):
+            ref = np.zeros(1, dtype=ATOM_DTYPE)
+            ref[0] = _read_atom(data[i])
+            if out[i].tobytes() != ref[0].tobytes():
+                return None
+        return out
+    except Exception:  # noqa: BLE001 -- anything unexpected: use the verified slow path
+        return None
 
 
 # --------------------------------------------------------------------------------------

@@ -434,3 +434,70 @@ def test_semicoherent_and_bsgl_helpers(oracle, monkeypatch):
     SC.uninstall(FakeCore)
     with pytest.raises(AssertionError):
         SemiCoherentSearch()._get_per_segment_twoF()
+
+
+class _SwigThis:
+    def __init__(self, addr):
+        self._a = addr
+
+    def __int__(self):
+        return self._a
+
+
+class _SwigAtom(FakeAtom):
+    """Element wrapper as SWIG hands them out: attributes + ``.this`` = C address of the struct."""
+
+    def __init__(self, rec, addr, reads):
+        super().__init__(rec)
+        self.this = _SwigThis(addr)
+        reads[0] += 1
+
+
+class _SwigArray:
+    """View of a contiguous C array of 32-byte FstatAtom structs (here: a numpy buffer)."""
+
+    def __init__(self, arr, stride=32, corrupt=None):
+        self.arr = np.ascontiguousarray(arr)
+        self.stride, self.corrupt, self.reads = stride, corrupt, [0]
+
+    def __getitem__(self, i):
+        rec = self.arr[i]
+        if self.corrupt is not None and i == self.corrupt:
+            rec = rec.copy()
+            rec["ab_alpha"] += 1.0  # the attribute path disagrees with the raw bytes
+        return _SwigAtom(rec, self.arr.ctypes.data + i * self.stride, self.reads)
+
+
+def test_zero_copy_swig_ingest_is_verified(monkeypatch):
+    """one block read of lal's FstatAtom[] instead of 6N attribute reads -- used
+    only when the layout assumption verifies at run time, otherwise the per-atom loop."""
+    b = synth_atoms(1, 500, ("H1", "L1"), seed=41)
+
+    def multi(**kw):
+        m = FakeMulti(b)
+        for X, v in enumerate(m.data):
+            v.data = _SwigArray(b.template(0)[X], **kw)
+        return m
+
+    m = multi()
+    got = from_multi_fstat_atoms(m)
+    for X in range(2):
+        assert np.array_equal(got.template(0)[X], b.template(0)[X])
+        assert m.data[X].data.reads[0] <= 6, "block read: only the verification atoms are touched"
+        assert not np.shares_memory(got.atoms, m.data[X].data.arr)
+    # wrong stride (not the 32-byte record) or bytes that disagree with the attributes: slow path, same result
+    for kw in ({"stride": 40}, {"corrupt": 499}, {"corrupt": 1}):
+        m = multi(**kw)
+        got = from_multi_fstat_atoms(m)
+        want = [a.copy() for a in b.template(0)]
+        if "corrupt" in kw:
+            for a in want:
+                a["ab_alpha"][kw["corrupt"]] += 1.0
+        for X in range(2):
+            assert np.array_equal(got.template(0)[X], want[X])
+            assert m.data[X].data.reads[0] >= 500
+    # switch
+    monkeypatch.setenv("PYFSTAT_B200_ZERO_COPY", "0")
+    m = multi()
+    from_multi_fstat_atoms(m)
+    assert m.data[0].data.reads[0] >= 500

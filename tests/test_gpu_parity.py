@@ -573,3 +573,50 @@ def test_rect_locate_pass_ties_across_tiles(gpu):
         flat = int(np.argmax(F[t]))
         assert (int(r2["m_ML"][t]), int(r2["n_ML"][t])) == divmod(flat, F.shape[2])
         assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
+
+
+@pytest.mark.gpu
+def test_random_window_sweep_default_dispatch(gpu, oracle):
+    """160 seeded random window ranges (aligned and unaligned steps, dt0 == dtau and not, steps of
+    several atoms, bands reaching past the data, short tau) on 60..900-atom data sets through the
+    default dispatch: whatever kernel the host planner picks (tiled R=4 / R=1, staged or not, any
+    tile shape; generic otherwise), F_mn stays within tolerance of the oracle, the fused argmax
+    equals np.argmax of the GPU's own map in all three reduction modes, and the status matches."""
+    rng = np.random.default_rng(20261017)
+    n_fast = 0
+    for trial in range(160):
+        n = int(rng.choice([60, 97, 200, 333, 640, 900]))
+        b = synth_atoms(1, n, ("H1", "L1"), seed=1000 + trial, gap_fraction=float(rng.choice([0.0, 0.0, 0.08])))
+        TA = 1800
+        wtype = 1 if trial % 4 else 2
+        step = int(rng.choice([TA, TA, TA, 2 * TA, 3 * TA, 900, 2700, 1801]))
+        dt0 = step
+        dtau = step if rng.random() < 0.7 else int(rng.choice([TA, 2 * TA, 600, 4500]))
+        t0 = 10**9 + int(rng.choice([0, 0, 0, 700, -900, 5 * TA]))
+        tau = int(rng.choice([2 * TA, 2 * TA, 3 * TA, TA, 5000, dtau]))
+        Tspan = n * TA
+        t0Band = int(rng.uniform(0.05, 1.1) * Tspan)
+        tauBand = int(rng.uniform(0.05, 1.1) * Tspan) if wtype == 1 else int(rng.uniform(0.02, 0.3) * Tspan)
+        # keep the maps small enough for the oracle
+        while (t0Band // dt0 + 1) * (tauBand // dtau + 1) > 250_000:
+            t0Band //= 2
+            tauBand //= 2
+        w = TransientWindowRange(wtype, t0, t0Band, dt0, tau, tauBand, dtau)
+        res, F = run_gpu(gpu, b, w, 0)
+        o = oracle.compute_map(b.template(0), TA, w, allow_degenerate=True)
+        Fo = o["F_mn"]
+        rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+        n_fast += int(res["path"][0])
+        # two-detector data with gaps has single-detector (ill-conditioned) bins: allow the
+        # documented O(eps cond) noise on the few cells near the conditioning cut
+        bad = rel > RTOL
+        assert bad.sum() <= max(5, 2e-4 * rel.size) and rel.max() <= 5e-3, (trial, w, rel.max(), int(bad.sum()))
+        o_strict = oracle.compute_map(b.template(0), TA, w, want_btsg=False)
+        assert int(res["status"][0]) == o_strict["status"], (trial, w)
+        flat = int(np.argmax(F[0]))
+        for btsg, fmn in ((True, True), (False, False), (True, False)):
+            r2 = res if (btsg and fmn) else run_gpu(gpu, b, w, 0, btsg=btsg, fmn=fmn)[0]
+            assert (int(r2["m_ML"][0]), int(r2["n_ML"][0])) == divmod(flat, F.shape[2]), (trial, w, btsg, fmn)
+            assert float(r2["maxF"][0]) == float(F[0].max())
+        assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB), (trial, w)
+    assert n_fast >= 100, "most of the sweep must exercise the tiled kernels"

@@ -620,3 +620,19 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
             assert float(r2["maxF"][0]) == float(F[0].max())
         assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB), (trial, w)
     assert n_fast >= 100, "most of the sweep must exercise the tiled kernels"
+
+
+@pytest.mark.gpu
+def test_full_size_oracle_parity_exp_30d(gpu, oracle):
+    """BASELINE configs[1] at full size: 30 d, H1+L1, exponential window (1.33e9 atom visits; the
+    oracle needs ~10 s on one core) -- every cell within tolerance, records equal."""
+    n = 1440
+    b = synth_atoms(1, n, ("H1", "L1"), seed=171)
+    w = canonical_window("exp", 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    assert int(res["path"][0]) == 1
+    o = oracle.compute_map(b.template(0), b.TAtom, w)
+    rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
+    assert rel.max() <= RTOL
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+    assert_records_match(res, 0, o, w)

@@ -749,11 +749,24 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         float *fmn = fmn_full ? fmn_full + (size_t)t_base * pcells : fmn_scratch;
         CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 0], st));
         if (path == PATH_GENERIC) {
-            dim3 grid((unsigned)((cells + TCW_GENERIC_THREADS - 1) / TCW_GENERIC_THREADS), 1, cnt);
-#define LAUNCH_GENERIC(WT, EX)                                                                         \
-    tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                              \
-        (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins, (int)none_window, g, \
-        (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p, (uint32_t *)h->d_flags.p)
+            // few cells in the launch (MCMC steps, per-segment / cumulative / single-cell maps): one
+            // warp per cell, channels across lanes; otherwise one thread per cell.  Same results.
+            const bool warp_per_cell = (uint64_t)cells * (uint64_t)cnt <= TCW_GENERIC_WARP_MAX_CELLS;
+            const unsigned per_block = warp_per_cell ? TCW_GENERIC_WARP_THREADS / 32 : TCW_GENERIC_THREADS;
+            dim3 grid((unsigned)((cells + per_block - 1) / per_block), 1, cnt);
+#define LAUNCH_GENERIC(WT, EX)                                                                              \
+    do {                                                                                                    \
+        if (warp_per_cell)                                                                                  \
+            tcw_map_generic_warp_kernel<WT, EX><<<grid, TCW_GENERIC_WARP_THREADS, 0, st>>>(                 \
+                (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
+                (int)none_window, g, (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p,  \
+                (uint32_t *)h->d_flags.p);                                                                  \
+        else                                                                                                \
+            tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                           \
+                (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
+                (int)none_window, g, (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p,  \
+                (uint32_t *)h->d_flags.p);                                                                  \
+    } while (0)
             if (w.type == TCW_WINDOW_RECT) LAUNCH_GENERIC(TCW_WINDOW_RECT, false);
             else if (exact) LAUNCH_GENERIC(TCW_WINDOW_EXP, true);
             else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);

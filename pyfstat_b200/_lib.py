@@ -243,19 +243,34 @@ class Handle:
         return results, F
 
     def map_batch_windows(self, batch: AtomBatch, windows, flags: int = 0, *, raise_on_degenerate: bool = True):
-        """``tcw_map_batch_windows``: one window range per template (same type and map shape)."""
-        ws = [TransientWindowRange.from_any(w) for w in windows]
-        if len(ws) != batch.T:
-            raise ValueError("need one window range per template")
-        for w in ws:
-            w.check_type()
-        N_t0, N_tau = ws[0].dims()
-        cws = (CWindowRange * batch.T)(*[CWindowRange(w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau) for w in ws])
+        """``tcw_map_batch_windows``: one window range per template (same type and map shape).
+
+        ``windows``: a sequence of window-range objects, or -- the fast path for a sampler step,
+        no per-object Python work -- a ``(T, 7)`` uint32 array with the columns of
+        ``transientWindowRange_t`` (type, t0, t0Band, dt0, tau, tauBand, dtau)."""
+        if isinstance(windows, np.ndarray):
+            wa = np.ascontiguousarray(windows, dtype=np.uint32)
+            if wa.shape != (batch.T, 7):
+                raise ValueError("need one window range (7 uint32 columns) per template")
+            if (wa[:, 0] >= 3).any():
+                TransientWindowRange(int(wa[:, 0].max())).check_type()  # raises like tcw:691-697
+            w0 = TransientWindowRange(*(int(v) for v in wa[0]))
+            N_t0, N_tau = w0.dims()
+            cws = wa.ctypes.data_as(C.c_void_p)
+        else:
+            ws = [TransientWindowRange.from_any(w) for w in windows]
+            if len(ws) != batch.T:
+                raise ValueError("need one window range per template")
+            for w in ws:
+                w.check_type()
+            N_t0, N_tau = ws[0].dims()
+            cws = C.cast((CWindowRange * batch.T)(
+                *[CWindowRange(w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau) for w in ws]), C.c_void_p)
         results = np.zeros(batch.T, dtype=RESULT_DTYPE)
         F = np.empty((batch.T, N_t0, N_tau), dtype=np.float32) if flags & WANT_FMN else None
         rc = self.L.tcw_map_batch_windows(
             self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
-            batch.T, batch.numDet, C.cast(cws, C.c_void_p), flags, F.ctypes.data if F is not None else None,
+            batch.T, batch.numDet, cws, flags, F.ctypes.data if F is not None else None,
             results.ctypes.data,
         )
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)

@@ -649,7 +649,11 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     int S = T;
     if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (pcells * 4)));
     S = std::min(S, 32768);
-    if (host_atoms && T >= 16) S = std::min(S, std::max(8, (T + 3) / 4));  // upload/compute overlap
+    if (host_atoms && T >= 16) {  // sub-batches double as upload chunks: upload/compute overlap
+        int chunks = 2;  // measured: MCMC step (23.6 MB, little compute) 1.29 ms with 1-2 chunks, 1.48 with 4, 1.92 with 8
+        if (const char *env = getenv("TCW_UPLOAD_CHUNKS")) chunks = std::max(1, atoi(env));
+        S = std::min(S, std::max(8, (T + chunks - 1) / chunks));
+    }
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
     if (want_fmn) {
         if ((rc = ensure(h, h->d_Fmn, (size_t)T * pcells * sizeof(float)))) return rc;

@@ -42,7 +42,13 @@ def transient_detstat_batch(batch, tstarts, tends, transientWindowType="rect", B
         return detstat, np.zeros(0, dtype=_lib.RESULT_DTYPE)
     idx = np.flatnonzero(ok)
     sub = batch if ok.all() else type(batch)(batch.atoms[idx], batch.n_atoms[idx], batch.TAtom)
-    wins = [TransientWindowRange(wtype, int(tstarts[i]), 0, step, int(tends[i] - tstarts[i]), 0, step) for i in idx]
+    # one transientWindowRange_t row per walker: t0 = int(tstart), tau = int(tend - tstart) (core.py:1447-1449)
+    t0 = tstarts[idx].astype(np.int64)
+    tau = (tends[idx] - tstarts[idx]).astype(np.int64)
+    if t0.min() < 0 or tau.min() < 0 or t0.max() > 0xFFFFFFFF or tau.max() > 0xFFFFFFFF:
+        raise ValueError("window start times / durations do not fit UINT4")
+    wins = np.zeros((len(idx), 7), dtype=np.uint32)
+    wins[:, 0], wins[:, 1], wins[:, 3], wins[:, 4], wins[:, 6] = wtype, t0, step, tau, step
     if flags is None:
         flags = default_flags()
     flags |= _lib.WANT_BTSG if BtSG else 0

@@ -89,9 +89,8 @@ def twoFX_at_maxTwoF(batch: AtomBatch, window, records, *, device: int = -1, fla
         raise ValueError("need one result record per template")
     if flags is None:
         flags = default_flags()
-    wins = [
-        TransientWindowRange(w.type, int(r["t0_ML"]), 0, w.dt0, int(r["tau_ML"]), 0, w.dtau) for r in records
-    ]
+    wins = np.zeros((batch.T, 7), dtype=np.uint32)  # one transientWindowRange_t row per template
+    wins[:, 0], wins[:, 1], wins[:, 3], wins[:, 4], wins[:, 6] = w.type, records["t0_ML"], w.dt0, records["tau_ML"], w.dtau
     out = np.empty((batch.T, batch.numDet), dtype=np.float64)
     h = get_handle(device)
     for X in range(batch.numDet):

@@ -276,6 +276,8 @@ class OracleBackedHandle:
         return res, (np.stack(Fs) if flags & _lib.WANT_FMN else None)
 
     def map_batch_windows(self, batch, windows, flags=0, raise_on_degenerate=True):
+        if isinstance(windows, np.ndarray):  # (T, 7) uint32 rows of transientWindowRange_t
+            windows = [TransientWindowRange(*(int(v) for v in row)) for row in windows]
         recs = [self.map_batch(batch[t], w, flags, raise_on_degenerate)[0] for t, w in enumerate(windows)]
         return np.concatenate(recs), None
 

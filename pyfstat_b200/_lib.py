@@ -239,7 +239,9 @@ class Handle:
             batch.T, batch.numDet, C.byref(cw), flags, F.ctypes.data if F is not None else None,
             results.ctypes.data,
         )
+        self._last_batch = None
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        self._T, self._last_batch = batch.T, batch  # the atoms stay resident: see batch.map_again
         return results, F
 
     def map_batch_windows(self, batch: AtomBatch, windows, flags: int = 0, *, raise_on_degenerate: bool = True):
@@ -278,7 +280,7 @@ class Handle:
 
     # ---- resident API ----------------------------------------------------------------
     def upload(self, batch: AtomBatch):
-        self._keep = batch
+        self._keep = self._last_batch = batch
         self._check(
             self.L.tcw_upload_atoms(
                 self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,

@@ -33,6 +33,25 @@ def map_batch(batch: AtomBatch, window, BtSG: bool = False, want_fmn: bool = Fal
     return get_handle(device).map_batch(batch, w, flags, raise_on_degenerate=raise_on_degenerate)
 
 
+def map_again(window, batch: AtomBatch, *, BtSG: bool = False, device: int = -1, flags: int | None = None,
+              raise_on_degenerate: bool = True) -> np.ndarray:
+    """Another window range over the batch that the LAST :func:`map_batch` call on this device
+    uploaded -- its atoms are still resident, so nothing is copied host-to-device
+    (``tcw_map_resident`` + ``tcw_fetch_results``).  ``batch`` is only used to check that the
+    caller means the same batch; returns the records."""
+    if flags is None:
+        flags = default_flags()
+    flags |= _lib.WANT_BTSG if BtSG else 0
+    h = get_handle(device)
+    if getattr(h, "_last_batch", None) is not batch or not hasattr(h, "map_resident"):
+        return h.map_batch(batch, TransientWindowRange.from_any(window), flags,
+                           raise_on_degenerate=raise_on_degenerate)[0]
+    w = TransientWindowRange.from_any(window)
+    w.check_type()
+    h.map_resident(w, flags)
+    return h.fetch_results(raise_on_degenerate)
+
+
 def shard_range(T: int, rank: int, world_size: int):
     """Contiguous block of templates owned by ``rank`` (all templates cost the same for a
     fixed window range, so no dynamic balancing)."""

@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import _lib
-from .batch import gather_records, map_batch, shard_range
+from .batch import gather_records, map_again, map_batch, shard_range
 from .window import TRANSIENT_NONE, TransientWindowRange
 
 logger = logging.getLogger(__name__)
@@ -100,8 +100,9 @@ class BatchedTransientGridSearch:
                 raise ValueError("atoms_for_points returned the wrong number of templates")
             t0 = time.time()
             r, _ = map_batch(batch, self.window, BtSG=self.BtSG, device=self.device)
-            # twoF over ALL the data = the 1x1 map of TRANSIENT_NONE (tcw:742-749)
-            full, _ = map_batch(batch, TransientWindowRange(type=TRANSIENT_NONE), device=self.device)
+            # twoF over ALL the data = the 1x1 map of TRANSIENT_NONE (tcw:742-749); the atoms of the
+            # batch are still resident on the device after the first call: no second upload
+            full = map_again(TransientWindowRange(type=TRANSIENT_NONE), batch, device=self.device)
             self.timingFstatMap += time.time() - t0
             recs.append(r)
             twoF.append(2.0 * full["maxF"].astype(np.float64))

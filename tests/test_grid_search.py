@@ -75,6 +75,7 @@ def test_batched_grid_search_host_logic(oracle, monkeypatch, tmp_path):
         return res, None
 
     monkeypatch.setattr(gs, "map_batch", fake_map_batch)
+    monkeypatch.setattr(gs, "map_again", lambda window, batch, **kw: fake_map_batch(batch, window)[0])
     w = canonical_window("rect", 10**9, N_ATOMS)
     s = gs.BatchedTransientGridSearch(atoms_for_points, RANGES, w, BtSG=True, batch_size=4)
     s.run()

@@ -160,6 +160,19 @@ int tcw_map_batch_windows(tcw_handle *h, const tcw_atom *atoms, const uint32_t *
                           const tcw_window_range *wins /* [T] */, uint32_t flags, float *F_mn_out,
                           tcw_result *results);
 
+/* Asynchronous split of tcw_map_batch, for search drivers whose host side has work of its own
+ * between batches (in PyFstat: lalpulsar.ComputeFstat producing the next batch's atoms,
+ * core.py:1359-1365): tcw_submit() enqueues the H2D copies (chunked on a copy stream) and all
+ * kernels and returns without waiting; tcw_wait() waits for them and copies the records (and
+ * F_mn, when TCW_WANT_FMN was submitted) to the host.  One batch in flight per handle: a second
+ * tcw_submit (or any other map / upload call) before tcw_wait returns TCW_E_STATE.  `atoms` and
+ * `n_atoms` must stay valid and unchanged until tcw_wait returns (pinned memory for a truly
+ * asynchronous copy). */
+int tcw_submit(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,
+               uint32_t atom_stride, uint32_t TAtom, int T, int numDet,
+               const tcw_window_range *win, uint32_t flags);
+int tcw_wait(tcw_handle *h, float *F_mn_out /* NULL unless TCW_WANT_FMN */, tcw_result *results);
+
 /* Device-resident variant used by batched search drivers and by bench.py's kernel-only
  * timing: upload once, then run any number of windows on the resident atoms. */
 int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms,

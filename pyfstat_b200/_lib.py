@@ -31,7 +31,7 @@ E_INVALID, E_WINDOW, E_CUDA, E_NOMEM, E_DEGENERATE, E_STATE = -1, -2, -3, -4, -5
 
 EXPORTED_SYMBOLS = (
     "tcw_abi_version", "tcw_create", "tcw_destroy", "tcw_last_error", "tcw_device_name",
-    "tcw_map_dims", "tcw_map_batch", "tcw_map_batch_windows", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
+    "tcw_map_dims", "tcw_map_batch", "tcw_map_batch_windows", "tcw_submit", "tcw_wait", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
     "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
     "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
     "tcw_host_alloc",
@@ -122,6 +122,8 @@ def load_library(build_if_missing: bool = True):
     L.tcw_map_batch_windows.argtypes = [vp, vp, vp, u32, u32, i32, i32, vp, u32, vp, vp]
     L.tcw_upload_atoms.argtypes = [vp, vp, vp, u32, u32, i32, i32]
     L.tcw_map_resident.argtypes = [vp, C.POINTER(CWindowRange), u32]
+    L.tcw_submit.argtypes = [vp, vp, vp, u32, u32, i32, i32, C.POINTER(CWindowRange), u32]
+    L.tcw_wait.argtypes = [vp, vp, vp]
     L.tcw_fetch_results.argtypes = [vp, vp]
     L.tcw_fetch_fmn.argtypes = [vp, i32, vp]
     L.tcw_fetch_merged.argtypes = [vp, i32, vp, u32]
@@ -276,6 +278,33 @@ class Handle:
             results.ctypes.data,
         )
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        return results, F
+
+    # ---- asynchronous split of map_batch ---------------------------------------------
+    def submit(self, batch: AtomBatch, window, flags: int = 0):
+        """``tcw_submit``: enqueue copies + kernels for ``batch`` and return at once; the host is
+        free (e.g. to produce the next batch's atoms) until :meth:`wait`.  One batch in flight."""
+        w = TransientWindowRange.from_any(window)
+        w.check_type()
+        cw = c_window(w)
+        self._last_batch = None
+        self._check(self.L.tcw_submit(
+            self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
+            batch.T, batch.numDet, C.byref(cw), flags))
+        self._pending = (batch, w, flags)  # keeps the host buffers alive until wait()
+
+    def wait(self, *, raise_on_degenerate: bool = True):
+        """``tcw_wait``: ``(results, F_mn or None)`` of the submitted batch."""
+        if getattr(self, "_pending", None) is None:
+            raise TcwError(E_STATE, "wait() without a submitted batch")
+        batch, w, flags = self._pending
+        self._pending = None
+        N_t0, N_tau = w.dims()
+        results = np.zeros(batch.T, dtype=RESULT_DTYPE)
+        F = np.empty((batch.T, N_t0, N_tau), dtype=np.float32) if flags & WANT_FMN else None
+        rc = self.L.tcw_wait(self._h, F.ctypes.data if F is not None else None, results.ctypes.data)
+        self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        self._T, self._last_batch = batch.T, batch
         return results, F
 
     # ---- resident API ----------------------------------------------------------------

@@ -33,6 +33,22 @@ def map_batch(batch: AtomBatch, window, BtSG: bool = False, want_fmn: bool = Fal
     return get_handle(device).map_batch(batch, w, flags, raise_on_degenerate=raise_on_degenerate)
 
 
+def submit_batch(batch: AtomBatch, window, BtSG: bool = False, *, device: int = -1, flags: int | None = None):
+    """Asynchronous :func:`map_batch`: enqueue the copies and kernels (``tcw_submit``) and return a
+    ticket; the host is free until :func:`wait_batch`.  One batch in flight per device."""
+    if flags is None:
+        flags = default_flags()
+    flags |= _lib.WANT_BTSG if BtSG else 0
+    h = get_handle(device)
+    h.submit(batch, TransientWindowRange.from_any(window), flags)
+    return h
+
+
+def wait_batch(ticket, *, raise_on_degenerate: bool = True) -> np.ndarray:
+    """Records of the batch submitted with :func:`submit_batch` (``tcw_wait``)."""
+    return ticket.wait(raise_on_degenerate=raise_on_degenerate)[0]
+
+
 def map_again(window, batch: AtomBatch, *, BtSG: bool = False, device: int = -1, flags: int | None = None,
               raise_on_degenerate: bool = True) -> np.ndarray:
     """Another window range over the batch that the LAST :func:`map_batch` call on this device

@@ -54,6 +54,7 @@ struct tcw_handle {
     cudaDeviceProp prop;
     uint64_t launches = 0;
 
+    bool in_flight = false, in_flight_fmn = false;  // tcw_submit .. tcw_wait
     // resident batch
     bool uploaded = false;
     int T = 0, numDet = 0;
@@ -310,6 +311,7 @@ static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n
     if (!h) return TCW_E_INVALID;
     if (!atoms || !n_atoms || T < 1 || numDet < 1 || atom_stride < 1 || TAtom < 1)
         return fail(h, TCW_E_INVALID, "tcw_upload_atoms: bad argument");
+    if (h->in_flight) return fail(h, TCW_E_STATE, "a submitted batch is in flight: call tcw_wait first");
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->uploaded = false;
     h->have_fmn = false;
@@ -535,6 +537,8 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     if (!h) return TCW_E_INVALID;
     if (!win) return fail(h, TCW_E_INVALID, "tcw_map_resident: window range is NULL");
     if (!h->uploaded) return fail(h, TCW_E_STATE, "tcw_map_resident: no resident atoms (call tcw_upload_atoms)");
+    if (h->in_flight && host_atoms == nullptr)
+        return fail(h, TCW_E_STATE, "a submitted batch is in flight: call tcw_wait first");
     if (win->type >= TCW_WINDOW_LAST)
         return fail(h, TCW_E_WINDOW, "Unknown window-type (" + std::to_string(win->type) +
                                          ") passed as input. Allowed are [0," +
@@ -955,6 +959,33 @@ extern "C" int tcw_map_batch(tcw_handle *h, const tcw_atom *atoms, const uint32_
         CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,
                                       (size_t)h->last_pitch * sizeof(float), (size_t)h->last_N_tau * sizeof(float),
                                       (size_t)T * h->last_N_t0, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return tcw_fetch_results(h, results);
+}
+
+extern "C" int tcw_submit(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_atoms, uint32_t atom_stride,
+                          uint32_t TAtom, int T, int numDet, const tcw_window_range *win, uint32_t flags) {
+    if (!h) return TCW_E_INVALID;
+    if (h->in_flight) return fail(h, TCW_E_STATE, "tcw_submit: a batch is already in flight (call tcw_wait)");
+    int rc = upload_common(h, atoms, n_atoms, atom_stride, TAtom, T, numDet, false);
+    if (rc) return rc;
+    rc = map_impl(h, win, flags, atoms);
+    if (rc) return rc;
+    h->in_flight = true;
+    h->in_flight_fmn = (flags & TCW_WANT_FMN) != 0;
+    return TCW_OK;
+}
+
+extern "C" int tcw_wait(tcw_handle *h, float *F_mn_out, tcw_result *results) {
+    if (!h) return TCW_E_INVALID;
+    if (!h->in_flight) return fail(h, TCW_E_STATE, "tcw_wait: no batch in flight (call tcw_submit)");
+    if (!results) return fail(h, TCW_E_INVALID, "tcw_wait: results is NULL");
+    if (h->in_flight_fmn && !F_mn_out) return fail(h, TCW_E_INVALID, "tcw_wait: the batch was submitted with TCW_WANT_FMN");
+    h->in_flight = false;
+    if (h->in_flight_fmn) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(F_mn_out, (size_t)h->last_N_tau * sizeof(float), h->d_Fmn.p,
+                                      (size_t)h->last_pitch * sizeof(float), (size_t)h->last_N_tau * sizeof(float),
+                                      (size_t)h->T * h->last_N_t0, cudaMemcpyDeviceToHost, h->stream));
     }
     return tcw_fetch_results(h, results);
 }

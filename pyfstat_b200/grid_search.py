@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import _lib
-from .batch import gather_records, map_again, map_batch, shard_range
+from .batch import gather_records, map_again, shard_range, submit_batch, wait_batch
 from .window import TRANSIENT_NONE, TransientWindowRange
 
 logger = logging.getLogger(__name__)
@@ -93,17 +93,30 @@ class BatchedTransientGridSearch:
     def _records_for_range(self, lo, hi):
         """Map records + full-coherent F for grid points [lo, hi), batch by batch."""
         recs, twoF = [], []
-        for a in range(lo, hi, self.batch_size):
+        starts = list(range(lo, hi, self.batch_size))
+
+        def produce(a):
             b = min(a + self.batch_size, hi)
             batch = self.atoms_for_points(self.input_data[a:b])
             if batch.T != b - a:
                 raise ValueError("atoms_for_points returned the wrong number of templates")
+            return batch
+
+        nxt = produce(starts[0]) if starts else None
+        for k, a in enumerate(starts):
+            batch = nxt
             t0 = time.time()
-            r, _ = map_batch(batch, self.window, BtSG=self.BtSG, device=self.device)
+            ticket = submit_batch(batch, self.window, BtSG=self.BtSG, device=self.device)
+            t_sub = time.time() - t0
+            # the GPU works on this batch while the host produces the atoms of the next one
+            # (in a real search: lalpulsar.ComputeFstat per Doppler point, core.py:1359-1365)
+            nxt = produce(starts[k + 1]) if k + 1 < len(starts) else None
+            t0 = time.time()
+            r = wait_batch(ticket)
             # twoF over ALL the data = the 1x1 map of TRANSIENT_NONE (tcw:742-749); the atoms of the
             # batch are still resident on the device after the first call: no second upload
             full = map_again(TransientWindowRange(type=TRANSIENT_NONE), batch, device=self.device)
-            self.timingFstatMap += time.time() - t0
+            self.timingFstatMap += t_sub + time.time() - t0
             recs.append(r)
             twoF.append(2.0 * full["maxF"].astype(np.float64))
         if not recs:

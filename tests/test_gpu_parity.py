@@ -636,3 +636,30 @@ def test_full_size_oracle_parity_exp_30d(gpu, oracle):
     assert rel.max() <= RTOL
     assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
     assert_records_match(res, 0, o, w)
+
+
+@pytest.mark.gpu
+def test_submit_wait_equals_map_batch(gpu):
+    """tcw_submit / tcw_wait (asynchronous split of tcw_map_batch): same records and map, one batch
+    in flight, resident follow-up map after the wait."""
+    b = synth_atoms(6, 300, ("H1", "L1"), seed=181)
+    for win in ("rect", "exp"):
+        w = canonical_window(win, 10**9, 300)
+        ref, Fref = gpu.map_batch(b, w, L.WANT_FMN | L.WANT_BTSG)
+        gpu.submit(b, w, L.WANT_FMN | L.WANT_BTSG)
+        with pytest.raises(L.TcwError):
+            gpu.submit(b, w, 0)  # second submit before wait
+        with pytest.raises(L.TcwError):
+            gpu.map_batch(b, w, 0)  # any other map while a batch is in flight
+        res, F = gpu.wait()
+        assert np.array_equal(F, Fref)
+        for k in ("maxF", "m_ML", "n_ML", "t0_ML", "tau_ML", "m_MP", "n_MP", "status"):
+            assert np.array_equal(res[k], ref[k]), k
+        assert np.allclose(res["lnBtSG"], ref["lnBtSG"], rtol=0, atol=1e-12)
+        with pytest.raises(L.TcwError):
+            gpu.wait()
+        # the batch stays resident: the full-span (TRANSIENT_NONE) map needs no second upload
+        gpu.map_resident(TransientWindowRange(type=0), 0)
+        full = gpu.fetch_results()
+        again, _ = gpu.map_batch(b, TransientWindowRange(type=0), 0)
+        assert np.array_equal(full["maxF"], again["maxF"])

@@ -74,7 +74,19 @@ def test_batched_grid_search_host_logic(oracle, monkeypatch, tmp_path):
                 res[k][t] = r[k]
         return res, None
 
-    monkeypatch.setattr(gs, "map_batch", fake_map_batch)
+    in_flight = []
+
+    def fake_submit(batch, window, BtSG=False, **kw):
+        assert not in_flight, "one batch in flight"
+        in_flight.append((batch, window, BtSG))
+        return in_flight
+
+    def fake_wait(ticket, **kw):
+        batch, window, BtSG = ticket.pop()
+        return fake_map_batch(batch, window, BtSG)[0]
+
+    monkeypatch.setattr(gs, "submit_batch", fake_submit)
+    monkeypatch.setattr(gs, "wait_batch", fake_wait)
     monkeypatch.setattr(gs, "map_again", lambda window, batch, **kw: fake_map_batch(batch, window)[0])
     w = canonical_window("rect", 10**9, N_ATOMS)
     s = gs.BatchedTransientGridSearch(atoms_for_points, RANGES, w, BtSG=True, batch_size=4)

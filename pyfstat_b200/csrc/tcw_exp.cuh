@@ -34,7 +34,9 @@
 #include "tcw_prep.cuh"
 
 #define TCW_EXP_KC 32      // k-steps per staged chunk (64: -2% at 30 d with FFMA2)
-#define TCW_EXP_STAGES 3
+#ifndef TCW_EXP_STAGES
+#define TCW_EXP_STAGES 3    // measured: 2, 3 and 4 stages give the same time (41.2 ms / 128 30-d maps): staging is fully hidden
+#endif
 #define TCW_EXP_TNT 16     // threads along tau per CTA (fixed); a warp = 2 (t0) x 16 (tau) threads
 
 // Tile configuration: NT threads, RM x RN cells per thread.

@@ -371,7 +371,8 @@ def test_mixed_geometry_batch(gpu, oracle):
 # ---- BASELINE sizes: size-independent properties ---------------------------------------------
 
 
-@pytest.mark.parametrize("win,n,dets", [("rect", 1440, ("H1",)), ("exp", 1440, ("H1", "L1")), ("rect", 2880, ("H1", "L1"))])
+@pytest.mark.parametrize("win,n,dets", [("rect", 1440, ("H1",)), ("exp", 1440, ("H1", "L1")), ("rect", 2880, ("H1", "L1")),
+                                          ("rect", 5760, ("H1", "L1"))])
 def test_full_size_properties(gpu, oracle, win, n, dets):
     """Configs 1-3 at full size.  (a) fused max/argmax == np.argmax of the materialised map;
     (b) lnBtSG == oracle's Bstat of that very map; (c) scaling the atoms by powers of two
@@ -663,3 +664,18 @@ def test_submit_wait_equals_map_batch(gpu):
         full = gpu.fetch_results()
         again, _ = gpu.map_batch(b, TransientWindowRange(type=0), 0)
         assert np.array_equal(full["maxF"], again["maxF"])
+
+
+@pytest.mark.gpu
+def test_full_size_oracle_parity_rect_120d(gpu, oracle):
+    """120 d rect map (3.3e7 cells; four regular tiles of 1440 d per row tile, i.e. with guarded
+    remainder chunks) against the oracle at full size."""
+    n = 5760
+    b = synth_atoms(1, n, ("H1", "L1"), seed=191)
+    w = canonical_window("rect", 10**9, n)
+    res, F = run_gpu(gpu, b, w, 0)
+    o = oracle.compute_map(b.template(0), b.TAtom, w)
+    rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
+    assert rel.max() <= RTOL
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+    assert_records_match(res, 0, o, w)

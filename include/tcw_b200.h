@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TCW_ABI_VERSION 1
+#define TCW_ABI_VERSION 2
 
 /* lalpulsar transientWindowType_t values used by the reference
  * (tcw:691-697, 742-743, 793-807; pyfstat/core.py:828-840).  lalpulsar is not importable
@@ -60,6 +60,21 @@ extern "C" {
 #define TCW_FORCE_GENERIC    0x10u /* always use the generic (any window geometry, bit-faithful
                                       sequential float32) kernels instead of the tiled fast
                                       kernels; used by the parity tests                     */
+#define TCW_BTSG_TABLE       0x20u /* lnBtSG pass: fetch every term from the XLALFastNegExp table
+                                      and sum in FP64 (the very values lalpulsar adds) instead of
+                                      recomputing the looked-up entry e^{-i0 dx} on the fly (same
+                                      table index, value to ~3e-7 relative).  Implied when a
+                                      non-canonical table was installed with tcw_set_exp_lut    */
+
+/* Default geometry of the emulated XLALFastNegExp table (lalpulsar/lib/TransientCW_utils.c,
+ * not in the reference tree): e^{-x} on [0, XMAX] in LENGTH steps, nearest-point lookup
+ * LUT[(UINT4)(x * LENGTH/XMAX + 0.5)], 0 beyond XMAX.  SURVEY A.4-1 records 1/dx = 256
+ * (5120 steps); the other recollection on file is 2000 steps (dx = 0.01).  Neither can be
+ * verified in the build container, so the geometry is a RUNTIME property of the handle:
+ * tcw_set_exp_lut(), or $TCW_EXP_LUT="xmax:length" at tcw_create().  The Python layer measures
+ * it from lalpulsar itself whenever lalpulsar is importable (pyfstat_b200/lut_probe.py). */
+#define TCW_EXPLUT_DEFAULT_XMAX   20.0
+#define TCW_EXPLUT_DEFAULT_LENGTH 5120u
 
 /* One F-stat atom, in the field order of lalpulsar's FstatAtom as read by the reference
  * (tcw:610-617: timestamp u32; a2_alpha, b2_alpha, ab_alpha f32; Fa_alpha, Fb_alpha c8).
@@ -107,6 +122,12 @@ typedef struct tcw_handle tcw_handle;
 /* ABI version of the loaded library (== TCW_ABI_VERSION of the header it was built from). */
 int tcw_abi_version(void);
 
+/* Device enumeration without opening a context or a handle (replaces drv.Device.count() /
+ * drv.Device(n).name() in init_transient_fstat_map_features, tcw:419-432): number of CUDA
+ * devices (0 if none / no driver), and the name of device `device`. */
+int tcw_device_count(void);
+int tcw_device_name_of(int device, char *buf, int buflen);
+
 /* Replaces the pycuda context creation in init_transient_fstat_map_features (tcw:395-484):
  * binds a handle to CUDA device `device`, creates its stream and events.  `device < 0`
  * honours $CUDA_DEVICE like the reference (tcw:434-437, 466-469), default 0. */
@@ -121,6 +142,15 @@ const char *tcw_last_error(const tcw_handle *h);
 /* Device name, as the reference logs it / matches cudaDeviceName against (tcw:419-476). */
 int tcw_device_name(const tcw_handle *h, char *buf, int buflen);
 
+/* Geometry (and optionally the contents) of the XLALFastNegExp table this handle emulates for
+ * the exponential-window weights (replaces the `lal` path's XLALFastNegExp calls behind
+ * lalpulsar.ComputeTransientFstatMap, tcw:571-575) and for the lnBtSG / posterior terms
+ * (lalpulsar.ComputeTransientBstat, tcw:578-586).  `table` is NULL (entries exp(-i*xmax/length)
+ * computed with the host libm, as XLALCreateExpLUT does) or points to length+1 doubles, e.g.
+ * measured from lalpulsar.  Invalidates the cached weight table.  1 <= length <= 2^22. */
+int tcw_set_exp_lut(tcw_handle *h, double xmax, uint32_t length, const double *table);
+int tcw_get_exp_lut(const tcw_handle *h, double *xmax, uint32_t *length, int *canonical);
+
 /* N_t0Range = floor(t0Band/dt0)+1, N_tauRange = floor(tauBand/dtau)+1 (tcw:775-780).
  * Host-only helper, needs no device. */
 int tcw_map_dims(const tcw_window_range *win, uint32_t *N_t0, uint32_t *N_tau);
@@ -132,8 +162,10 @@ int tcw_map_dims(const tcw_window_range *win, uint32_t *N_t0, uint32_t *N_tau);
  *
  *   atoms    host buffer (pinned or pageable), T*numDet detector vectors, each `atom_stride`
  *            atoms apart: vector (t,X) starts at atoms[(t*numDet + X)*atom_stride].
- *            Timestamps must be strictly increasing within a vector.
- *   n_atoms  [T*numDet] number of valid atoms of each vector (1 <= n <= atom_stride)
+ *            Timestamps must be non-decreasing within a vector (atoms falling into the same
+ *            TAtom bin are summed, as XLALmergeMultiFstatAtomsBinned does).
+ *   n_atoms  [T*numDet] number of valid atoms of each vector (0 <= n <= atom_stride; every
+ *            template needs at least one atom in some detector)
  *   TAtom    atom duration = multiFstatAtoms.data[0].TAtom (tcw:704), same for all detectors
  *   win      window range (TRANSIENT_NONE is replaced internally by a rect window spanning
  *            the data, tcw:742-749, on a copy)

@@ -17,8 +17,9 @@
  * The `lal`-only behaviours (TCW_SEM_LAL) are restated from the published lalsuite algorithm
  * as recalled; each is behind a switch and listed in DESIGN.md:
  *   L1 exponential weights and the lnBtSG terms come from the lookup table XLALFastNegExp:
- *      e^{-x} tabulated on [0, EXPLUT_XMAX=20] with EXPLUT_LENGTH=2000 steps, nearest point
- *      `LUT[(UINT4)(x*100 + 0.5)]`, 0 for x > 20, libm exp for x < 0;
+ *      e^{-x} tabulated on [0, xmax] in `length` steps, nearest point
+ *      `LUT[(UINT4)(x*length/xmax + 0.5)]`, 0 for x > xmax, libm exp for x < 0; xmax and length
+ *      are run-time settings (default 20 / 5120 = SURVEY A.4-1; the other recollection is 20 / 2000);
  *   L2 REAL4 accumulators; in the exponential case each term is `REAL4 * REAL8 window value`
  *      evaluated in double and added to the REAL4 accumulator;
  *   L3 a cell with i_t1 == i_t0 aborts the map (XLAL_EDOM);
@@ -66,34 +67,59 @@ typedef struct {
     int32_t status;
 } oracle_result_t;
 
-/* ---- XLALFastNegExp (recalled, L1) ------------------------------------------------------ */
-#define EXPLUT_XMAX 20.0
-#define EXPLUT_LENGTH 2000
-static double expLUT[EXPLUT_LENGTH + 1];
-static int expLUT_ready = 0;
+/* ---- XLALFastNegExp (L1; lalpulsar/lib/TransientCW_utils.c, restated) ----------------------
+ * Table of e^{-x} on [0, xmax] with `length` steps (length + 1 entries, entry i = exp(-(i*dx)),
+ * dx = xmax/length), nearest-point lookup LUT[(UINT4)(mx * (length/xmax) + 0.5)], 0 for
+ * mx > xmax, libm exp for mx < 0.  The geometry is a RUNTIME setting (oracle_set_exp_lut):
+ * SURVEY A.4-1 records xmax = 20, 1/dx = 256 (length 5120), the default here; the other
+ * recollection on file is length 2000 (dx = 0.01).  Neither is verifiable without lalsuite. */
+static double explut_xmax = 20.0;
+static uint32_t explut_length = 5120;
+static double *expLUT = NULL;
+static uint32_t expLUT_entries = 0;
 
 static void create_exp_lut(void) {
-    double dx = EXPLUT_XMAX / EXPLUT_LENGTH;
-    for (int i = 0; i <= EXPLUT_LENGTH; i++) expLUT[i] = exp(-(i * dx));
-    expLUT_ready = 1;
+    double dx = explut_xmax / explut_length;
+    double *t = (double *)malloc(((size_t)explut_length + 1) * sizeof(double));
+    for (uint32_t i = 0; i <= explut_length; i++) t[i] = exp(-(i * dx));
+    expLUT = t;
+    expLUT_entries = explut_length + 1;
+}
+
+/* not thread-safe: call before any map (tests / bench do so from the main thread) */
+int oracle_set_exp_lut(double xmax, uint32_t length) {
+    if (!(xmax > 0) || length < 1) return ERR_INVALID;
+    free(expLUT);
+    expLUT = NULL;
+    explut_xmax = xmax;
+    explut_length = length;
+    create_exp_lut();
+    return 0;
+}
+
+void oracle_get_exp_lut(double *xmax, uint32_t *length) {
+    *xmax = explut_xmax;
+    *length = explut_length;
 }
 
 static inline double fast_neg_exp(double mx) {
-    if (mx > EXPLUT_XMAX) return 0.0;
+    if (mx > explut_xmax) return 0.0;
     if (mx < 0) return exp(-mx);
-    if (!expLUT_ready) create_exp_lut();
-    uint32_t i0 = (uint32_t)(mx * ((EXPLUT_LENGTH) / (EXPLUT_XMAX)) + 0.5);
+    uint32_t i0 = (uint32_t)(mx * ((explut_length) / (explut_xmax)) + 0.5);
     return expLUT[i0];
 }
 
-double oracle_fast_neg_exp(double mx) { return fast_neg_exp(mx); }
+double oracle_fast_neg_exp(double mx) {
+    if (!expLUT) create_exp_lut();
+    return fast_neg_exp(mx);
+}
 
 /* copy of the table for the tests (so the CUDA side can be checked entry by entry) */
 int oracle_exp_lut(double *out, int capacity) {
-    if (!expLUT_ready) create_exp_lut();
-    if (capacity < EXPLUT_LENGTH + 1) return ERR_INVALID;
-    memcpy(out, expLUT, sizeof(expLUT));
-    return EXPLUT_LENGTH + 1;
+    if (!expLUT) create_exp_lut();
+    if (capacity < (int)expLUT_entries) return ERR_INVALID;
+    memcpy(out, expLUT, (size_t)expLUT_entries * sizeof(double));
+    return (int)expLUT_entries;
 }
 
 /* ---- detector merge (tcw:702-709; rule recalled, L4) ------------------------------------ */
@@ -104,13 +130,17 @@ int oracle_merge_binned(const atom_t *atoms, const uint32_t *n_atoms, int numDet
                         uint32_t stride, uint32_t TAtom, atom_t *out, uint32_t capacity,
                         uint32_t *numOut) {
     if (!atoms || !n_atoms || numDet < 1 || TAtom == 0) return ERR_INVALID;
-    uint32_t tMin = 0x7fffffffu - 1, tMax = 0;
+    uint32_t tMin = 0xffffffffu, tMax = 0;
+    int any = 0;
     for (int X = 0; X < numDet; X++) {
-        if (n_atoms[X] == 0 || n_atoms[X] > stride) return ERR_INVALID;
+        if (n_atoms[X] > stride) return ERR_INVALID;
+        if (n_atoms[X] == 0) continue; /* a detector without atoms contributes nothing */
+        any = 1;
         const atom_t *a = atoms + (size_t)X * stride;
         if (a[0].timestamp < tMin) tMin = a[0].timestamp;
         if (a[n_atoms[X] - 1].timestamp > tMax) tMax = a[n_atoms[X] - 1].timestamp;
     }
+    if (!any || tMax < tMin) return ERR_INVALID;
     uint32_t N = (uint32_t)floor(1.0 * (tMax - tMin) / TAtom) + 1;
     *numOut = N;
     if (N > capacity) return ERR_INVALID;
@@ -258,6 +288,7 @@ int oracle_map(const atom_t *merged, uint32_t numAtoms, uint32_t TAtom, const wi
                int semantics, int exact_exp, int allow_degenerate, int rect_vanilla, double *F_mn,
                oracle_result_t *res) {
     if (!merged || !win_in || !res || numAtoms == 0 || TAtom == 0) return ERR_INVALID;
+    if (!expLUT) create_exp_lut();
     window_range_t w = *win_in; /* by value: never mutate the caller's (tcw:742-749 does) */
     if (w.type >= WIN_LAST) return ERR_WINDOW;
     uint32_t t0_data = merged[0].timestamp;
@@ -361,6 +392,7 @@ int oracle_map(const atom_t *merged, uint32_t numAtoms, uint32_t TAtom, const wi
 int oracle_bstat(const double *F_mn, uint32_t N_t0, uint32_t N_tau, double maxF,
                  const window_range_t *win, int use_lut, oracle_result_t *res) {
     if (!F_mn || !res || N_t0 == 0 || N_tau == 0) return ERR_INVALID;
+    if (!expLUT) create_exp_lut();
     double sum_eB = 0;
     double *rows = (double *)calloc(N_t0, sizeof(double));
     double *cols = (double *)calloc(N_tau, sizeof(double));
@@ -405,7 +437,7 @@ int oracle_template(const atom_t *atoms, const uint32_t *n_atoms, int numDet, ui
     /* upper bound on bins: span/TAtom + 1 */
     uint32_t tMin = 0xffffffffu, tMax = 0;
     for (int X = 0; X < numDet; X++) {
-        if (n_atoms[X] == 0) return ERR_INVALID;
+        if (n_atoms[X] == 0) continue;
         const atom_t *a = atoms + (size_t)X * stride;
         if (a[0].timestamp < tMin) tMin = a[0].timestamp;
         if (a[n_atoms[X] - 1].timestamp > tMax) tMax = a[n_atoms[X] - 1].timestamp;
@@ -458,6 +490,7 @@ int oracle_batch(const atom_t *atoms, const uint32_t *n_atoms, uint32_t stride, 
                  int T, int numDet, const window_range_t *win, int semantics, int exact_exp,
                  int allow_degenerate, int want_btsg, int num_threads, oracle_result_t *results) {
     int worst = 0;
+    if (!expLUT) create_exp_lut(); /* before the threads start */
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads > 0 ? num_threads : 1)
 #endif

@@ -85,6 +85,7 @@ def lib():
         L.oracle_fstat_from_sums.restype = C.c_float
         L.oracle_fstat_from_sums.argtypes = [C.c_float] * 7
         L.oracle_index_range.restype = None
+        L.oracle_set_exp_lut.argtypes = [C.c_double, C.c_uint32]
         _lib = L
     return _lib
 
@@ -112,10 +113,24 @@ def fast_neg_exp(x: float) -> float:
     return lib().oracle_fast_neg_exp(float(x))
 
 
+def set_exp_lut(xmax: float = 20.0, length: int = 5120) -> None:
+    """Geometry of the emulated XLALFastNegExp table (default: SURVEY A.4-1, 20 / 5120)."""
+    rc = lib().oracle_set_exp_lut(float(xmax), int(length))
+    if rc:
+        raise ValueError("oracle_set_exp_lut failed")
+
+
+def get_exp_lut():
+    x, n = C.c_double(), C.c_uint32()
+    lib().oracle_get_exp_lut(C.byref(x), C.byref(n))
+    return x.value, n.value
+
+
 def exp_lut() -> np.ndarray:
-    out = np.zeros(2001, dtype=np.float64)
-    n = lib().oracle_exp_lut(_ptr(out), 2001)
-    assert n == 2001
+    _, length = get_exp_lut()
+    out = np.zeros(length + 1, dtype=np.float64)
+    n = lib().oracle_exp_lut(_ptr(out), length + 1)
+    assert n == length + 1
     return out
 
 
@@ -141,7 +156,7 @@ def index_range(wtype, t0_m, tau_n, t0_data, TAtom, numAtoms):
 
 def _pack(det_arrays):
     numDet = len(det_arrays)
-    stride = max(len(a) for a in det_arrays)
+    stride = max(1, max(len(a) for a in det_arrays))
     atoms = np.zeros((numDet, stride), dtype=ATOM_DTYPE)
     n_atoms = np.zeros(numDet, dtype=np.uint32)
     for X, a in enumerate(det_arrays):
@@ -153,8 +168,8 @@ def _pack(det_arrays):
 def merge_binned(det_arrays, TAtom: int) -> np.ndarray:
     """XLALmergeMultiFstatAtomsBinned restatement -> merged ATOM_DTYPE array."""
     atoms, n_atoms, stride = _pack(det_arrays)
-    tmin = min(int(a["timestamp"][0]) for a in det_arrays)
-    tmax = max(int(a["timestamp"][-1]) for a in det_arrays)
+    tmin = min(int(a["timestamp"][0]) for a in det_arrays if len(a))
+    tmax = max(int(a["timestamp"][-1]) for a in det_arrays if len(a))
     cap = (tmax - tmin) // TAtom + 2
     out = np.zeros(cap, dtype=ATOM_DTYPE)
     N = C.c_uint32()

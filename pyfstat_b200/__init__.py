@@ -23,6 +23,7 @@ from .backend import (
     unregister,
 )
 from . import semicoherent
+from .mcmc import TransientWalkerPool, transient_detstat_batch
 from .window import (
     TRANSIENT_EXPONENTIAL,
     TRANSIENT_LAST,
@@ -35,7 +36,7 @@ from .window import (
 __all__ = [
     "ATOM_DTYPE", "AtomBatch", "batch_from_detector_lists", "from_multi_fstat_atoms", "synth_atoms",
     "BACKEND_NAME", "b200_compute_transient_fstat_map", "backend_available", "fstat_map_class",
-    "get_handle", "register", "unregister", "semicoherent",
+    "get_handle", "register", "unregister", "semicoherent", "TransientWalkerPool", "transient_detstat_batch",
     "TRANSIENT_NONE", "TRANSIENT_RECTANGULAR", "TRANSIENT_EXPONENTIAL", "TRANSIENT_LAST",
     "TransientWindowRange", "canonical_window",
 ]

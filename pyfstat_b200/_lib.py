@@ -17,7 +17,7 @@ from .window import TransientWindowRange
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libtcw_b200.so")
 
-TCW_ABI_VERSION = 1
+TCW_ABI_VERSION = 2
 
 # flags (include/tcw_b200.h)
 WANT_FMN = 0x1
@@ -25,6 +25,10 @@ WANT_BTSG = 0x2
 EXP_EXACT = 0x4
 ALLOW_DEGENERATE = 0x8
 FORCE_GENERIC = 0x10
+BTSG_TABLE = 0x20
+
+# default geometry of the emulated XLALFastNegExp table (TCW_EXPLUT_DEFAULT_* in the header)
+EXPLUT_DEFAULT = (20.0, 5120)
 
 # error codes
 E_INVALID, E_WINDOW, E_CUDA, E_NOMEM, E_DEGENERATE, E_STATE = -1, -2, -3, -4, -5, -6
@@ -35,7 +39,8 @@ EXPORTED_SYMBOLS = (
     "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
     "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
     "tcw_host_alloc",
-    "tcw_host_free", "tcw_cell_index_range",
+    "tcw_host_free", "tcw_cell_index_range", "tcw_set_exp_lut", "tcw_get_exp_lut",
+    "tcw_device_count", "tcw_device_name_of",
 )
 
 
@@ -141,8 +146,24 @@ def load_library(build_if_missing: bool = True):
     L.tcw_host_free.argtypes = [vp]
     L.tcw_host_free.restype = None
     L.tcw_cell_index_range.argtypes = [u32, u32, u32, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    L.tcw_device_count.argtypes = []
+    L.tcw_device_count.restype = i32
+    L.tcw_device_name_of.argtypes = [i32, C.c_char_p, i32]
+    L.tcw_set_exp_lut.argtypes = [vp, C.c_double, u32, vp]
+    L.tcw_get_exp_lut.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(i32)]
     _lib = L
     return L
+
+
+def device_names(build_if_missing: bool = False):
+    """Names of the CUDA devices, without opening a context or a handle (tcw:419-432)."""
+    L = load_library(build_if_missing)
+    out = []
+    for d in range(L.tcw_device_count()):
+        buf = C.create_string_buffer(256)
+        if L.tcw_device_name_of(d, buf, 256) == 0:
+            out.append(buf.value.decode())
+    return out
 
 
 def c_window(w) -> CWindowRange:
@@ -163,7 +184,11 @@ def cell_index_range(window_type, t0_m, tau_n, t0_data, TAtom, numAtoms):
 
 
 class PinnedBuffer:
-    """cudaHostAlloc'ed buffer exposing the Python buffer protocol through a ctypes array."""
+    """cudaHostAlloc'ed buffer exposing the Python buffer protocol through a ctypes array.
+
+    Lifetime: ``array`` (and therefore every ``np.frombuffer`` view of it, whose ``.base`` chain
+    holds the ctypes array) keeps this object -- the owner of the allocation -- alive through
+    ``array._owner``; ``cudaFreeHost`` runs only once the last view is gone."""
 
     def __init__(self, nbytes: int):
         L = load_library()
@@ -172,6 +197,7 @@ class PinnedBuffer:
             raise MemoryError(f"cudaHostAlloc({nbytes}) failed")
         self.nbytes = nbytes
         self.array = (C.c_ubyte * nbytes).from_address(self._ptr)
+        self.array._owner = self  # the exported buffer owns the allocation (cycle: freed by the gc)
 
     def __del__(self):
         ptr, self._ptr = getattr(self, "_ptr", None), None
@@ -191,6 +217,9 @@ class Handle:
             raise TcwError(rc, (self.L.tcw_last_error(None) or b"").decode())
         self._h = h
         self._keep = None  # keeps the uploaded host arrays alive
+        self._last_batch = None  # the batch whose atoms are resident on the device
+        self.device_index = device
+        self.generation = 0  # bumped by every map: tells whether the device F_mn is still a given map's
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -219,6 +248,23 @@ class Handle:
             raise MemoryError(msg)
         raise TcwError(rc, msg)
 
+    def set_exp_lut(self, xmax: float = EXPLUT_DEFAULT[0], length: int = EXPLUT_DEFAULT[1], table=None):
+        """``tcw_set_exp_lut``: geometry (and optionally the ``length + 1`` entries) of the emulated
+        XLALFastNegExp table."""
+        tab = None
+        if table is not None:
+            tab = np.ascontiguousarray(table, dtype=np.float64)
+            if tab.shape != (int(length) + 1,):
+                raise ValueError("table needs length + 1 entries")
+        self._check(self.L.tcw_set_exp_lut(self._h, float(xmax), int(length),
+                                           tab.ctypes.data if tab is not None else None))
+
+    def get_exp_lut(self):
+        """``(xmax, length, canonical)`` of the table this handle emulates."""
+        x, n, c = C.c_double(), C.c_uint32(), C.c_int()
+        self._check(self.L.tcw_get_exp_lut(self._h, C.byref(x), C.byref(n), C.byref(c)))
+        return x.value, n.value, bool(c.value)
+
     @property
     def device_name(self) -> str:
         buf = C.create_string_buffer(256)
@@ -242,6 +288,7 @@ class Handle:
             results.ctypes.data,
         )
         self._last_batch = None
+        self.generation += 1
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)
         self._T, self._last_batch = batch.T, batch  # the atoms stay resident: see batch.map_again
         return results, F
@@ -272,12 +319,15 @@ class Handle:
                 *[CWindowRange(w.type, w.t0, w.t0Band, w.dt0, w.tau, w.tauBand, w.dtau) for w in ws]), C.c_void_p)
         results = np.zeros(batch.T, dtype=RESULT_DTYPE)
         F = np.empty((batch.T, N_t0, N_tau), dtype=np.float32) if flags & WANT_FMN else None
+        self._last_batch = None
+        self.generation += 1
         rc = self.L.tcw_map_batch_windows(
             self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
             batch.T, batch.numDet, cws, flags, F.ctypes.data if F is not None else None,
             results.ctypes.data,
         )
         self._check(rc, allow_degenerate_status=not raise_on_degenerate)
+        self._T, self._last_batch = batch.T, batch
         return results, F
 
     # ---- asynchronous split of map_batch ---------------------------------------------
@@ -288,6 +338,7 @@ class Handle:
         w.check_type()
         cw = c_window(w)
         self._last_batch = None
+        self.generation += 1
         self._check(self.L.tcw_submit(
             self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
             batch.T, batch.numDet, C.byref(cw), flags))
@@ -309,17 +360,20 @@ class Handle:
 
     # ---- resident API ----------------------------------------------------------------
     def upload(self, batch: AtomBatch):
-        self._keep = self._last_batch = batch
+        self._keep = batch
+        self._last_batch = None
+        self.generation += 1
         self._check(
             self.L.tcw_upload_atoms(
                 self._h, batch.atoms.ctypes.data, batch.n_atoms.ctypes.data, batch.stride, batch.TAtom,
                 batch.T, batch.numDet,
             )
         )
-        self._T = batch.T
+        self._T, self._last_batch = batch.T, batch
 
     def map_resident(self, window, flags: int = 0):
         cw = c_window(window)
+        self.generation += 1
         self._check(self.L.tcw_map_resident(self._h, C.byref(cw), flags))
 
     def fetch_results(self, raise_on_degenerate: bool = True) -> np.ndarray:
@@ -369,13 +423,11 @@ class Handle:
 
 
 def pinned_atoms_alloc():
-    """Allocator for :func:`pyfstat_b200.atoms.synth_atoms` placing the batch in pinned memory."""
-    keep = []
+    """Allocator for :func:`pyfstat_b200.atoms.synth_atoms` placing the batch in pinned memory.
+    The returned buffers own their allocation (see :class:`PinnedBuffer`): dropping the allocator
+    does not free memory that an :class:`AtomBatch` still views."""
 
     def alloc(nbytes):
-        buf = PinnedBuffer(nbytes)
-        keep.append(buf)
-        return buf.array
+        return PinnedBuffer(nbytes).array
 
-    alloc.keep = keep
     return alloc

@@ -48,8 +48,10 @@ class AtomBatch:
         n_atoms = np.ascontiguousarray(n_atoms, dtype=np.uint32)
         if n_atoms.shape != atoms.shape[:2]:
             raise ValueError("n_atoms must have shape (T, numDet)")
-        if n_atoms.min(initial=1) < 1 or n_atoms.max(initial=0) > atoms.shape[2]:
-            raise ValueError("each detector vector needs 1 <= n_atoms <= stride")
+        if n_atoms.max(initial=0) > atoms.shape[2]:
+            raise ValueError("each detector vector needs 0 <= n_atoms <= stride")
+        if n_atoms.size and n_atoms.max(axis=1).min() < 1:
+            raise ValueError("every template needs at least one atom in some detector")
         if int(TAtom) <= 0:
             raise ValueError("TAtom must be a positive integer")
         self.atoms = atoms
@@ -89,7 +91,7 @@ def batch_from_detector_lists(templates, TAtom: int) -> AtomBatch:
     """Build an :class:`AtomBatch` from ``templates[t][X]`` = 1-D ATOM_DTYPE arrays."""
     T = len(templates)
     numDet = len(templates[0])
-    stride = max(len(a) for tpl in templates for a in tpl)
+    stride = max(1, max(len(a) for tpl in templates for a in tpl))
     atoms = np.zeros((T, numDet, stride), dtype=ATOM_DTYPE)
     n_atoms = np.zeros((T, numDet), dtype=np.uint32)
     for t, tpl in enumerate(templates):

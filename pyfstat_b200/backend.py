@@ -29,7 +29,7 @@ import threading
 
 import numpy as np
 
-from . import _lib
+from . import _lib, lut_probe
 from .atoms import AtomBatch, from_multi_fstat_atoms
 from .window import TRANSIENT_NONE, TransientWindowRange
 
@@ -39,15 +39,47 @@ BACKEND_NAME = "b200"
 
 _handles = {}
 _handles_lock = threading.Lock()
+_probed_lut = None  # (xmax, length, table) measured from lalpulsar, False if unavailable
+
+
+def resolve_device(device: int = -1) -> int:
+    """``-1`` -> ``$CUDA_DEVICE`` (as the reference, tcw:434-437, 466-469), default 0."""
+    if device is None or device < 0:
+        return int(os.environ.get("CUDA_DEVICE", "0"))
+    return int(device)
+
+
+def exp_lut_geometry():
+    """Geometry ``(xmax, length, table | None, source)`` of the XLALFastNegExp table new handles
+    emulate, in this order: ``$PYFSTAT_B200_EXPLUT="xmax:length"``; measured from lalpulsar
+    itself when it is importable (:mod:`pyfstat_b200.lut_probe`); the library default
+    (``_lib.EXPLUT_DEFAULT``)."""
+    global _probed_lut
+    env = os.environ.get("PYFSTAT_B200_EXPLUT")
+    if env:
+        xmax, length = lut_probe.parse_geometry(env)
+        return xmax, length, None, "$PYFSTAT_B200_EXPLUT"
+    if _probed_lut is None:
+        _probed_lut = lut_probe.probe_lalpulsar() or False
+        if _probed_lut:
+            logger.info("XLALFastNegExp table measured from lalpulsar: xmax = %g, %d steps",
+                        _probed_lut[0], _probed_lut[1])
+    if _probed_lut:
+        return _probed_lut[0], _probed_lut[1], _probed_lut[2], "measured from lalpulsar.FastNegExp"
+    return _lib.EXPLUT_DEFAULT[0], _lib.EXPLUT_DEFAULT[1], None, "library default (SURVEY A.4-1)"
 
 
 def get_handle(device: int = -1) -> "_lib.Handle":
-    """Process-global handle per device (calls are serialised on its stream)."""
+    """Process-global handle per device index (calls are serialised on its stream)."""
+    idx = resolve_device(device)
     with _handles_lock:
-        h = _handles.get(device)
+        h = _handles.get(idx)
         if h is None or h._h is None:
-            h = _lib.Handle(device)
-            _handles[device] = h
+            h = _lib.Handle(idx)
+            xmax, length, table, _src = exp_lut_geometry()
+            if table is not None or (xmax, length) != h.get_exp_lut()[:2]:
+                h.set_exp_lut(xmax, length, table)
+            _handles[idx] = h
         return h
 
 
@@ -176,6 +208,10 @@ def fstat_map_class(tcw_module=None):
         (``nan`` unless computed with ``BtSG=True``, tcw:142-144).  ``F_mn`` is only computed,
         copied to the host and cached when it is first read; ``get_maxF_idx()`` and the
         ``get_*`` estimators return the fused GPU results without touching it.
+
+        Nothing is computed twice: whichever of ``F_mn`` / ``get_lnBtSG()`` is asked for first
+        runs ONE pass that produces both (``F_mn`` stays on the device until it is read), on the
+        atoms still resident from the original call when no other map ran in between.
         """
 
         def __init__(self, record, batch, window, flags, handle_device=-1):
@@ -186,6 +222,7 @@ def fstat_map_class(tcw_module=None):
             self._flags = flags & ~(_lib.WANT_FMN | _lib.WANT_BTSG)
             self._device = handle_device
             self._F_mn = None
+            self._fmn_gen = None  # handle generation whose device F_mn is this map's
             self.maxF = float(record["maxF"])
             self.t0_ML = int(record["t0_ML"])
             self.tau_ML = int(record["tau_ML"])
@@ -193,6 +230,30 @@ def fstat_map_class(tcw_module=None):
             self.t0_MP = float(record["t0_MP"])
             self.tau_MP = float(record["tau_MP"])
             self._have_btsg = not np.isnan(self.lnBtSG)
+
+        # ---- one place that talks to the GPU -----------------------------------------
+        def _run(self, window, flags):
+            """Records of ``window`` over this map's atoms: on the atoms still resident on the
+            device when the handle's last batch is ours (no host-to-device copy), else through
+            ``tcw_map_batch``.  ``WANT_FMN`` leaves F_mn on the device (see ``_materialise``)."""
+            h = get_handle(self._device)
+            if getattr(h, "_last_batch", None) is self._batch:
+                h.map_resident(window, flags)
+                res = h.fetch_results(raise_on_degenerate=False)
+            else:
+                h.upload(self._batch)
+                h.map_resident(window, flags)
+                res = h.fetch_results(raise_on_degenerate=False)
+            return h, res
+
+        def _full_pass(self):
+            """F_mn (left on the device) and the lnBtSG record in ONE pass."""
+            h, res = self._run(self._window, self._flags | _lib.WANT_FMN | _lib.WANT_BTSG)
+            self._fmn_gen = h.generation
+            self._rec = res[0]
+            self.lnBtSG = float(res["lnBtSG"][0])
+            self._have_btsg = True
+            return h
 
         # ---- lazy F_mn --------------------------------------------------------------
         @property
@@ -204,10 +265,9 @@ def fstat_map_class(tcw_module=None):
         def _materialise(self):
             if self._F_mn is None:
                 h = get_handle(self._device)
-                _, F = h.map_batch(
-                    self._batch, self._window, self._flags | _lib.WANT_FMN, raise_on_degenerate=False
-                )
-                self._F_mn = F[0]
+                if self._fmn_gen is None or h.generation != self._fmn_gen:
+                    h = self._full_pass()
+                self._F_mn = h.fetch_fmn(0, *self.shape)
             return self._F_mn
 
         @F_mn.setter
@@ -224,8 +284,7 @@ def fstat_map_class(tcw_module=None):
                 return float(self._F_mn[m, n])
             w = self._window
             one = TransientWindowRange(w.type, w.t0 + m * w.dt0, 0, w.dt0, w.tau + n * w.dtau, 0, w.dtau)
-            h = get_handle(self._device)
-            res, _ = h.map_batch(self._batch, one, self._flags | _lib.ALLOW_DEGENERATE)
+            _, res = self._run(one, self._flags | _lib.ALLOW_DEGENERATE)
             return float(res["maxF"][0])
 
         # ---- fused reductions (override the numpy versions, tcw:186-287) ------------
@@ -234,26 +293,21 @@ def fstat_map_class(tcw_module=None):
 
         def _ensure_btsg(self):
             if not self._have_btsg:
-                h = get_handle(self._device)
-                res, _ = h.map_batch(
-                    self._batch, self._window, self._flags | _lib.WANT_BTSG, raise_on_degenerate=False
-                )
-                self._rec = res[0]
-                self.lnBtSG = float(res["lnBtSG"][0])
-                self._t0_MP_gpu = float(res["t0_MP"][0])
-                self._tau_MP_gpu = float(res["tau_MP"][0])
-                self._have_btsg = True
-            else:
-                self._t0_MP_gpu = float(self._rec["t0_MP"])
-                self._tau_MP_gpu = float(self._rec["tau_MP"])
+                self._full_pass()
 
         def get_lnBtSG(self):
             self._ensure_btsg()
             self.lnBtSG = float(self._rec["lnBtSG"])
             return self.lnBtSG
 
+        def _mp_window(self, windowRange):
+            # TRANSIENT_NONE: the reference's pycuda path mutates the caller's range into the rect
+            # window spanning the data (tcw:742-749); ours is never mutated, so substitute here
+            return self._window if int(windowRange.type) == TRANSIENT_NONE else windowRange
+
         def get_t0_max_posterior(self, windowRange):
             self._ensure_btsg()
+            windowRange = self._mp_window(windowRange)
             N_t0 = int(self._rec["N_t0"])
             dx = windowRange.t0Band / N_t0  # consistent with LAL (tcw:248-251)
             self.t0_MP = windowRange.t0 + (int(self._rec["m_MP"]) + 0.5) * dx
@@ -261,24 +315,39 @@ def fstat_map_class(tcw_module=None):
 
         def get_tau_max_posterior(self, windowRange):
             self._ensure_btsg()
+            windowRange = self._mp_window(windowRange)
             N_tau = int(self._rec["N_tau"])
             dy = windowRange.tauBand / N_tau  # tcw:283-286
             self.tau_MP = windowRange.tau + (int(self._rec["n_MP"]) + 0.5) * dy
             return self.tau_MP
 
         if base is object:
-            # PyFstat absent: provide the text writer with the reference's format
-            # (tcw:289-317: columns t0[s] tau[s] 2F, "  %10d %10d %- 11.8g")
+            # PyFstat absent: the text format of tcw:289-317 / 159-184 -- optional "# " header
+            # lines, a column line, then one row "t0 tau 2F" per cell, t0 outer / tau inner
             def write_F_mn_to_file(self, tCWfile, windowRange, header=[]):
-                with open(tCWfile, "w") as tfp:
-                    for hline in header:
-                        tfp.write("# {:s}\n".format(hline))
-                    tfp.write("# t0[s]     tau[s]     2F\n")
-                    for m, F_m in enumerate(self.F_mn):
-                        this_t0 = windowRange.t0 + m * windowRange.dt0
-                        for n, this_F in enumerate(F_m):
-                            this_tau = windowRange.tau + n * windowRange.dtau
-                            tfp.write("  %10d %10d %- 11.8g\n" % (this_t0, this_tau, 2.0 * this_F))
+                F = np.asarray(self.F_mn, dtype=np.float64)
+                windowRange = self._mp_window(windowRange)
+                t0s = windowRange.t0 + windowRange.dt0 * np.arange(F.shape[0], dtype=np.int64)
+                taus = windowRange.tau + windowRange.dtau * np.arange(F.shape[1], dtype=np.int64)
+                table = np.column_stack([np.repeat(t0s, F.shape[1]), np.tile(taus, F.shape[0]), 2.0 * F.ravel()])
+                head = "\n".join([str(line) for line in header] + ["t0[s]     tau[s]     2F"])
+                np.savetxt(tCWfile, table, fmt="  %10d %10d %- 11.8g", header=head, comments="# ")
+
+            @classmethod
+            def read_from_file(cls, tCWfile):
+                """Map object holding the F_mn of a file written by ``write_F_mn_to_file`` (2F is
+                halved back to F; rows and columns from the distinct t0 / tau values)."""
+                cols = np.loadtxt(tCWfile, comments="#", ndmin=2)
+                t0s, taus = np.unique(cols[:, 0]), np.unique(cols[:, 1])
+                self = cls.__new__(cls)
+                self._F_mn = (0.5 * cols[:, 2]).reshape(len(t0s), len(taus))
+                idx = np.unravel_index(np.argmax(self._F_mn), self._F_mn.shape)
+                self.maxF = float(self._F_mn[idx])
+                self.t0_ML, self.tau_ML = float(t0s[idx[0]]), float(taus[idx[1]])
+                self.lnBtSG = self.t0_MP = self.tau_MP = float("nan")
+                self._have_btsg, self._fmn_gen = False, None
+                self._rec = {"N_t0": len(t0s), "N_tau": len(taus), "m_ML": idx[0], "n_ML": idx[1]}
+                return self
 
     B200TransientFstatMap.__qualname__ = "B200TransientFstatMap"
     _class_cache[base] = B200TransientFstatMap
@@ -306,6 +375,7 @@ def b200_compute_transient_fstat_map(multiFstatAtoms, windowRange, BtSG=False, *
         flags = default_flags()
     h = get_handle(device)
     res, _ = h.map_batch(batch, window, flags | (_lib.WANT_BTSG if BtSG else 0))
+    device = h.device_index
     if window.type == TRANSIENT_NONE:  # describe the substituted window for lazy F_mn / MP
         window = TransientWindowRange(
             1, int(res["t0_data"][0]), 0, batch.TAtom, int(res["numAtoms"][0]) * batch.TAtom, 0, batch.TAtom
@@ -315,13 +385,56 @@ def b200_compute_transient_fstat_map(multiFstatAtoms, windowRange, BtSG=False, *
 
 
 def backend_available() -> bool:
-    """True if the CUDA library loads and a device can be opened."""
+    """True if the CUDA library loads and a device can be opened (creates the handle)."""
     try:
         get_handle(-1)
         return True
     except Exception as e:  # noqa: BLE001
         logger.debug("b200 backend unavailable: %s", e)
         return False
+
+
+def backend_present() -> bool:
+    """Cheap, side-effect-free feature probe: the library file exists (no nvcc build is
+    attempted) and the driver reports a CUDA device.  No context, stream or handle is created,
+    so a process that only ever uses ``lal`` / ``pycuda`` pays nothing for this backend."""
+    try:
+        if not os.path.exists(_lib.LIB_PATH):
+            return False
+        return _lib.load_library(build_if_missing=False).tcw_device_count() > 0
+    except Exception as e:  # noqa: BLE001
+        logger.debug("b200 backend not present: %s", e)
+        return False
+
+
+def select_device(cudaDeviceName=None) -> int:
+    """Device choice of ``init_transient_fstat_map_features`` (tcw:419-476): all devices are
+    enumerated; ``cudaDeviceName`` is matched PARTIALLY against their names (spaces and
+    underscores as dashes), first match wins (warning if several) and is written to
+    ``$CUDA_DEVICE``; otherwise ``$CUDA_DEVICE`` or 0.  Raises the reference's RuntimeErrors."""
+    names = [n.replace(" ", "-").replace("_", "-") for n in _lib.device_names()]
+    logger.info("Found %d CUDA device(s).", len(names))
+    for n, name in enumerate(names):
+        logger.info("device %d: model: %s", n, name)
+    devnum = int(os.environ.get("CUDA_DEVICE", "0"))
+    if cudaDeviceName:
+        matches = [i for i, name in enumerate(names) if cudaDeviceName in name]
+        if not matches:
+            raise RuntimeError(
+                'Requested CUDA device "{}" not found. Available devices: [{}]'.format(cudaDeviceName, ",".join(names))
+            )
+        devnum = matches[0]
+        if len(matches) > 1:
+            logger.warning('Found %d CUDA devices matching name "%s". Choosing first one with index %d.',
+                           len(matches), cudaDeviceName, devnum)
+        os.environ["CUDA_DEVICE"] = str(devnum)
+    if devnum >= len(names):
+        raise RuntimeError(
+            "Requested CUDA device number {} exceeds number of available devices!"
+            " Please change through environment variable $CUDA_DEVICE.".format(devnum)
+        )
+    logger.info("Choosing CUDA device %d, of %d devices present: %s", devnum, len(names), names[devnum])
+    return devnum
 
 
 def register(tcw_module=None, name: str = BACKEND_NAME):
@@ -355,24 +468,21 @@ def register(tcw_module=None, name: str = BACKEND_NAME):
 
     def _get_transient_fstat_map_features():
         features = orig_features()
-        features[name] = backend_available()
+        features[name] = backend_present()  # import-probing only, like the stock entries (tcw:351-358)
         return features
 
     def init_transient_fstat_map_features(feature="lal", cudaDeviceName=None):
         if feature != name:
+            # other backends: report ours lazily -- no handle, no context, no build
             features, ctx = orig_init(feature, cudaDeviceName)
-            features[name] = backend_available()
+            features[name] = backend_present()
             return features, ctx
         features = _get_transient_fstat_map_features()
         if not features[name]:
             raise RuntimeError(f"{name} use was requested, but no CUDA device / library is usable.")
-        h = get_handle(-1)
-        devname = h.device_name.replace(" ", "-").replace("_", "-")
-        if cudaDeviceName and cudaDeviceName not in devname:  # partial match as tcw:440-454
-            raise RuntimeError(
-                'Requested CUDA device "{}" not found. Available devices: [{}]'.format(cudaDeviceName, devname)
-            )
-        logger.info("Transient F-stat maps on CUDA device %s (backend %r).", devname, name)
+        devnum = select_device(cudaDeviceName)
+        h = get_handle(devnum)  # opens the device (raises if it is not an sm_100 part)
+        logger.info("Transient F-stat maps on CUDA device %d: %s (backend %r).", devnum, h.device_name, name)
         # the handle is process-global and closed at exit; a context object is only handed
         # out when the caller will detach() it ("cuda" in the name, core.py:493-505)
         return features, (_DetachableContext() if "cuda" in name else None)

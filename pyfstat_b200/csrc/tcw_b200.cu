@@ -54,6 +54,13 @@ struct tcw_handle {
     cudaDeviceProp prop;
     uint64_t launches = 0;
 
+    // pinned staging of the small per-call arrays (n_atoms, meta, per-template windows): the caller's
+    // pageable buffers are consumed before the call returns, with no stream synchronisation
+    void *hp_small[2] = {nullptr, nullptr};  // [0] n_atoms + meta, [1] per-template windows
+    size_t hp_small_cap[2] = {0, 0};
+    cudaEvent_t ev_small[2] = {nullptr, nullptr};
+    bool small_pending[2] = {false, false};
+
     bool in_flight = false, in_flight_fmn = false;  // tcw_submit .. tcw_wait
     // resident batch
     bool uploaded = false;
@@ -73,6 +80,10 @@ struct tcw_handle {
     bool w_valid = false;
     tcw_window_range w_key = {};
     uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_i00 = 0, w_TN = 0;
+    // XLALFastNegExp table geometry (runtime: tcw_set_exp_lut)
+    double lut_xmax = 0.0;
+    uint32_t lut_len = 0;
+    bool lut_canonical = false;
     int exp_variant = 1;  // ExpCfgB: measured fastest (r01: A 14.70 ms, B 13.77 ms, C 13.80 ms per 32 x 30-d templates)
     int w_exact = -1;
     std::vector<int32_t> w_Kn;
@@ -117,10 +128,98 @@ static int ensure(tcw_handle *h, DevBuf &b, size_t bytes) {
     return TCW_OK;
 }
 
+// Pinned staging area of `bytes` bytes, free to be overwritten (the previous asynchronous copies out
+// of it have completed).
+static int small_stage(tcw_handle *h, int slot, size_t bytes, unsigned char **out) {
+    if (h->small_pending[slot]) {
+        CUDA_TRY(h, cudaEventSynchronize(h->ev_small[slot]));
+        h->small_pending[slot] = false;
+    }
+    if (bytes > h->hp_small_cap[slot]) {
+        if (h->hp_small[slot]) cudaFreeHost(h->hp_small[slot]);
+        h->hp_small[slot] = nullptr;
+        h->hp_small_cap[slot] = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 4, 4096);
+        if (cudaHostAlloc(&h->hp_small[slot], want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, TCW_E_NOMEM, "cudaHostAlloc of the staging area failed");
+        }
+        h->hp_small_cap[slot] = want;
+    }
+    *out = (unsigned char *)h->hp_small[slot];
+    return TCW_OK;
+}
+
 static void release(DevBuf &b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
     b.cap = 0;
+}
+
+static ExpLut lut_dev(const tcw_handle *h) {
+    ExpLut l;
+    l.tab = (const double *)h->d_lut.p;
+    l.len = h->lut_len;
+    l.xmax = h->lut_xmax;
+    l.dxinv = (double)h->lut_len / h->lut_xmax;  // EXPLUT_DXINV = LENGTH / XMAX
+    const double k = -(h->lut_xmax / (double)h->lut_len) * 1.4426950408889634074;  // -dx log2(e)
+    // k_hi keeps 11 significant bits (10 stored) so that i0 * k_hi is exact in FP32 for i0 < 2^13
+    float hi = (float)k;
+    uint32_t bits;
+    memcpy(&bits, &hi, 4);
+    bits &= 0xFFFFE000u;
+    memcpy(&hi, &bits, 4);
+    l.neg_dx_log2e_hi = hi;
+    l.neg_dx_log2e_lo = (float)(k - (double)hi);
+    l.canonical = h->lut_canonical ? 1u : 0u;
+    return l;
+}
+
+// Installs the XLALFastNegExp table: `length + 1` entries on [0, xmax], lookup index
+// (UINT4)(x * length / xmax + 0.5).  table == NULL: built here as exp(-(i * dx)), dx = xmax / length,
+// with the host's libm -- the way lalpulsar's XLALCreateExpLUT fills it.
+static int set_exp_lut(tcw_handle *h, double xmax, uint32_t length, const double *table) {
+    if (!(xmax > 0.0) || !(xmax < 1e6) || length < 1 || length > (1u << 22))
+        return fail(h, TCW_E_INVALID, "tcw_set_exp_lut: need 0 < xmax < 1e6 and 1 <= length <= 2^22");
+    std::vector<double> lut((size_t)length + 1);
+    const double dx = xmax / (double)length;
+    bool canonical = true;
+    for (uint32_t i = 0; i <= length; i++) {
+        const double ref = exp(-((double)i * dx));
+        lut[i] = table ? table[i] : ref;
+        if (table && !(fabs(table[i] - ref) <= 1e-13 * ref)) canonical = false;
+    }
+    int rc = ensure(h, h->d_lut, lut.size() * sizeof(double));
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy(h->d_lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->lut_xmax = xmax;
+    h->lut_len = length;
+    h->lut_canonical = canonical;
+    h->w_valid = false;  // cached exponential-window weights were built from the old table
+    const size_t smem = TCW_BTSG_TABLE_SMEM(length);
+    if (smem <= (size_t)h->prop.sharedMemPerBlockOptin) {
+        CUDA_TRY(h, cudaFuncSetAttribute(tcw_btsg_table_kernel<false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(tcw_btsg_table_kernel<false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    return TCW_OK;
+}
+
+extern "C" int tcw_set_exp_lut(tcw_handle *h, double xmax, uint32_t length, const double *table) {
+    if (!h) return TCW_E_INVALID;
+    if (h->in_flight) return fail(h, TCW_E_STATE, "a submitted batch is in flight: call tcw_wait first");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return set_exp_lut(h, xmax, length, table);
+}
+
+extern "C" int tcw_get_exp_lut(const tcw_handle *h, double *xmax, uint32_t *length, int *canonical) {
+    if (!h) return TCW_E_INVALID;
+    if (xmax) *xmax = h->lut_xmax;
+    if (length) *length = h->lut_len;
+    if (canonical) *canonical = h->lut_canonical ? 1 : 0;
+    return TCW_OK;
 }
 
 extern "C" int tcw_abi_version(void) { return TCW_ABI_VERSION; }
@@ -157,6 +256,26 @@ extern "C" int tcw_cell_index_range(uint32_t window_type, uint32_t t0_m, uint32_
     return TCW_OK;
 }
 
+extern "C" int tcw_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+extern "C" int tcw_device_name_of(int device, char *buf, int buflen) {
+    if (!buf || buflen < 1) return TCW_E_INVALID;
+    cudaDeviceProp prop;
+    if (device < 0 || device >= tcw_device_count() || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        return TCW_E_CUDA;
+    }
+    snprintf(buf, buflen, "%s", prop.name);
+    return TCW_OK;
+}
+
 extern "C" int tcw_create(int device, tcw_handle **out) {
     if (!out) return fail(nullptr, TCW_E_INVALID, "tcw_create: out is NULL");
     *out = nullptr;
@@ -189,19 +308,28 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (auto &ev : h->ev_timer) CUDA_TRY(nullptr, cudaEventCreate(&ev));
     for (auto &ev : h->ev_stage) CUDA_TRY(nullptr, cudaEventCreate(&ev));
+    for (auto &ev : h->ev_small) CUDA_TRY(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(nullptr, cudaEventCreate(&h->ev_fin));
-    // XLALFastNegExp table, computed on the host exactly like lalpulsar builds it
-    // (recalled: exp(-i*dx), dx = 20/2000), so the device lookups are bit-identical
-    std::vector<double> lut(TCW_LUT_LEN + 1);
-    const double dx = TCW_LUT_XMAX / TCW_LUT_LEN;
-    for (int i = 0; i <= TCW_LUT_LEN; i++) lut[i] = exp(-(i * dx));
-    int rc = ensure(h, h->d_lut, lut.size() * sizeof(double));
-    if (rc) {
-        g_create_error = h->err;
-        delete h;
-        return rc;
+    // XLALFastNegExp table.  Default geometry: SURVEY A.4-1 (xmax 20, 1/dx = 256 -> 5120 steps);
+    // $TCW_EXP_LUT="xmax:length" or tcw_set_exp_lut() override it (round 1 compiled in 20:2000).
+    {
+        double xmax = TCW_EXPLUT_DEFAULT_XMAX;
+        uint32_t length = TCW_EXPLUT_DEFAULT_LENGTH;
+        if (const char *env = getenv("TCW_EXP_LUT")) {
+            double x = 0;
+            unsigned long n = 0;
+            if (sscanf(env, "%lf:%lu", &x, &n) == 2) {
+                xmax = x;
+                length = (uint32_t)n;
+            }
+        }
+        int rc = set_exp_lut(h, xmax, length, nullptr);
+        if (rc) {
+            g_create_error = h->err;
+            delete h;
+            return rc;
+        }
     }
-    CUDA_TRY(nullptr, cudaMemcpy(h->d_lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
     // opt in to large dynamic shared memory once
 #define RECT_ATTR(RR, STG)                                                                              \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_kernel<RR, STG>,                                 \
@@ -220,14 +348,6 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ExpCfgC::kSmem));
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_BTSG_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_BTSG_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_BTSG_SMEM));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_btsg_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           TCW_BTSG_SMEM));
     *out = h;
     return TCW_OK;
 }
@@ -245,6 +365,10 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     for (auto ev : h->ev_stage)
         if (ev) cudaEventDestroy(ev);
     if (h->ev_fin) cudaEventDestroy(h->ev_fin);
+    for (auto ev : h->ev_small)
+        if (ev) cudaEventDestroy(ev);
+    for (auto p : h->hp_small)
+        if (p) cudaFreeHost(p);
     for (auto ev : h->ev_sub) cudaEventDestroy(ev);
     for (auto ev : h->ev_up) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -322,14 +446,18 @@ static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n
     bool uniform = true;
     for (int t = 0; t < T; t++) {
         uint32_t tMin = 0xFFFFFFFFu, tMax = 0;
+        bool any = false;
         for (int X = 0; X < numDet; X++) {
             const uint32_t n = n_atoms[(size_t)t * numDet + X];
-            if (n < 1 || n > atom_stride)
-                return fail(h, TCW_E_INVALID, "tcw_upload_atoms: n_atoms out of range [1, atom_stride]");
+            if (n > atom_stride)
+                return fail(h, TCW_E_INVALID, "tcw_upload_atoms: n_atoms out of range [0, atom_stride]");
+            if (n == 0) continue;  // a detector without atoms contributes nothing to the merge
+            any = true;
             const tcw_atom *a = atoms + ((size_t)t * numDet + X) * atom_stride;
             tMin = std::min(tMin, a[0].timestamp);
             tMax = std::max(tMax, a[n - 1].timestamp);
         }
+        if (!any) return fail(h, TCW_E_INVALID, "tcw_upload_atoms: a template has no atoms in any detector");
         if (tMax < tMin) return fail(h, TCW_E_INVALID, "tcw_upload_atoms: timestamps not increasing");
         h->meta[t].t0_data = tMin;
         h->meta[t].numAtoms = (tMax - tMin) / TAtom + 1;
@@ -356,13 +484,19 @@ static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n
     if (copy_atoms)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_atoms.p, atoms, n_vec * atom_stride * sizeof(tcw_atom),
                                     cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_natoms.p, n_atoms, n_vec * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_meta.p, h->meta.data(), (size_t)T * sizeof(TplMeta),
-                                cudaMemcpyHostToDevice, h->stream));
-    // n_atoms / meta are small pageable buffers owned by the caller / by us: make sure the
-    // copies have consumed them before returning
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // n_atoms (caller's, pageable) and meta go through the pinned staging area: consumed here, copied
+    // asynchronously, no stream synchronisation on the latency path
+    const size_t nb_n = n_vec * sizeof(uint32_t), nb_m = (size_t)T * sizeof(TplMeta);
+    unsigned char *stg = nullptr;
+    if ((rc = small_stage(h, 0, nb_n + nb_m, &stg))) return rc;
+    memcpy(stg, n_atoms, nb_n);
+    memcpy(stg + nb_n, h->meta.data(), nb_m);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_natoms.p, stg, nb_n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_meta.p, stg + nb_n, nb_m, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_small[0], h->stream));
+    h->small_pending[0] = true;
+    // tcw_upload_atoms copies the caller's (possibly pageable) atoms here: consumed before returning
+    if (copy_atoms) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->uploaded = true;
     return TCW_OK;
 }
@@ -532,8 +666,8 @@ static size_t subbatch_bytes() {
 // host_atoms == nullptr: the atoms are resident.  Otherwise they are still on the host (pinned
 // for real overlap): the batch is cut into chunks whose H2D copies run on a second stream while
 // the previous chunk is being computed.
-static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms,
-                    const tcw_window_range *per_template = nullptr) {
+static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms,
+                          const tcw_window_range *per_template) {
     if (!h) return TCW_E_INVALID;
     if (!win) return fail(h, TCW_E_INVALID, "tcw_map_resident: window range is NULL");
     if (!h->uploaded) return fail(h, TCW_E_STATE, "tcw_map_resident: no resident atoms (call tcw_upload_atoms)");
@@ -589,7 +723,11 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     const MapWindow *d_wins = nullptr;
     if (per_template) {
         if (none_window) return fail(h, TCW_E_INVALID, "per-template windows cannot be TRANSIENT_NONE");
-        std::vector<MapWindow> wins(T);
+        int rcw = ensure(h, h->d_wins, (size_t)T * sizeof(MapWindow));
+        if (rcw) return rcw;
+        unsigned char *stg = nullptr;
+        if ((rcw = small_stage(h, 1, (size_t)T * sizeof(MapWindow), &stg))) return rcw;
+        MapWindow *wins = reinterpret_cast<MapWindow *>(stg);
         for (int t = 0; t < T; t++) {
             const tcw_window_range &pw = per_template[t];
             if (pw.type != win->type || pw.dt0 == 0 || pw.dtau == 0 || pw.t0Band / pw.dt0 + 1 != w.N_t0 ||
@@ -604,9 +742,11 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             wins[t].t0Band = pw.t0Band;
             wins[t].tauBand = pw.tauBand;
         }
-        int rcw = ensure(h, h->d_wins, (size_t)T * sizeof(MapWindow));
-        if (rcw) return rcw;
-        CUDA_TRY(h, cudaMemcpy(h->d_wins.p, wins.data(), (size_t)T * sizeof(MapWindow), cudaMemcpyHostToDevice));
+        // pinned staging + asynchronous copy: no synchronous pageable cudaMemcpy on the MCMC step path
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_wins.p, wins, (size_t)T * sizeof(MapWindow), cudaMemcpyHostToDevice,
+                                    h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev_small[1], h->stream));
+        h->small_pending[1] = true;
         d_wins = (const MapWindow *)h->d_wins.p;
     }
 
@@ -626,7 +766,9 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             if (ok) path = PATH_FAST;
         } else {
             ep = plan_exp(h, w);
-            if (ep.ok) path = PATH_FAST;
+            uint32_t TM, TN;
+            exp_tile_dims(h->exp_variant, &TM, &TN);
+            if (ep.ok && (w.N_t0 + TM - 1) / TM <= 65535u) path = PATH_FAST;  // grid.y limit -> generic kernels
         }
     }
 
@@ -667,6 +809,34 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         fmn_scratch = (float *)h->d_scratch.p;
     }
     const int n_sub = (T + S - 1) / S;
+    // rect tile plan + its group-max table: decided and allocated before anything is enqueued; a map
+    // whose row tiles exceed the grid limit takes the generic kernels instead of failing
+    uint32_t *groupmax = nullptr;
+    if (path == PATH_FAST && w.type == TCW_WINDOW_RECT) {
+        rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
+        const uint32_t rows_per_tile = TCW_RECT_WARPS * rp.G * (uint32_t)rect_R;
+        const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
+        if (n_gy > 65535u) {
+            path = PATH_GENERIC;
+        } else if (!want_btsg) {
+            // The map kernel tracks max VALUES only.  The argmax is completed by the lnBtSG pass
+            // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
+            // template re-evaluates only the row groups whose maximum equals the template maximum.
+            const size_t n_entries = (size_t)S * n_gy * (1 + rp.n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX;
+            if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
+            groupmax = (uint32_t *)h->d_tilemax.p;
+        }
+    }
+    const bool need_P2 = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
+    const ExpLut lut = lut_dev(h);
+    // fixed-point scale of the lnBtSG marginals: every term is <= 1, so a map's total is <= cells
+    int fx_bits = 62;
+    for (uint64_t c = cells64; c > 1; c >>= 1) fx_bits--;
+    fx_bits -= 1;
+    const double fx_scale = ldexp(1.0, fx_bits);
+    const bool btsg_table = !exact && ((flags & TCW_BTSG_TABLE) || !h->lut_canonical);
+    if (want_btsg && btsg_table && TCW_BTSG_TABLE_SMEM(h->lut_len) > (size_t)h->prop.sharedMemPerBlockOptin)
+        return fail(h, TCW_E_INVALID, "the installed exp table does not fit shared memory for the table-fetching lnBtSG pass");
     while ((int)h->ev_sub.size() < 3 * n_sub) {
         cudaEvent_t ev;
         CUDA_TRY(h, cudaEventCreate(&ev));
@@ -709,7 +879,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             eg.delta = ep.delta;
             const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->prop.multiProcessorCount * 16);
             tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg,
-                                                         (const double *)h->d_lut.p, (int)exact);
+                                                         lut, (int)exact);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
@@ -750,7 +920,7 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         tcw_prep_kernel<<<cnt, TCW_PREP_THREADS, 0, st>>>(
             (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p, t_base,
             h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, need_X8 ? (float *)h->d_X8.p : nullptr, h->xpad,
-            need_P ? (double *)h->d_P.p : nullptr, h->ppad, (uint32_t *)h->d_flags.p);
+            need_P2 ? (double *)h->d_P.p : nullptr, h->ppad, (uint32_t *)h->d_flags.p);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
         if (sb == 0) CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
@@ -767,12 +937,12 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         if (warp_per_cell)                                                                                  \
             tcw_map_generic_warp_kernel<WT, EX><<<grid, TCW_GENERIC_WARP_THREADS, 0, st>>>(                 \
                 (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
-                (int)none_window, g, (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p,  \
+                (int)none_window, g, lut, fmn, (unsigned long long *)h->d_maxkey.p,  \
                 (uint32_t *)h->d_flags.p);                                                                  \
         else                                                                                                \
             tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                           \
                 (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
-                (int)none_window, g, (const double *)h->d_lut.p, fmn, (unsigned long long *)h->d_maxkey.p,  \
+                (int)none_window, g, lut, fmn, (unsigned long long *)h->d_maxkey.p,  \
                 (uint32_t *)h->d_flags.p);                                                                  \
     } while (0)
             if (w.type == TCW_WINDOW_RECT) LAUNCH_GENERIC(TCW_WINDOW_RECT, false);
@@ -780,23 +950,12 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
             else LAUNCH_GENERIC(TCW_WINDOW_EXP, false);
 #undef LAUNCH_GENERIC
         } else if (w.type == TCW_WINDOW_RECT) {
-            if (sb == 0) rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
             const uint32_t rect_G = rp.G, DD = rp.DD, DT = rp.DT, n_reg = rp.n_reg;
             const bool rect_staged = rp.staged;
             const uint32_t rows_per_tile = TCW_RECT_WARPS * rect_G * rect_R;
             const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
             dim3 grid(1 + n_reg, n_gy, cnt);
-            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
             const size_t smem = TCW_RECT_SMEM;
-            // The map kernel tracks max VALUES only.  The argmax is completed by the lnBtSG pass
-            // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
-            // template re-evaluates only the row groups whose maximum equals the template maximum.
-            uint32_t *groupmax = nullptr;
-            if (!want_btsg) {
-                const size_t n_entries = (size_t)S * n_gy * (1 + n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX;
-                if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
-                groupmax = (uint32_t *)h->d_tilemax.p;
-            }
 #define LAUNCH_RECT(RR, STG)                                                                               \
     do {                                                                                                   \
         tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                                \
@@ -818,7 +977,6 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
 #undef LAUNCH_RECT
         } else {
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, (w.N_t0 + exp_TM - 1) / exp_TM, cnt);
-            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the tiled kernel");
 #define LAUNCH_EXP(CFG)                                                                                   \
     tcw_exp_map_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                                     \
         (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,    \
@@ -833,19 +991,23 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
         CUDA_TRY(h, cudaGetLastError());
         CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 1], st));
         if (want_btsg) {
-            dim3 grid((w.N_tau + TCW_BTSG_COLS - 1) / TCW_BTSG_COLS, (w.N_t0 + TCW_BTSG_ROWS - 1) / TCW_BTSG_ROWS,
-                      cnt);
-            if (grid.y > 65535) return fail(h, TCW_E_INVALID, "map has too many t0 rows for the lnBtSG pass");
+            // tiles linearised in grid.x (col tile fastest): no 65535 limit on either map dimension
+            const uint32_t n_ct = (w.N_tau + TCW_BTSG_COLS - 1) / TCW_BTSG_COLS;
+            const uint32_t n_rt = (w.N_t0 + TCW_BTSG_ROWS - 1) / TCW_BTSG_ROWS;
+            dim3 grid(n_ct * n_rt, 1, cnt);
             const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
-#define LAUNCH_BTSG(EX, LOC)                                                                          \
-    tcw_btsg_kernel<EX, LOC><<<grid, TCW_BTSG_THREADS, TCW_BTSG_SMEM, st>>>(                          \
-        fmn, t_base, w.N_t0, w.N_tau, w.pitch, (unsigned long long *)h->d_maxkey.p,                    \
-        (const double *)h->d_lut.p,                                                                  \
-        (double *)h->d_rowsum.p, (double *)h->d_colsum.p)
-            if (exact && locate) LAUNCH_BTSG(true, true);
-            else if (exact) LAUNCH_BTSG(true, false);
-            else if (locate) LAUNCH_BTSG(false, true);
-            else LAUNCH_BTSG(false, false);
+#define LAUNCH_BTSG(KERNEL, EX, LOC, SMEM)                                                            \
+    KERNEL<EX, LOC><<<grid, TCW_BTSG_THREADS, SMEM, st>>>(                                            \
+        fmn, t_base, w.N_t0, w.N_tau, w.pitch, n_ct, (unsigned long long *)h->d_maxkey.p, lut, fx_scale, \
+        (unsigned long long *)h->d_rowsum.p, (unsigned long long *)h->d_colsum.p)
+            if (btsg_table) {
+                const size_t smem = TCW_BTSG_TABLE_SMEM(h->lut_len);
+                if (locate) LAUNCH_BTSG(tcw_btsg_table_kernel, false, true, smem);
+                else LAUNCH_BTSG(tcw_btsg_table_kernel, false, false, smem);
+            } else if (exact && locate) LAUNCH_BTSG(tcw_btsg_kernel, true, true, 0);
+            else if (exact) LAUNCH_BTSG(tcw_btsg_kernel, true, false, 0);
+            else if (locate) LAUNCH_BTSG(tcw_btsg_kernel, false, true, 0);
+            else LAUNCH_BTSG(tcw_btsg_kernel, false, false, 0);
 #undef LAUNCH_BTSG
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
@@ -856,8 +1018,9 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
 
     // ---- stage 4: one result record per template ----
     tcw_finalize_kernel<<<T, TCW_FIN_THREADS, 0, st>>>(
-        (const unsigned long long *)h->d_maxkey.p, (const uint32_t *)h->d_flags.p, (const double *)h->d_rowsum.p,
-        (const double *)h->d_colsum.p, (const TplMeta *)h->d_meta.p, w, d_wins, (int)none_window, TAtom, (int)want_btsg,
+        (const unsigned long long *)h->d_maxkey.p, (const uint32_t *)h->d_flags.p,
+        (const unsigned long long *)h->d_rowsum.p, (const unsigned long long *)h->d_colsum.p, 1.0 / fx_scale,
+        (const TplMeta *)h->d_meta.p, w, d_wins, (int)none_window, TAtom, (int)want_btsg,
         (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)path, (tcw_result *)h->d_results.p);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -869,6 +1032,24 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
     h->last_N_tau = w.N_tau;
     h->last_pitch = w.pitch;
     return TCW_OK;
+}
+
+// Error exits of map_impl_inner may leave copies / kernels enqueued: drain both streams so that the
+// caller may free or reuse its host atoms, and drop the partially uploaded / prepared batch.
+static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, const tcw_atom *host_atoms,
+                    const tcw_window_range *per_template = nullptr) {
+    const int rc = map_impl_inner(h, win, flags, host_atoms, per_template);
+    if (rc != TCW_OK && h) {
+        const std::string keep = h->err;
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        cudaGetLastError();
+        if (host_atoms) h->uploaded = false;
+        h->stage_valid = false;
+        h->have_fmn = false;
+        h->err = keep;
+    }
+    return rc;
 }
 
 extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags) {

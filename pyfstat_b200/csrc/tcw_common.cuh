@@ -14,8 +14,19 @@
 #include "tcw_b200.h"
 
 #define TCW_NCH 7          // a2, b2, ab, Fa_re, Fa_im, Fb_re, Fb_im (tcw:711-721)
-#define TCW_LUT_LEN 2000   // XLALFastNegExp table (recalled: EXPLUT_LENGTH)
-#define TCW_LUT_XMAX 20.0  // (recalled: EXPLUT_XMAX)
+
+// XLALFastNegExp emulation: e^{-x} from a table of `len + 1` points on [0, xmax],
+// nearest point `tab[(UINT4)(x * dxinv + 0.5)]` with dxinv = len / xmax, 0 beyond xmax.  The
+// geometry is a RUNTIME property of the handle (tcw_set_exp_lut): lalsuite's constants cannot be
+// read in the build container, so nothing about them is compiled in.
+struct ExpLut {
+    const double *tab;  // device pointer, len + 1 entries
+    double dxinv;       // len / xmax
+    double xmax;
+    uint32_t len;
+    float neg_dx_log2e_hi, neg_dx_log2e_lo;  // -(xmax/len) * log2(e) split in two floats (lnBtSG pass)
+    uint32_t canonical;  // 1 if tab[i] == exp(-i * xmax/len) to 1e-13: values may be recomputed instead of fetched
+};
 
 // ---------------------------------------------------------------------------------------
 // exact uint32 division by a runtime-invariant divisor

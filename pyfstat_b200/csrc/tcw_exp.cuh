@@ -66,7 +66,7 @@ struct ExpTableGeom {
 
 // W[nt][k][TN]: weight of relative atom k for column n = nt*TN + j.
 __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__restrict__ Kn,
-                                     ExpTableGeom eg, const double *__restrict__ lut, int exact) {
+                                     ExpTableGeom eg, const ExpLut lut, int exact) {
     const size_t total = (size_t)eg.n_tiles * eg.KW * eg.TN;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {

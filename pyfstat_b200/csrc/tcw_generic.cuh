@@ -15,19 +15,19 @@
 
 #define TCW_GENERIC_THREADS 256
 
-// XLALFastNegExp (recalled): nearest-point lookup in a table of e^{-x},
-// x in [0,20], 2000 steps; 0 beyond; (libm exp for negative x never happens here: x >= 0).
-__device__ __forceinline__ double fast_neg_exp_lut(double mx, const double *__restrict__ lut) {
-    if (mx > TCW_LUT_XMAX) return 0.0;
-    const uint32_t i0 = __double2uint_rz(__dadd_rn(__dmul_rn(mx, (double)TCW_LUT_LEN / TCW_LUT_XMAX), 0.5));
-    return __ldg(lut + i0);
+// XLALFastNegExp: nearest-point lookup in a table of e^{-x} on [0, xmax];
+// 0 beyond; (libm exp for negative x never happens here: x >= 0).  Table geometry: ExpLut.
+__device__ __forceinline__ double fast_neg_exp_lut(double mx, const ExpLut &lut) {
+    if (mx > lut.xmax) return 0.0;
+    const uint32_t i0 = __double2uint_rz(__dadd_rn(__dmul_rn(mx, lut.dxinv), 0.5));
+    return __ldg(lut.tab + min(i0, lut.len));
 }
 
 template <int WTYPE, bool EXACT_EXP>
 __global__ void __launch_bounds__(TCW_GENERIC_THREADS)
 tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
                        int t_base, MapWindow w, const MapWindow *__restrict__ wins, int none_window,
-                       IndexGeom g, const double *__restrict__ lut,
+                       IndexGeom g, const ExpLut lut,
                        float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
                        uint32_t *__restrict__ flags) {
     __shared__ unsigned long long red[TCW_GENERIC_THREADS / 32];
@@ -99,7 +99,7 @@ template <int WTYPE, bool EXACT_EXP>
 __global__ void __launch_bounds__(TCW_GENERIC_WARP_THREADS)
 tcw_map_generic_warp_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
                             int t_base, MapWindow w, const MapWindow *__restrict__ wins, int none_window,
-                            IndexGeom g, const double *__restrict__ lut,
+                            IndexGeom g, const ExpLut lut,
                             float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
                             uint32_t *__restrict__ flags) {
     const int tz = blockIdx.z;

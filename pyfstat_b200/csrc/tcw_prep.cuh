@@ -34,13 +34,14 @@ tcw_prep_kernel(const tcw_atom *__restrict__ atoms, const uint32_t *__restrict__
     const tcw_atom *At = atoms + (size_t)t * numDet * stride;
     const uint32_t *nt = n_atoms + (size_t)t * numDet;
 
-    // sortedness check (strictly increasing timestamps per detector)
+    // sortedness check (non-decreasing timestamps per detector; atoms sharing a bin are summed in
+    // order, as XLALmergeMultiFstatAtomsBinned accumulates them)
     bool unsorted = false;
     for (int Xd = 0; Xd < numDet; Xd++) {
         const tcw_atom *a = At + (size_t)Xd * stride;
         const uint32_t n = nt[Xd];
         for (uint32_t i = tid; i + 1 < n; i += blockDim.x)
-            unsorted |= !(a[i].timestamp < a[i + 1].timestamp);
+            unsorted |= a[i].timestamp > a[i + 1].timestamp;
     }
     if (unsorted) atomicOr(&flags[t], TCW_FLAG_UNSORTED);
 

@@ -57,6 +57,40 @@ def oracle():
     return O
 
 
+# the two XLALFastNegExp table geometries on file: SURVEY A.4-1 and round 1's
+EXPLUT_GEOMETRIES = [(20.0, 5120), (20.0, 2000)]
+EXPLUT_DEFAULT = EXPLUT_GEOMETRIES[0]
+
+
+@pytest.fixture(params=EXPLUT_GEOMETRIES, ids=lambda g: f"lut{g[1]}")
+def explut(request, oracle):
+    """Runs the test once per table geometry (the CPU oracle is switched; GPU tests switch their
+    handle with ``gpu.set_exp_lut(*explut)``), restoring the default afterwards."""
+    oracle.set_exp_lut(*request.param)
+    yield request.param
+    oracle.set_exp_lut(*EXPLUT_DEFAULT)
+
+
+def _gpu_usable():
+    """False only when the library loads and the driver reports NO CUDA device.  A library that
+    is missing or does not load is not a reason to skip: the gpu tests then fail loudly."""
+    try:
+        from pyfstat_b200 import _lib
+
+        return _lib.load_library().tcw_device_count() > 0
+    except Exception:  # noqa: BLE001
+        return True
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not errored) on a box without a usable CUDA device."""
+    if any(item.get_closest_marker("gpu") for item in items) and not _gpu_usable():
+        skip = pytest.mark.skip(reason="no usable CUDA device (pyfstat_b200 has no CPU fallback)")
+        for item in items:
+            if item.get_closest_marker("gpu"):
+                item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def gpu():
     from pyfstat_b200 import _lib
@@ -64,3 +98,11 @@ def gpu():
     h = _lib.Handle(0)
     yield h
     h.close()
+
+
+@pytest.fixture
+def gpu_lut(gpu, explut):
+    """The session handle switched to the parametrised table geometry (and back)."""
+    gpu.set_exp_lut(*explut)
+    yield gpu
+    gpu.set_exp_lut(*EXPLUT_DEFAULT)

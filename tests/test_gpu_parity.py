@@ -29,6 +29,12 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4      # F_mn relative tolerance of the tiled kernels vs the oracle
 ATOL_LNB = 1e-4  # lnBtSG absolute tolerance
+# lnBtSG of the default (streaming) pass against the oracle's Bstat OF THE SAME MAP: the table index
+# of every term is lalpulsar's (FP64), the looked-up value e^{-i0 dx} is recomputed to ~3e-7
+# relative and partial sums of 8 terms are FP32.  With L.BTSG_TABLE every term is fetched from the
+# table and summed in FP64: ATOL_TABLE.
+ATOL_PASS = 2e-6
+ATOL_TABLE = 1e-10
 
 
 def run_gpu(gpu, batch, w, flags=0, btsg=True, fmn=True):
@@ -97,7 +103,7 @@ def test_generic_kernels_bit_exact_vs_oracle(gpu, oracle, win, dets, n, gap, see
         assert np.array_equal(F[t], o["F_mn"].astype(np.float32)), f"t={t}: F_mn differs"
         assert float(res["maxF"][t]) == o["maxF"]
         assert_records_match(res, t, o, w)
-        assert float(res["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=1e-11)
+        assert float(res["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=ATOL_PASS)
         assert float(res["t0_MP"][t]) == pytest.approx(o["t0_MP"], abs=1e-6)
         assert float(res["tau_MP"][t]) == pytest.approx(o["tau_MP"], abs=1e-6)
         merged = gpu.fetch_merged(t, o["numAtoms"])
@@ -131,7 +137,7 @@ def test_generic_kernels_arbitrary_windows_bit_exact(gpu, oracle, spec):
     o = oracle.compute_map(b.template(0), b.TAtom, w, allow_degenerate=True)
     assert np.array_equal(F[0], o["F_mn"].astype(np.float32))
     assert_records_match(res, 0, o, w)
-    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=1e-11)
+    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_PASS)
     # lal's single-atom abort is reported per template
     o_strict = oracle.compute_map(b.template(0), b.TAtom, w, want_btsg=False)
     assert int(res["status"][0]) == o_strict["status"]
@@ -186,9 +192,9 @@ def test_tiled_kernels_within_tolerance(gpu, oracle, win, dets, n, gap, seed):
         if not near_tie:
             assert_records_match(res, t, o, w, check_mp=False)
         assert float(res["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
-        # the lnBtSG pass itself is exact given the map it sees (LUT emulation is bit-faithful)
+        # the lnBtSG pass itself, given the map it sees (table indices are bit-faithful)
         again = oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=True)
-        assert float(res["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=1e-11)
+        assert float(res["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
         assert (int(res["m_MP"][t]), int(res["n_MP"][t])) == (again["m_MP"], again["n_MP"])
 
 
@@ -386,7 +392,7 @@ def test_full_size_properties(gpu, oracle, win, n, dets):
     assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, n + 1)
     assert float(res["maxF"][0]) == float(F[0].max())
     again = oracle.bstat(F[0].astype(np.float64), float(res["maxF"][0]), w, use_lut=True)
-    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=1e-10)
+    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
     assert (int(res["m_MP"][0]), int(res["n_MP"][0])) == (again["m_MP"], again["n_MP"])
 
     scaled = AtomBatch(b.atoms.copy(), b.n_atoms, b.TAtom)
@@ -529,7 +535,7 @@ def test_full_size_exp_120d_config4_shape(gpu, oracle):
     assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, n + 1)
     assert float(res["maxF"][0]) == float(F[0].max())
     again = oracle.bstat(F[0].astype(np.float64), float(res["maxF"][0]), w, use_lut=True)
-    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=1e-10)
+    assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
     assert (int(res["m_MP"][0]), int(res["n_MP"][0])) == (again["m_MP"], again["n_MP"])
     rng = np.random.default_rng(5)
     cells = [(0, 0), (0, n), (n - 2, 0), (n - 2, n), divmod(flat, n + 1)]
@@ -679,3 +685,181 @@ def test_full_size_oracle_parity_rect_120d(gpu, oracle):
     assert rel.max() <= RTOL
     assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
     assert_records_match(res, 0, o, w)
+
+
+# ---- XLALFastNegExp table geometry: a runtime property, both recollections on file --------------
+
+
+def test_exp_lut_geometry_is_runtime(gpu_lut, oracle, explut):
+    """Exponential window + lnBtSG under BOTH table geometries (20 / 5120; round 1's
+    20 / 2000): generic kernels bit-identical to the oracle switched to the same geometry, tiled
+    kernel within RTOL, table-fetching lnBtSG pass exact given its map, streaming pass within
+    ATOL_PASS of it."""
+    gpu = gpu_lut
+    assert gpu.get_exp_lut() == (explut[0], explut[1], True)
+    b = synth_atoms(2, 300, ("H1", "L1"), seed=201)
+    w = canonical_window("exp", 10**9, 300)
+    res_g, F_g = run_gpu(gpu, b, w, L.FORCE_GENERIC | L.BTSG_TABLE)
+    res_t, F_t = run_gpu(gpu, b, w, L.BTSG_TABLE)
+    res_s, F_s = run_gpu(gpu, b, w, 0)
+    assert np.array_equal(F_t, F_s)
+    for t in range(b.T):
+        o = oracle.compute_map(b.template(t), b.TAtom, w)
+        assert np.array_equal(F_g[t], o["F_mn"].astype(np.float32)), "generic kernels must follow the table geometry"
+        assert float(res_g["lnBtSG"][t]) == pytest.approx(o["lnBtSG"], abs=ATOL_TABLE)
+        assert_records_match(res_g, t, o, w)
+        rel = np.abs(F_t[t] - o["F_mn"]) / np.abs(o["F_mn"])
+        assert rel.max() <= RTOL
+        again = oracle.bstat(F_t[t].astype(np.float64), float(res_t["maxF"][t]), w, use_lut=True)
+        assert float(res_t["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_TABLE)
+        assert float(res_s["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
+        for r in (res_t, res_s):
+            assert (int(r["m_MP"][t]), int(r["n_MP"][t])) == (again["m_MP"], again["n_MP"])
+    # rect window: only the lnBtSG terms see the table
+    wr = canonical_window("rect", 10**9, 300)
+    res_r, F_r = run_gpu(gpu, b, wr, 0)
+    res_rt, _ = run_gpu(gpu, b, wr, L.BTSG_TABLE)
+    for t in range(b.T):
+        again = oracle.bstat(F_r[t].astype(np.float64), float(res_r["maxF"][t]), wr, use_lut=True)
+        assert float(res_rt["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_TABLE)
+        assert float(res_r["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
+
+
+def test_exp_lut_geometries_really_differ(gpu, oracle):
+    """The two geometries move exponential-window F_mn by more than the parity bar (why the
+    constant must not be guessed), and an uploaded non-canonical table is honoured verbatim."""
+    b = synth_atoms(1, 200, ("H1", "L1"), seed=211)
+    w = canonical_window("exp", 10**9, 200)
+    try:
+        gpu.set_exp_lut(20.0, 5120)
+        r1, F1 = run_gpu(gpu, b, w, 0)
+        gpu.set_exp_lut(20.0, 2000)
+        r2, F2 = run_gpu(gpu, b, w, 0)
+        assert (np.abs(F1 - F2) / np.abs(F1)).max() > RTOL
+        # a measured table (as lut_probe uploads it): entries scaled by (1 + 1e-3) -> not canonical ->
+        # the table-fetching pass is used and lnBtSG of a rect map moves by exactly ln(1.001)
+        wr = canonical_window("rect", 10**9, 200)
+        base, _ = run_gpu(gpu, b, wr, L.BTSG_TABLE)
+        tab = np.exp(-(np.arange(2001) * (20.0 / 2000))) * 1.001
+        gpu.set_exp_lut(20.0, 2000, tab)
+        assert gpu.get_exp_lut() == (20.0, 2000, False)
+        moved, _ = run_gpu(gpu, b, wr, 0)
+        assert float(moved["lnBtSG"][0]) == pytest.approx(float(base["lnBtSG"][0]) + math.log(1.001), abs=1e-9)
+        with pytest.raises(ValueError):
+            gpu.set_exp_lut(20.0, 2000, tab[:-1])
+        with pytest.raises(L.TcwError):
+            gpu.set_exp_lut(-1.0, 2000)
+    finally:
+        gpu.set_exp_lut(*L.EXPLUT_DEFAULT)
+    assert gpu.get_exp_lut() == (L.EXPLUT_DEFAULT[0], L.EXPLUT_DEFAULT[1], True)
+
+
+# ---- the whole chain on the GPU: register -> reference dispatcher -> ctypes -> CUDA ------------
+
+
+def test_full_chain_register_dispatch_cuda(oracle, tmp_path):
+    """register(tcw) -> init_transient_fstat_map_features("b200") -> call_compute_transient_fstat_map
+    -> registered callable -> C ABI -> kernels on the real device, then every field the reference's
+    callers read (core.py:1460, 1465, 1527, 1541; grid_based_searches.py:1125-1133).  The module is
+    tests/fake_tcw.py (same registry / dispatcher interface; /root/reference is absent on the GPU box)."""
+    import fake_tcw
+    import pyfstat_b200
+    from pyfstat_b200 import backend
+
+    class Multi:  # lalpulsar.MultiFstatAtomVector duck type (tcw:607-632)
+        def __init__(self, batch):
+            self.length = batch.numDet
+            self.data = [self._vec(a, batch.TAtom) for a in batch.template(0)]
+
+        @staticmethod
+        def _vec(a, TAtom):
+            class V:
+                pass
+
+            v = V()
+            v.length, v.TAtom = len(a), TAtom
+
+            class A:
+                def __init__(s, r):
+                    s.timestamp, s.a2_alpha, s.b2_alpha, s.ab_alpha = int(r[0]), float(r[1]), float(r[2]), float(r[3])
+                    s.Fa_alpha, s.Fb_alpha = complex(r[4], r[5]), complex(r[6], r[7])
+
+            v.data = [A(r) for r in a]
+            return v
+
+    n = 120
+    b = synth_atoms(1, n, ("H1", "L1"), seed=221)
+    pyfstat_b200.register(fake_tcw)
+    try:
+        feats, ctx = fake_tcw.init_transient_fstat_map_features("b200")
+        assert feats["b200"] is True and ctx is None
+        with pytest.raises(RuntimeError):
+            fake_tcw.init_transient_fstat_map_features("b200", cudaDeviceName="no-such-device")
+        name = L.device_names()[0].replace(" ", "-")
+        fake_tcw.init_transient_fstat_map_features("b200", cudaDeviceName=name[-4:])  # partial match (tcw:440-454)
+        h = backend.get_handle(-1)
+        for win in ("rect", "exp"):
+            w = canonical_window(win, 10**9, n)
+            launches0 = h.launch_count
+            fm, timing = fake_tcw.call_compute_transient_fstat_map("b200", feats, Multi(b), w, True)
+            assert h.launch_count > launches0 and timing >= 0
+            o = oracle.compute_map(b.template(0), 1800, w)
+            assert 2 * fm.maxF == pytest.approx(2 * o["maxF"], rel=RTOL)                 # core.py:1460
+            assert fm.lnBtSG == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)                 # core.py:1465
+            idx = fm.get_maxF_idx()                                                     # core.py:1527, grid:1128
+            assert idx == (o["m_ML"], o["n_ML"])
+            assert (fm.t0_ML, fm.tau_ML) == (w.t0 + idx[0] * w.dt0, w.tau + idx[1] * w.dtau)  # grid:1129-1130
+            assert fm.t0_MP == pytest.approx(o["t0_MP"]) and fm.tau_MP == pytest.approx(o["tau_MP"])  # grid:1132-1133
+            launches1 = h.launch_count
+            cell = fm.F_mn[idx]                                                         # core.py:1541
+            assert float(cell) == pytest.approx(fm.maxF, rel=RTOL) and fm._F_mn is None
+            assert fm.get_lnBtSG() == fm.lnBtSG and h.launch_count > launches1
+            launches2 = h.launch_count
+            path = tmp_path / f"{win}.dat"
+            fm.write_F_mn_to_file(str(path), w, header=["chain test"])                  # grid:1125-1127
+            launches3 = h.launch_count
+            F = np.asarray(fm.F_mn)
+            assert h.launch_count == launches3 > launches2, "materialised once, by the writer"
+            rel = np.abs(F - o["F_mn"]) / np.abs(o["F_mn"])
+            assert F.shape == (n - 1, n + 1) and rel.max() <= RTOL
+            back = type(fm).read_from_file(str(path)) if hasattr(type(fm), "read_from_file") else None
+            if back is not None:
+                assert np.allclose(back.F_mn, F, rtol=1e-7) and back.get_maxF_idx() == idx
+                assert (back.t0_ML, back.tau_ML) == (fm.t0_ML, fm.tau_ML)
+            # BtSG=False: nan until asked, then ONE pass serves lnBtSG and F_mn
+            fm2, _ = fake_tcw.call_compute_transient_fstat_map("b200", feats, Multi(b), w, False)
+            assert math.isnan(fm2.lnBtSG) and math.isnan(fm2.t0_MP)
+            k0 = h.launch_count
+            assert fm2.get_lnBtSG() == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+            k1 = h.launch_count
+            assert np.array_equal(np.asarray(fm2.F_mn), F) and h.launch_count == k1 > k0
+        # TRANSIENT_NONE through the chain: full-span F, caller's range untouched
+        wn = TransientWindowRange(0, 1, 2, 3, 4, 5, 6)
+        fm3, _ = fake_tcw.call_compute_transient_fstat_map("b200", feats, Multi(b), wn, False)
+        assert (wn.type, wn.t0, wn.t0Band, wn.dt0, wn.tau, wn.tauBand, wn.dtau) == (0, 1, 2, 3, 4, 5, 6)
+        o3 = oracle.compute_map(b.template(0), 1800, wn)
+        assert fm3.maxF == np.float32(o3["maxF"]) and fm3.F_mn.shape == (1, 1)
+        with pytest.raises(ValueError):
+            fake_tcw.call_compute_transient_fstat_map("b200", feats, Multi(b), TransientWindowRange(3, 0, 0, 1, 0, 0, 1), False)
+    finally:
+        pyfstat_b200.unregister(fake_tcw)
+
+
+def test_empty_detector_and_shared_bins(gpu, oracle):
+    """A detector without atoms is skipped by the merge and atoms sharing a TAtom bin are summed in
+    order, as the oracle's XLALmergeMultiFstatAtomsBinned restatement does."""
+    b = synth_atoms(1, 64, ("H1", "L1"), seed=231)
+    atoms = b.atoms.copy()
+    n_atoms = b.n_atoms.copy()
+    n_atoms[0, 1] = 0  # L1 delivers nothing
+    atoms[0, 0, 10]["timestamp"] = atoms[0, 0, 9]["timestamp"] + 600  # two H1 atoms in one bin
+    bb = AtomBatch(atoms, n_atoms, b.TAtom)
+    w = canonical_window("rect", 10**9, 64)
+    res, F = run_gpu(gpu, bb, w, L.FORCE_GENERIC | L.ALLOW_DEGENERATE)
+    o = oracle.compute_map(bb.template(0), 1800, w, allow_degenerate=True)
+    assert np.array_equal(F[0], o["F_mn"].astype(np.float32))
+    assert np.array_equal(gpu.fetch_merged(0, o["numAtoms"]).T, oracle.merged_to_matrix(o["merged"]))
+    bad = atoms.copy()
+    bad[0, 0, 10]["timestamp"] = bad[0, 0, 8]["timestamp"]  # going backwards: rejected
+    with pytest.raises(L.TcwError):
+        run_gpu(gpu, AtomBatch(bad, n_atoms, b.TAtom), w, L.FORCE_GENERIC)

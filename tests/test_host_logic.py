@@ -254,12 +254,20 @@ class OracleBackedHandle:
 
     device_name = "oracle (test double)"
     _h = 1
+    device_index = 0
 
     def __init__(self, oracle):
         self.O = oracle
         self.calls = []
+        self.uploads = 0
+        self.generation = 0
+        self._last_batch = None
 
-    def map_batch(self, batch, window, flags=0, raise_on_degenerate=True):
+    def get_exp_lut(self):
+        x, n = self.O.get_exp_lut()
+        return x, n, True
+
+    def _compute(self, batch, window, flags, raise_on_degenerate):
         self.calls.append(flags)
         w = TransientWindowRange.from_any(window)
         res = np.zeros(batch.T, dtype=_lib.RESULT_DTYPE)
@@ -274,6 +282,30 @@ class OracleBackedHandle:
                 raise _lib.DegenerateWindowError(_lib.E_DEGENERATE, "degenerate")
             Fs.append(r["F_mn"].astype(np.float32))
         return res, (np.stack(Fs) if flags & _lib.WANT_FMN else None)
+
+    def map_batch(self, batch, window, flags=0, raise_on_degenerate=True):
+        self.generation += 1
+        self.uploads += 1
+        self._last_batch = batch
+        return self._compute(batch, window, flags, raise_on_degenerate)
+
+    # resident API (what the result object uses for everything after the first call)
+    def upload(self, batch):
+        self.generation += 1
+        self.uploads += 1
+        self._last_batch = batch
+
+    def map_resident(self, window, flags=0):
+        self.generation += 1
+        self._resident = self._compute(self._last_batch, window, flags, False)
+
+    def fetch_results(self, raise_on_degenerate=True):
+        return self._resident[0]
+
+    def fetch_fmn(self, t, N_t0, N_tau):
+        F = self._resident[1][t]
+        assert F.shape == (N_t0, N_tau)
+        return F.copy()
 
     def map_batch_windows(self, batch, windows, flags=0, raise_on_degenerate=True):
         if isinstance(windows, np.ndarray):  # (T, 7) uint32 rows of transientWindowRange_t
@@ -290,6 +322,8 @@ def test_plugin_through_real_reference_dispatcher(ref_tcw, oracle, monkeypatch, 
     own pyTransientFstatMap base class, with the device replaced by a test double."""
     fake = OracleBackedHandle(oracle)
     monkeypatch.setattr(backend, "get_handle", lambda device=-1: fake)
+    monkeypatch.setattr(backend, "backend_present", lambda: True)
+    monkeypatch.setattr(backend, "select_device", lambda name=None: 0)
     pyfstat_b200.register(ref_tcw)
     try:
         feats, ctx = ref_tcw.init_transient_fstat_map_features("b200")
@@ -337,7 +371,12 @@ def test_plugin_through_real_reference_dispatcher(ref_tcw, oracle, monkeypatch, 
         # BtSG=False: nan until asked (tcw:142-144), then computed on demand
         fm2, _ = ref_tcw.call_compute_transient_fstat_map("b200", feats, FakeMulti(b), w, BtSG=False)
         assert math.isnan(fm2.lnBtSG) and math.isnan(fm2.t0_MP)
+        n_calls, n_up = len(fake.calls), fake.uploads
         assert fm2.get_lnBtSG() == o["lnBtSG"]
+        # ONE pass serves both lnBtSG and the F_mn read that follows, on the resident atoms
+        assert np.array_equal(np.asarray(fm2.F_mn), F)
+        assert fm2.get_t0_max_posterior(w) == pytest.approx(o["t0_MP"])
+        assert len(fake.calls) == n_calls + 1 and fake.uploads == n_up
         # unknown window type: ValueError like tcw:691-697
         with pytest.raises(ValueError):
             ref_tcw.call_compute_transient_fstat_map(

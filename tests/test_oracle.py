@@ -104,18 +104,38 @@ def test_reference_python_class_live(oracle, ref_tcw):
 # ---- XLALFastNegExp restatement ------------------------------------------------------------
 
 
-def test_fast_neg_exp_table(oracle):
+def test_fast_neg_exp_table(oracle, explut):
+    """Both table geometries on file (20 / 5120; the other recollection: 20 / 2000)."""
+    xmax, length = explut
+    dx = xmax / length
     lut = oracle.exp_lut()
-    assert len(lut) == 2001 and lut[0] == 1.0
-    assert lut[2000] == pytest.approx(math.exp(-20.0), rel=1e-15)
-    assert oracle.fast_neg_exp(20.0001) == 0.0
+    assert oracle.get_exp_lut() == (xmax, length)
+    assert len(lut) == length + 1 and lut[0] == 1.0
+    assert lut[length] == pytest.approx(math.exp(-xmax), rel=1e-14)
+    assert oracle.fast_neg_exp(xmax * 1.000005) == 0.0
     assert oracle.fast_neg_exp(-0.5) == pytest.approx(math.exp(0.5), rel=1e-15)
-    # nearest-point lookup: x in [i*0.01 - 0.005, i*0.01 + 0.005) -> LUT[i]
-    assert oracle.fast_neg_exp(0.0149) == lut[1]
-    assert oracle.fast_neg_exp(0.0151) == lut[2]
-    xs = np.linspace(0, 20, 4001)
+    # nearest-point lookup: x in [i*dx - dx/2, i*dx + dx/2) -> LUT[i]
+    assert oracle.fast_neg_exp(1.49 * dx) == lut[1]
+    assert oracle.fast_neg_exp(1.51 * dx) == lut[2]
+    xs = np.linspace(0, xmax, 4001)
     err = max(abs(oracle.fast_neg_exp(x) - math.exp(-x)) / math.exp(-x) for x in xs)
-    assert err < 0.0051  # half a table step
+    assert 0.2 * dx < err < 0.51 * dx  # half a table step
+
+
+def test_lut_probe_measures_the_geometry(oracle, explut):
+    """pyfstat_b200.lut_probe recovers (xmax, length, entries) from the step function alone --
+    the same routine that measures lalpulsar.FastNegExp wherever lalpulsar is importable."""
+    from pyfstat_b200 import lut_probe
+
+    xmax, length, table = lut_probe.measure_exp_lut(oracle.fast_neg_exp)
+    assert (xmax, length) == explut
+    assert np.array_equal(table, oracle.exp_lut())
+    with pytest.raises(ValueError):
+        lut_probe.measure_exp_lut(lambda x: math.exp(-x))  # smooth: no cut-off / no steps
+    with pytest.raises(ValueError):
+        lut_probe.measure_exp_lut(lambda x: 0.0 if x > 20 else math.exp(-math.floor(x * 10) / 10))  # floor, not nearest
+    assert lut_probe.parse_geometry("20:2000") == (20.0, 2000)
+    assert lut_probe.probe_lalpulsar() is None or len(lut_probe.probe_lalpulsar()) == 3
 
 
 # ---- index ranges: the uint32 arithmetic of Rect.cu:21-31, 54-69 / Exp.cu:27-65 -----------

@@ -31,6 +31,7 @@
 #include "tcw_generic.cuh"
 #include "tcw_prep.cuh"
 #include "tcw_rect.cuh"
+#include "tcw_rect_p.cuh"
 
 static std::string g_create_error;
 
@@ -70,7 +71,8 @@ struct tcw_handle {
     bool uniform = true;  // all templates share (t0_data, numAtoms)
     std::vector<TplMeta> meta;
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
-        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins, d_tilemax;
+        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins, d_tilemax, d_counter;
+    int rect_persist = 1;  // regular rect tiles through the persistent warp-specialised kernel ($TCW_RECT_PERSIST=0: off)
 
     // last map
     bool have_fmn = false;
@@ -348,6 +350,9 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ExpCfgC::kSmem));
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TCW_RECTP_SMEM));
+    if (const char *v = getenv("TCW_RECT_PERSIST")) h->rect_persist = atoi(v);
     *out = h;
     return TCW_OK;
 }
@@ -358,7 +363,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
-                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins, &h->d_tilemax})
+                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins, &h->d_tilemax, &h->d_counter})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -653,6 +658,30 @@ static RectPlan plan_rect(const tcw_handle *h, const MapWindow &w, int S, uint32
     return best;
 }
 
+// The regular tiles (d >= DD) of a rect launch may run in the persistent kernel (tcw_rect_p.cuh) if,
+// with ITS row tiling (112 rows), every such tile is off-diagonal for every template and its
+// end-prefix slice fits the staged capacity.
+static bool rectp_ok(const tcw_handle *h, const MapWindow &w, const RectPlan &rp, uint32_t R, uint32_t TAtom,
+                     const IndexGeom &g) {
+    if (!h->rect_persist || R != 4 || !rp.staged || rp.n_reg < 1 || rp.DT % 32 != 0 || rp.DT > TCW_RECT_DT) return false;
+    const uint32_t rows = TCW_RECTP_ROWS;
+    const uint64_t span = ((uint64_t)(rows - 1) * w.dt0 + (uint64_t)(rp.DT - 1) * w.dtau) / TAtom + 6;
+    if (span > TCW_RECT_ECAP) return false;
+    const uint32_t n_gy = (w.N_t0 + rows - 1) / rows;
+    const int n_check = h->uniform ? 1 : h->T;
+    for (int t = 0; t < n_check; t++) {
+        const TplMeta &mt = h->meta[t];
+        for (uint32_t gy = 0; gy < n_gy; gy++) {
+            const uint32_t m0 = gy * rows;
+            const uint32_t m_last = std::min(m0 + rows, w.N_t0) - 1;
+            const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + rp.DD * w.dtau, mt.t0_data, mt.numAtoms, g);
+            const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, mt.t0_data, mt.numAtoms, g);
+            if (((e_lo + 1) & ~1u) < s_hi + 2) return false;
+        }
+    }
+    return true;
+}
+
 static size_t subbatch_bytes() {
     const char *env = getenv("TCW_SUBBATCH_MB");
     size_t mb = env ? (size_t)atol(env) : 2048;
@@ -812,19 +841,26 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     // rect tile plan + its group-max table: decided and allocated before anything is enqueued; a map
     // whose row tiles exceed the grid limit takes the generic kernels instead of failing
     uint32_t *groupmax = nullptr;
+    bool rect_p = false;
     if (path == PATH_FAST && w.type == TCW_WINDOW_RECT) {
         rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
         const uint32_t rows_per_tile = TCW_RECT_WARPS * rp.G * (uint32_t)rect_R;
         const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
         if (n_gy > 65535u) {
             path = PATH_GENERIC;
-        } else if (!want_btsg) {
-            // The map kernel tracks max VALUES only.  The argmax is completed by the lnBtSG pass
-            // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
-            // template re-evaluates only the row groups whose maximum equals the template maximum.
-            const size_t n_entries = (size_t)S * n_gy * (1 + rp.n_reg) * TCW_RECT_WARPS * TCW_RECT_GMAX;
-            if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
-            groupmax = (uint32_t *)h->d_tilemax.p;
+        } else {
+            rect_p = rectp_ok(h, w, rp, (uint32_t)rect_R, TAtom, g);
+            if (!want_btsg) {
+                // The map kernels track max VALUES only.  The argmax is completed by the lnBtSG pass
+                // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
+                // template re-evaluates only the row groups whose maximum equals the template maximum
+                // (table: one entry per d tile and row group of the map).
+                const size_t n_grp = (w.N_t0 + rect_R - 1) / rect_R;
+                const size_t n_entries = (size_t)S * (1 + rp.n_reg) * n_grp;
+                if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
+                groupmax = (uint32_t *)h->d_tilemax.p;
+            }
+            if (rect_p && (rc = ensure(h, h->d_counter, (size_t)n_sub * sizeof(uint32_t)))) return rc;
         }
     }
     const bool need_P2 = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
@@ -848,6 +884,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_maxkey.p, 0, (size_t)T * sizeof(unsigned long long), st));
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (size_t)T * sizeof(uint32_t), st));
+    if (rect_p) CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, (size_t)n_sub * sizeof(uint32_t), st));
     if (want_btsg) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_rowsum.p, 0, (size_t)T * w.N_t0 * sizeof(double), st));
         CUDA_TRY(h, cudaMemsetAsync(h->d_colsum.p, 0, (size_t)T * w.N_tau * sizeof(double), st));
@@ -954,19 +991,34 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             const bool rect_staged = rp.staged;
             const uint32_t rows_per_tile = TCW_RECT_WARPS * rect_G * rect_R;
             const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
-            dim3 grid(1 + n_reg, n_gy, cnt);
+            // head strip (and, without the persistent kernel, every tile) in the one-tile-per-CTA kernel
+            dim3 grid(rect_p ? 1 : 1 + n_reg, n_gy, cnt);
+            const uint32_t gx_total = 1 + n_reg;
             const size_t smem = TCW_RECT_SMEM;
+            if (rect_p) {
+                // regular tiles: one persistent CTA per SM, producer / consumer warps, tile queue
+                const uint32_t n_gy_p = (w.N_t0 + TCW_RECTP_ROWS - 1) / TCW_RECTP_ROWS;
+                const uint64_t n_tiles64 = (uint64_t)cnt * n_gy_p * n_reg;
+                if (n_tiles64 >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many rect tiles in one launch");
+                const uint32_t n_tiles = (uint32_t)n_tiles64;
+                const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
+                tcw_rect_map_p_kernel<<<ctas, TCW_RECTP_THREADS, TCW_RECTP_SMEM, st>>>(
+                    (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, n_reg, n_gy_p,
+                    n_tiles, (uint32_t *)h->d_counter.p + sb, fmn, (unsigned long long *)h->d_maxkey.p, groupmax);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
 #define LAUNCH_RECT(RR, STG)                                                                               \
     do {                                                                                                   \
         tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                                \
             (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, rect_G, \
-            fmn, (unsigned long long *)h->d_maxkey.p, groupmax, (uint32_t *)h->d_flags.p);                 \
+            gx_total, fmn, (unsigned long long *)h->d_maxkey.p, groupmax, (uint32_t *)h->d_flags.p);       \
         if (groupmax) {                                                                                    \
             h->launches++;                                                                                 \
             CUDA_TRY(h, cudaGetLastError());                                                               \
             tcw_rect_locate_kernel<RR, STG><<<cnt, TCW_RECT_THREADS, smem, st>>>(                          \
                 (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
-                rect_G, grid.x, grid.y, (unsigned long long *)h->d_maxkey.p, groupmax,                     \
+                rect_G, gx_total, grid.y, (unsigned long long *)h->d_maxkey.p, groupmax,                   \
                 (uint32_t *)h->d_flags.p);                                                                 \
         }                                                                                                  \
     } while (0)

@@ -315,12 +315,18 @@ __device__ __forceinline__ FstatConst2 fstat_const2() {
     k.neg_quarter = pack2(-0.25f, -0.25f);
     return k;
 }
+// NOGUARD: the caller holds a tile-wide conditioning certificate; the margin is not computed (3 packed
+// instructions less per cell pair) and M0 = M1 = 1.
+template <bool NOGUARD = false>
 __device__ __forceinline__ void fstat_core2(const FstatConst2 &k, f32x2 Ad, f32x2 Bd, f32x2 Cp, f32x2 Fa_re,
                                             f32x2 Fa_im, f32x2 Fb_re, f32x2 Fb_im, float &F0, float &F1,
                                             float &M0, float &M1) {
-    const f32x2 sumAB = add2(Ad, Bd);
     const f32x2 det = fma2(mul2(Cp, k.neg_quarter), Cp, mul2(Ad, Bd));  // AB - C^2
-    const f32x2 margin = fma2(mul2(sumAB, k.neg_kappa), sumAB, det);    // det - kappa s^2
+    f32x2 margin = det;
+    if (!NOGUARD) {
+        const f32x2 sumAB = add2(Ad, Bd);
+        margin = fma2(mul2(sumAB, k.neg_kappa), sumAB, det);  // det - kappa s^2
+    }
     const f32x2 fa2 = fma2(Fa_re, Fa_re, mul2(Fa_im, Fa_im));
     const f32x2 fb2 = fma2(Fb_re, Fb_re, mul2(Fb_im, Fb_im));
     const f32x2 re = fma2(Fa_re, Fb_re, mul2(Fa_im, Fb_im));
@@ -328,7 +334,8 @@ __device__ __forceinline__ void fstat_core2(const FstatConst2 &k, f32x2 Ad, f32x
     float d0, d1, n0, n1, r0, r1;
     unpack2(det, d0, d1);
     unpack2(num, n0, n1);
-    unpack2(margin, M0, M1);
+    if (NOGUARD) M0 = M1 = 1.0f;
+    else unpack2(margin, M0, M1);
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
     F0 = n0 * r0;

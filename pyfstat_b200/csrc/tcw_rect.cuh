@@ -82,7 +82,7 @@ __device__ __forceinline__ float rect_chan_scale(int c) { return c == 2 ? -2.0f 
 // then F = num / det and the conditioning margin, both UNGUARDED (the caller applies the guard).
 //   DIAG = false: Q comes from the per-tile table of {q, q} pairs;
 //   DIAG = true : Q is built here from the staged FP64 slice and the group's P[rho].
-template <int R, bool DIAG>
+template <int R, bool DIAG, bool NOGUARD = false>
 __device__ __forceinline__ void rect_eval(const f32x2 *__restrict__ sQ2, const double *__restrict__ sP,
                                           const double *__restrict__ sGg, uint32_t idx,
                                           const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH], const FstatConst2 &kc,
@@ -105,7 +105,7 @@ __device__ __forceinline__ void rect_eval(const f32x2 *__restrict__ sQ2, const d
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) S[c] = add2(Q2[c], Rs2[rp][c]);
         float f0, f1, m0, m1;
-        fstat_core2(kc, S[0], S[1], S[2], S[3], S[4], S[5], S[6], f0, f1, m0, m1);
+        fstat_core2<NOGUARD>(kc, S[0], S[1], S[2], S[3], S[4], S[5], S[6], f0, f1, m0, m1);
         F[2 * rp] = f0;
         mg[2 * rp] = m0;
         if (2 * rp + 1 < R) {
@@ -170,7 +170,9 @@ __device__ __forceinline__ void rect_chunk_careful(
 // All chunks [j_begin, j_end) of one group.
 //   CHECKED = false: every (row, d) is a valid cell; with TRACK = false the chunks run in blocks
 //   of TCW_RECT_JB with the guard folded into one minimum per block (see the header).
-template <int R, bool DIAG, bool CHECKED, bool STORE, bool TRACK>
+//   NOGUARD = true (tile-wide conditioning certificate, see tcw_rect_p.cuh): the unguarded block
+//   path neither computes nor tests the margins.
+template <int R, bool DIAG, bool CHECKED, bool STORE, bool TRACK, bool NOGUARD = false>
 __device__ __forceinline__ void rect_rows(
     const f32x2 *__restrict__ sQ2, const double *__restrict__ sP, const double *__restrict__ sGg,
     const uint32_t *__restrict__ sE, const f32x2 (&Rs2)[(R + 1) / 2][TCW_NCH], float *const (&rowp)[R],
@@ -207,7 +209,7 @@ __device__ __forceinline__ void rect_rows(
 #pragma unroll
             for (int u = 0; u < JBX; u++) {
                 float F[R], mg[R];
-                rect_eval<R, DIAG>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, F, mg);
+                rect_eval<R, DIAG, NOGUARD>(sQ2, sP, sGg, end_index(j + u), Rs2, kc, F, mg);
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     if (STORE) rowp[r][32 * (j + u)] = F[r];
@@ -215,7 +217,7 @@ __device__ __forceinline__ void rect_rows(
 #pragma unroll
                     for (int r = 0; r < R; r += 2) {
                         vmax = fmax3(vmax, F[r], F[r + 1]);
-                        mmin = fmin3_nan(mmin, mg[r], mg[r + 1]);
+                        if (!NOGUARD) mmin = fmin3_nan(mmin, mg[r], mg[r + 1]);
                     }
                 } else {
 #pragma unroll
@@ -225,7 +227,7 @@ __device__ __forceinline__ void rect_rows(
                     }
                 }
             }
-            if (!(mmin > 0.0f)) {  // rare: some cell of the block needs the F = 2 fallback -> redo guarded
+            if (!NOGUARD && !(mmin > 0.0f)) {  // rare: some cell of the block needs the F = 2 fallback -> redo guarded
                 vmax = vmax_in;
 #pragma unroll 1
                 for (int u = 0; u < JBX; u++) {
@@ -443,11 +445,10 @@ __device__ __forceinline__ unsigned long long rect_tile(
         const uint32_t gi = TRACK ? it / TCW_RECT_WARPS : it;
         const uint32_t wsel = TRACK ? it % TCW_RECT_WARPS : warp;  // the warp that owned the group in the map pass
         const uint32_t grow = (gi * TCW_RECT_WARPS + wsel) * R;  // first row of the group, relative to m0
-        uint32_t *gslot = gmax ? gmax + gi * TCW_RECT_WARPS + wsel : nullptr;  // this group's max value
-        if (m0 + grow >= w.N_t0) {
-            if (!TRACK && gslot && lane == 0) *gslot = 0u;
-            continue;
-        }
+        // this group's max value; gmax points at the entry of the tile's first row group in the
+        // table [tz][d tile][row group of the map] (independent of the row tiling of the kernel)
+        uint32_t *gslot = gmax ? gmax + gi * TCW_RECT_WARPS + wsel : nullptr;
+        if (m0 + grow >= w.N_t0) continue;
         if (TRACK && *gslot != top) continue;  // locate pass: only the groups that attain the template max
         float vgrp = -1.0f;  // maxF starts at -1, strict > (tcw:135-139)
         const uint32_t u_off = grow;
@@ -570,17 +571,21 @@ __device__ __forceinline__ void rect_locate(const double *__restrict__ P, uint32
                                             unsigned long long *red, uint32_t *hit) {
     const uint32_t top = (uint32_t)(*(volatile unsigned long long *)&maxkey[t] >> 32);
     if (top == 0u) return;
-    constexpr uint32_t GE = TCW_RECT_WARPS * TCW_RECT_GMAX;  // table entries per tile
+    // table layout: [tz][d tile bx][row group of the map], n_grp = ceil(N_t0 / R) groups
+    const uint32_t n_grp = (w.N_t0 + R - 1) / R;
+    const uint32_t gpt = TCW_RECT_WARPS * G;  // row groups per tile of THIS pass
     const uint32_t n_tiles = gx * gy;
-    uint32_t *gm = groupmax + (size_t)tz * n_tiles * GE;
+    uint32_t *gm = groupmax + (size_t)tz * gx * n_grp;
     for (uint32_t base = 0; base < n_tiles; base += TCW_RECT_HITWORDS * 32) {
         const uint32_t n_here = min(n_tiles - base, (uint32_t)(TCW_RECT_HITWORDS * 32));
         for (uint32_t i = threadIdx.x; i < TCW_RECT_HITWORDS; i += TCW_RECT_THREADS) hit[i] = 0u;
         __syncthreads();
-        for (uint32_t e = threadIdx.x; e < n_here * GE; e += TCW_RECT_THREADS) {
-            const uint32_t tl = e / GE;
-            if ((e % GE) < TCW_RECT_WARPS * G && __ldcg(gm + (size_t)base * GE + e) == top)
-                atomicOr(&hit[tl >> 5], 1u << (tl & 31));
+        // tiles are numbered by * gx + bx; mark those holding a group that attains the template max
+        for (uint32_t e = threadIdx.x; e < gx * n_grp; e += TCW_RECT_THREADS) {
+            const uint32_t bx = e / n_grp, grp = e - bx * n_grp;
+            const uint32_t tile = (grp / gpt) * gx + bx;
+            if (tile >= base && tile < base + n_here && __ldcg(gm + e) == top)
+                atomicOr(&hit[(tile - base) >> 5], 1u << ((tile - base) & 31));
         }
         __syncthreads();
         for (uint32_t wd = 0; wd < (n_here + 31) / 32; wd++) {
@@ -588,10 +593,11 @@ __device__ __forceinline__ void rect_locate(const double *__restrict__ P, uint32
             while (bits) {
                 const uint32_t tile = base + wd * 32 + (uint32_t)(__ffs(bits) - 1);
                 bits &= bits - 1;
+                const uint32_t bx = tile % gx, by = tile / gx;
                 const unsigned long long key =
-                    rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, tile % gx, tile / gx, w, g, DD, DT, G, nullptr,
-                                               flags, gm + (size_t)tile * GE, top, smem, bar, phase & 1u, phase == 0u,
-                                               red);
+                    rect_tile<R, STAGED, true>(P, ppad, meta, t, tz, bx, by, w, g, DD, DT, G, nullptr, flags,
+                                               gm + (size_t)bx * n_grp + (size_t)by * gpt, top, smem, bar, phase & 1u,
+                                               phase == 0u, red);
                 phase++;
                 if (threadIdx.x == 0 && key != 0ull) atomicMax(&maxkey[t], key);
                 __syncthreads();  // red[] and the staged slice are reused by the next tile
@@ -604,7 +610,7 @@ __device__ __forceinline__ void rect_locate(const double *__restrict__ P, uint32
 // grid: x = d tiles, y = row tiles, z = template in sub-batch.  Publishes the max VALUE per
 // template (atomicMax on the packed key, index part 0) and, when the argmax has to be completed
 // by tcw_rect_locate_kernel (groupmax != nullptr: no lnBtSG pass follows), per row group:
-// 8 x GMAX entries per tile.
+// one entry per (d tile, row group of the map).
 // Natural dispatch order (x fastest): the cheap head-strip tiles are interleaved with the regular
 // ones, which keeps the CTAs sharing an SM out of phase (one stages while the other computes).
 // Measured: running all regular tiles first and the head tiles last is 7 % slower; so is running
@@ -613,14 +619,19 @@ template <int R, bool STAGED>
 __global__ void __launch_bounds__(TCW_RECT_THREADS, TCW_RECT_MINB)
 tcw_rect_map_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta *__restrict__ meta,
                     int t_base, MapWindow w, IndexGeom g, uint32_t DD, uint32_t DT, uint32_t G,
-                    float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
+                    uint32_t gx_total, float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
                     uint32_t *__restrict__ groupmax, uint32_t *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char tcw_rect_smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned long long red[TCW_RECT_WARPS];
     const int tz = blockIdx.z, t = t_base + tz;
-    const size_t tile = ((size_t)tz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    uint32_t *gmax = groupmax ? groupmax + tile * (TCW_RECT_WARPS * TCW_RECT_GMAX) : nullptr;
+    // group-max table [tz][d tile][row group of the map]; gx_total = d tiles of the whole map (this
+    // launch may cover only the head strip, gridDim.x == 1, when the regular tiles run in the
+    // persistent kernel of tcw_rect_p.cuh)
+    const uint32_t n_grp = (w.N_t0 + R - 1) / R;
+    uint32_t *gmax = groupmax ? groupmax + ((size_t)tz * gx_total + blockIdx.x) * n_grp +
+                                    (size_t)blockIdx.y * (TCW_RECT_WARPS * G)
+                              : nullptr;
     const unsigned long long key = rect_tile<R, STAGED, false>(P, ppad, meta, t, tz, blockIdx.x, blockIdx.y, w, g, DD,
                                                                DT, G, Fmn, flags, gmax, 0u, tcw_rect_smem, &bar, 0u,
                                                                true, red);

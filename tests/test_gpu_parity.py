@@ -625,7 +625,15 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
             r2 = res if (btsg and fmn) else run_gpu(gpu, b, w, 0, btsg=btsg, fmn=fmn)[0]
             assert (int(r2["m_ML"][0]), int(r2["n_ML"][0])) == divmod(flat, F.shape[2]), (trial, w, btsg, fmn)
             assert float(r2["maxF"][0]) == float(F[0].max())
-        assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB), (trial, w)
+        # lnBtSG: the pass is exact given the map it sees; against the oracle's own map the bar holds
+        # for maps of a useful size.  Through a nearest-point table lnBtSG is a DISCONTINUOUS function
+        # of F_mn: a last-digit difference in one F can move that term by one table step (0.39 % at
+        # dx = 1/256), which averages out over thousands of cells but not over a few dozen -- there the
+        # bound is one table step times the weight of the flipped terms (documented in DESIGN.md L1).
+        again = oracle.bstat(F[0].astype(np.float64), float(res["maxF"][0]), w, use_lut=True)
+        assert float(res["lnBtSG"][0]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS), (trial, w)
+        tol = ATOL_LNB if rel.size >= 2000 else 1.0 / 256
+        assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=tol), (trial, w, rel.size)
     assert n_fast >= 100, "most of the sweep must exercise the tiled kernels"
 
 

@@ -72,7 +72,9 @@ struct tcw_handle {
     std::vector<TplMeta> meta;
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
         d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins, d_tilemax, d_counter;
-    int rect_persist = 1;  // regular rect tiles through the persistent warp-specialised kernel ($TCW_RECT_PERSIST=0: off)
+    // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
+    // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
+    int rect_persist = 1;
 
     // last map
     bool have_fmn = false;
@@ -592,7 +594,7 @@ struct RectPlan {
 };
 
 static RectPlan plan_rect(const tcw_handle *h, const MapWindow &w, int S, uint32_t R, uint32_t TAtom,
-                          const IndexGeom &g) {
+                          const IndexGeom &g, uint32_t force_G = 0) {
     const TplMeta &mt0 = h->meta[0];
     const uint32_t d_total = w.N_tau + R - 1;
     const double slots = (double)h->prop.multiProcessorCount * TCW_RECT_MINB;
@@ -601,7 +603,8 @@ static RectPlan plan_rect(const tcw_handle *h, const MapWindow &w, int S, uint32
     RectPlan best;
     double best_cost = -1.0;
     for (uint32_t G = g_max; G >= 1; G /= 2) {
-        if (env_g && (uint32_t)atoi(env_g) != G) continue;
+        if (env_g && !force_G && (uint32_t)atoi(env_g) != G) continue;
+        if (force_G && G != force_G) continue;
         const uint32_t rows = TCW_RECT_WARPS * G * R;
         const uint32_t n_gy = (w.N_t0 + rows - 1) / rows;
         // widest regular tile whose end indices still fit the staged slice
@@ -658,27 +661,46 @@ static RectPlan plan_rect(const tcw_handle *h, const MapWindow &w, int S, uint32
     return best;
 }
 
-// The regular tiles (d >= DD) of a rect launch may run in the persistent kernel (tcw_rect_p.cuh) if,
-// with ITS row tiling (112 rows), every such tile is off-diagonal for every template and its
-// end-prefix slice fits the staged capacity.
-static bool rectp_ok(const tcw_handle *h, const MapWindow &w, const RectPlan &rp, uint32_t R, uint32_t TAtom,
-                     const IndexGeom &g) {
-    if (!h->rect_persist || R != 4 || !rp.staged || rp.n_reg < 1 || rp.DT % 32 != 0 || rp.DT > TCW_RECT_DT) return false;
+// A rect launch may run in the persistent kernel (tcw_rect_p.cuh) if its 128-row tiling (= the G = 4
+// plan) is staged, every tile at d >= DD is off-diagonal for EVERY template of the batch (the plan
+// checked template 0) and there are enough tiles to fill the GPU a few times over -- small
+// launches (single-template calls) keep the one-tile-per-CTA kernel and its finer tiles.  The
+// regular tiles are re-cut as wide as the staged slice allows.
+static bool plan_rect_p(const tcw_handle *h, const MapWindow &w, int S, uint32_t R, uint32_t TAtom,
+                        const IndexGeom &g, RectPlan *out) {
+    if (!h->rect_persist || R != 4) return false;
+    RectPlan p = plan_rect(h, w, S, R, TAtom, g, TCW_RECT_GMAX);
+    if (!p.staged || p.G != TCW_RECT_GMAX) return false;
     const uint32_t rows = TCW_RECTP_ROWS;
-    const uint64_t span = ((uint64_t)(rows - 1) * w.dt0 + (uint64_t)(rp.DT - 1) * w.dtau) / TAtom + 6;
-    if (span > TCW_RECT_ECAP) return false;
+    const uint32_t d_total = w.N_tau + R - 1;
+    if (p.DD >= d_total) return false;  // no regular tiles at all
+    uint32_t dt_cap = 0;
+    for (uint32_t dt = TCW_RECT_DT; dt >= 64; dt -= 32)
+        if (((uint64_t)(rows - 1) * w.dt0 + (uint64_t)(dt - 1) * w.dtau) / TAtom + 6 <= TCW_RECT_ECAP) {
+            dt_cap = dt;
+            break;
+        }
+    if (!dt_cap || ((uint64_t)(rows - 1) * w.dt0 + (uint64_t)(p.DD - 1) * w.dtau) / TAtom + 6 > TCW_RECT_ECAP) return false;
+    const uint32_t rest = d_total - p.DD;
+    p.n_reg = (rest + dt_cap - 1) / dt_cap;
+    const uint32_t even = (rest + p.n_reg - 1) / p.n_reg;
+    p.DT = (even + 127u) & ~127u;
+    if (p.DT > dt_cap) p.DT = (even + 31u) & ~31u;
     const uint32_t n_gy = (w.N_t0 + rows - 1) / rows;
+    if (h->rect_persist < 2 && (uint64_t)S * n_gy * (1 + p.n_reg) < 3ull * (uint64_t)h->prop.multiProcessorCount)
+        return false;
     const int n_check = h->uniform ? 1 : h->T;
     for (int t = 0; t < n_check; t++) {
         const TplMeta &mt = h->meta[t];
         for (uint32_t gy = 0; gy < n_gy; gy++) {
             const uint32_t m0 = gy * rows;
             const uint32_t m_last = std::min(m0 + rows, w.N_t0) - 1;
-            const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + rp.DD * w.dtau, mt.t0_data, mt.numAtoms, g);
+            const uint32_t e_lo = index_t1(w.t0 + w.tau + m0 * w.dt0 + p.DD * w.dtau, mt.t0_data, mt.numAtoms, g);
             const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, mt.t0_data, mt.numAtoms, g);
             if (((e_lo + 1) & ~1u) < s_hi + 2) return false;
         }
     }
+    *out = p;
     return true;
 }
 
@@ -843,13 +865,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     uint32_t *groupmax = nullptr;
     bool rect_p = false;
     if (path == PATH_FAST && w.type == TCW_WINDOW_RECT) {
-        rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
+        rect_p = plan_rect_p(h, w, S, (uint32_t)rect_R, TAtom, g, &rp);
+        if (!rect_p) rp = plan_rect(h, w, S, (uint32_t)rect_R, TAtom, g);
         const uint32_t rows_per_tile = TCW_RECT_WARPS * rp.G * (uint32_t)rect_R;
         const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
         if (n_gy > 65535u) {
             path = PATH_GENERIC;
+            rect_p = false;
         } else {
-            rect_p = rectp_ok(h, w, rp, (uint32_t)rect_R, TAtom, g);
             if (!want_btsg) {
                 // The map kernels track max VALUES only.  The argmax is completed by the lnBtSG pass
                 // (which re-reads F_mn anyway) or, without it, by the locate kernel: one CTA per
@@ -991,28 +1014,27 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             const bool rect_staged = rp.staged;
             const uint32_t rows_per_tile = TCW_RECT_WARPS * rect_G * rect_R;
             const uint32_t n_gy = (w.N_t0 + rows_per_tile - 1) / rows_per_tile;
-            // head strip (and, without the persistent kernel, every tile) in the one-tile-per-CTA kernel
-            dim3 grid(rect_p ? 1 : 1 + n_reg, n_gy, cnt);
+            dim3 grid(1 + n_reg, n_gy, cnt);
             const uint32_t gx_total = 1 + n_reg;
             const size_t smem = TCW_RECT_SMEM;
             if (rect_p) {
-                // regular tiles: one persistent CTA per SM, producer / consumer warps, tile queue
-                const uint32_t n_gy_p = (w.N_t0 + TCW_RECTP_ROWS - 1) / TCW_RECTP_ROWS;
-                const uint64_t n_tiles64 = (uint64_t)cnt * n_gy_p * n_reg;
+                // one persistent CTA per SM, producer / consumer warps, tile queue over all tiles
+                const uint64_t n_tiles64 = (uint64_t)cnt * n_gy * gx_total;  // 128-row tiles: same n_gy as G = 4
                 if (n_tiles64 >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many rect tiles in one launch");
                 const uint32_t n_tiles = (uint32_t)n_tiles64;
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
                 tcw_rect_map_p_kernel<<<ctas, TCW_RECTP_THREADS, TCW_RECTP_SMEM, st>>>(
-                    (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, n_reg, n_gy_p,
-                    n_tiles, (uint32_t *)h->d_counter.p + sb, fmn, (unsigned long long *)h->d_maxkey.p, groupmax);
-                h->launches++;
-                CUDA_TRY(h, cudaGetLastError());
+                    (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, n_reg, n_gy,
+                    n_tiles, (uint32_t *)h->d_counter.p + sb, fmn, (unsigned long long *)h->d_maxkey.p, groupmax,
+                    (uint32_t *)h->d_flags.p);
             }
 #define LAUNCH_RECT(RR, STG)                                                                               \
     do {                                                                                                   \
-        tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                                \
-            (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, rect_G, \
-            gx_total, fmn, (unsigned long long *)h->d_maxkey.p, groupmax, (uint32_t *)h->d_flags.p);       \
+        if (!rect_p)                                                                                       \
+            tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                            \
+                (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
+                rect_G, gx_total, fmn, (unsigned long long *)h->d_maxkey.p, groupmax,                      \
+                (uint32_t *)h->d_flags.p);                                                                 \
         if (groupmax) {                                                                                    \
             h->launches++;                                                                                 \
             CUDA_TRY(h, cudaGetLastError());                                                               \

@@ -871,3 +871,79 @@ def test_empty_detector_and_shared_bins(gpu, oracle):
     bad[0, 0, 10]["timestamp"] = bad[0, 0, 8]["timestamp"]  # going backwards: rejected
     with pytest.raises(L.TcwError):
         run_gpu(gpu, AtomBatch(bad, n_atoms, b.TAtom), w, L.FORCE_GENERIC)
+
+
+# ---- the persistent warp-specialised rect kernel (tcw_rect_p.cuh) --------------------------------
+
+
+@pytest.fixture(scope="module")
+def gpu_persist():
+    """A handle that takes the persistent rect kernel whenever the plan allows (by default only
+    launches with enough tiles to fill the GPU do), and one that never does."""
+    import os
+
+    old = os.environ.get("TCW_RECT_PERSIST")
+    try:
+        os.environ["TCW_RECT_PERSIST"] = "2"
+        hp = L.Handle(0)
+        os.environ["TCW_RECT_PERSIST"] = "0"
+        h0 = L.Handle(0)
+    finally:
+        if old is None:
+            os.environ.pop("TCW_RECT_PERSIST", None)
+        else:
+            os.environ["TCW_RECT_PERSIST"] = old
+    yield hp, h0
+    hp.close()
+    h0.close()
+
+
+PERSIST_CASES = [
+    # dets, n, gap, tau0 (atoms), templates
+    (("H1", "L1"), 300, 0.0, 2, 3),
+    (("H1", "L1"), 700, 0.1, 2, 2),
+    (("H1", "L1", "V1"), 257, 0.0, 3, 2),
+    (("H1",), 400, 0.0, 2, 2),          # ill-conditioned short windows: guarded tiles, F = 2 fallbacks
+    (("H1", "L1"), 500, 0.0, 1, 2),     # tau = one atom: degenerate cells on the diagonal (head tiles)
+    (("H1", "L1"), 1700, 0.05, 2, 1),   # two regular tiles per row tile
+]
+
+
+@pytest.mark.parametrize("dets,n,gap,tau0,T", PERSIST_CASES)
+def test_rect_persistent_kernel(gpu_persist, oracle, dets, n, gap, tau0, T):
+    """Same maps through the persistent kernel (head + regular tiles, dynamic row groups, conditioning
+    certificate) and through the one-tile-per-CTA kernel: F_mn within tolerance of the oracle and of
+    each other, identical fallback cells, np.argmax-consistent fused argmax in all reduction modes,
+    same degenerate status."""
+    hp, h0 = gpu_persist
+    b = synth_atoms(T, n, dets, seed=300 + n, gap_fraction=gap)
+    w = canonical_window("rect", 10**9, n)
+    w.tau = tau0 * 1800
+    flags = L.ALLOW_DEGENERATE if tau0 == 1 else 0
+    res_p, F_p = run_gpu(hp, b, w, flags)
+    res_0, F_0 = run_gpu(h0, b, w, flags)
+    assert np.all(res_p["path"] == 1)
+    flipped = (F_p == 2.0) != (F_0 == 2.0)  # cells within rounding of the cond = 1e4 cut may flip
+    assert flipped.sum() <= (5 * T if len(dets) == 1 else 0), "fallback cells must not depend on the kernel"
+    rel_k = np.abs(F_p - F_0)[~flipped] / np.maximum(np.abs(F_0[~flipped]), 1e-30)
+    assert rel_k.max() <= (1e-3 if len(dets) == 1 else 2e-5), rel_k.max()
+    for t in range(T):
+        o = oracle.compute_map(b.template(t), b.TAtom, w, allow_degenerate=True)
+        rel = np.abs(F_p[t] - o["F_mn"]) / np.maximum(np.abs(o["F_mn"]), 1e-30)
+        if len(dets) > 1:
+            assert rel.max() <= RTOL, (t, rel.max())
+        else:
+            ok = ~flipped[t] & ((F_p[t] == 2.0) == (o["F_mn"] == 2.0))
+            assert (~ok).sum() <= 10 and np.quantile(rel[ok], 0.999) <= RTOL and rel[ok].max() <= 5e-3
+        flat = int(np.argmax(F_p[t]))
+        for btsg, fmn in ((True, True), (False, False), (True, False), (False, True)):
+            r2 = res_p if (btsg and fmn) else run_gpu(hp, b, w, flags, btsg=btsg, fmn=fmn)[0]
+            assert (int(r2["m_ML"][t]), int(r2["n_ML"][t])) == divmod(flat, F_p.shape[2]), (t, btsg, fmn)
+            assert float(r2["maxF"][t]) == float(F_p[t].max())
+        again = oracle.bstat(F_p[t].astype(np.float64), float(res_p["maxF"][t]), w, use_lut=True)
+        assert float(res_p["lnBtSG"][t]) == pytest.approx(again["lnBtSG"], abs=ATOL_PASS)
+        assert (int(res_p["m_MP"][t]), int(res_p["n_MP"][t])) == (again["m_MP"], again["n_MP"])
+    if tau0 == 1:  # lal's single-atom abort is reported by both kernels
+        strict_p = run_gpu(hp, b, w, 0)[0]
+        strict_0 = run_gpu(h0, b, w, 0)[0]
+        assert np.all(strict_p["status"] == L.E_DEGENERATE) and np.all(strict_0["status"] == L.E_DEGENERATE)

@@ -15,7 +15,8 @@ from .atoms import ATOM_DTYPE, AtomBatch
 from .window import TransientWindowRange
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libtcw_b200.so")
+# $PYFSTAT_B200_LIB: another build of the same library (development: kernel variants side by side)
+LIB_PATH = os.environ.get("PYFSTAT_B200_LIB") or os.path.join(PKG, "libtcw_b200.so")
 
 TCW_ABI_VERSION = 2
 
@@ -105,7 +106,7 @@ def load_library(build_if_missing: bool = True):
     if build_if_missing:
         from . import build as _build
 
-        if _build.needs_build() and _build.find_nvcc() is not None:
+        if not os.environ.get("PYFSTAT_B200_LIB") and _build.needs_build() and _build.find_nvcc() is not None:
             _build.build()
     if not os.path.exists(LIB_PATH):
         raise ImportError(

@@ -7,17 +7,17 @@
 // samples sit in that prologue and its barriers, during which the SM runs on the other CTA's 8
 // warps alone; the narrow head-strip tiles (the diagonal) are almost all prologue.  Here ONE CTA
 // per SM lives for the whole launch and splits into
-//   * 2 producer warps: fetch the next tile (global atomic counter), issue the 1-D TMA bulk copies
+//   * 1 producer warp: fetches the next tile (global atomic counter), issue the 1-D TMA bulk copies
 //     of its FP64 prefix slice (cp.async.bulk -> UBLKCP), build the end-index table and the
 //     per-row terms, convert the slice in place -- into the OTHER of two shared-memory tile
 //     buffers, and
-//   * 14 consumer warps that never leave the F-stat loops (rect_rows of tcw_rect.cuh, unchanged
+//   * 15 consumer warps that never leave the F-stat loops (rect_rows of tcw_rect.cuh, unchanged
 //     arithmetic).  The 32 row groups (4 rows each) of a 128-row tile are handed out through a
 //     shared-memory counter: warp schedulers hosting a producer warp run 3 consumer warps, the
 //     others 4, so equal static shares left the faster warps waiting ~10 % of the time (ncu
 //     r02_rectp_v1: long-scoreboard samples on the `ready` barrier),
 // handing tiles over through mbarriers (full: TMA bytes landed; ready: tables + {q,q} built;
-// empty: every row group of the buffer's tile is done).
+// empty: every row group of the buffer's tile is done and every consumer warp has left it).
 //
 // Tile kinds.  Regular tiles (d >= DD) are off-diagonal by the host's certificate: one split
 // point per tile, {q,q} table, packed-FP32 loop.  Head tiles (d < DD, holding the diagonal) keep
@@ -38,8 +38,10 @@
 #pragma once
 #include "tcw_rect.cuh"
 
-#define TCW_RECTP_CWARPS 14
-#define TCW_RECTP_PWARPS 2
+#ifndef TCW_RECTP_CWARPS
+#define TCW_RECTP_CWARPS 15  // measured (60 d, T = 64, F_mn stored): see DESIGN.md section 5
+#define TCW_RECTP_PWARPS 1
+#endif
 #define TCW_RECTP_THREADS ((TCW_RECTP_CWARPS + TCW_RECTP_PWARPS) * 32)
 #define TCW_RECTP_PTHREADS (TCW_RECTP_PWARPS * 32)
 #define TCW_RECTP_ROWS 128                      // rows per tile
@@ -55,10 +57,13 @@
 #define TCW_RECTP_COND_MAX 2500.0  // certificate bound (reference cut: 1e4)
 
 struct RectPDesc {
-    uint32_t tile;     // 0xFFFFFFFF: no more tiles
-    uint32_t noguard;  // tile-wide conditioning certificate holds (regular tiles)
-    uint32_t a0;       // first staged prefix index
-    uint32_t next;     // next row group to hand out
+    uint32_t tile;      // 0xFFFFFFFF: no more tiles
+    uint32_t noguard;   // bit g: the conditioning certificate holds for row group g (regular tiles)
+    uint32_t a0;        // first staged prefix index
+    uint32_t next;      // next row group to hand out
+    uint32_t numAtoms;  // of the tile's template (consumers need no global load per tile)
+    uint32_t t0_data;
+    uint32_t pad[2];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -87,7 +92,7 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
         for (int b = 0; b < 2; b++) {
             mbar_init(&bar_full[b], 1);
             mbar_init(&bar_ready[b], TCW_RECTP_PTHREADS);
-            mbar_init(&bar_empty[b], TCW_RECTP_GROUPS);
+            mbar_init(&bar_empty[b], TCW_RECTP_GROUPS + TCW_RECTP_CWARPS);
         }
         mbar_fence_init();
     }
@@ -146,6 +151,8 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
                              &bar_full[b]);
                 desc[b].a0 = a0;
                 desc[b].next = 0u;
+                desc[b].numAtoms = numAtoms;
+                desc[b].t0_data = t0_data;
                 if (head) desc[b].noguard = 0u;
             }
             // start index and start prefixes P_c[i_t0(row)] of the tile's rows, issued while the bulk copies fly
@@ -183,23 +190,33 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
                 }
                 mbar_wait(&bar_full[b], (k >> 1) & 1u);
             } else {
-                // conditioning certificate of the tile (one thread; 12 FP64 loads)
-                if (pt == 32) {
-                    const uint32_t s_lo = index_t0(w.t0 + m0 * w.dt0, t0_data, numAtoms, g);
-                    const uint32_t s_hi = index_t0(w.t0 + m_last * w.dt0, t0_data, numAtoms, g);
-                    double core[3], hull[3];
+                // conditioning certificate per row group (lane g <-> group g; 12 FP64 loads each): every
+                // window of the group contains [s_hi, e_lo] and lies inside [s_lo, e_hi]
+                if (pt < TCW_RECTP_GROUPS) {
+                    const uint32_t r0 = m0 + pt * R;
+                    bool ok = false;
+                    if (r0 < w.N_t0) {
+                        const uint32_t r3 = min(r0 + R - 1, w.N_t0 - 1);
+                        const uint32_t s_lo = index_t0(w.t0 + r0 * w.dt0, t0_data, numAtoms, g);
+                        const uint32_t s_hi = index_t0(w.t0 + r3 * w.dt0, t0_data, numAtoms, g);
+                        const uint32_t ge_lo = index_t1(t1_tile + (pt * R) * w.dtau, t0_data, numAtoms, g);
+                        const uint32_t ge_hi = index_t1(t1_tile + (pt * R + d_last - d0) * w.dtau, t0_data, numAtoms, g);
+                        double core[3], hull[3];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const double *pc = Pt + (size_t)c * ppad;
-                        core[c] = __ldg(pc + e_lo + 1) - __ldg(pc + s_hi);
-                        hull[c] = __ldg(pc + e_hi + 1) - __ldg(pc + s_lo);
+                        for (int c = 0; c < 3; c++) {
+                            const double *pc = Pt + (size_t)c * ppad;
+                            core[c] = __ldg(pc + ge_lo + 1) - __ldg(pc + s_hi);
+                            hull[c] = __ldg(pc + ge_hi + 1) - __ldg(pc + s_lo);
+                        }
+                        const double sc = core[0] + core[1];
+                        const double dc = sqrt((core[0] - core[1]) * (core[0] - core[1]) + 4.0 * core[2] * core[2]);
+                        const double sh = hull[0] + hull[1];
+                        const double dh = sqrt((hull[0] - hull[1]) * (hull[0] - hull[1]) + 4.0 * hull[2] * hull[2]);
+                        const double lmin = sc - dc, lmax = sh + dh;
+                        ok = ge_lo >= s_hi && lmin > 0.0 && lmax < TCW_RECTP_COND_MAX * lmin;
                     }
-                    const double sc = core[0] + core[1];
-                    const double dc = sqrt((core[0] - core[1]) * (core[0] - core[1]) + 4.0 * core[2] * core[2]);
-                    const double sh = hull[0] + hull[1];
-                    const double dh = sqrt((hull[0] - hull[1]) * (hull[0] - hull[1]) + 4.0 * hull[2] * hull[2]);
-                    const double lmin = sc - dc, lmax = sh + dh;
-                    desc[b].noguard = (lmin > 0.0 && lmax < TCW_RECTP_COND_MAX * lmin) ? 1u : 0u;
+                    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+                    if (pt == 0) desc[b].noguard = mask;
                 }
                 mbar_wait(&bar_full[b], (k >> 1) & 1u);
                 // split point rho = a0: per-row terms fl32(P[rho] - P[s]) and, in place over the FP64
@@ -243,14 +260,14 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
         mbar_wait(&bar_ready[b], (k >> 1) & 1u);
         const uint32_t tile = desc[b].tile;
         if (tile == 0xFFFFFFFFu) break;
-        const bool noguard = desc[b].noguard != 0u;
+        const uint32_t noguard_mask = desc[b].noguard;
         const uint32_t a0 = desc[b].a0;
         const uint32_t bx = tile % gx_total;
         const uint32_t by = (tile / gx_total) % n_gy;
         const uint32_t tz = tile / (gx_total * n_gy);
         const bool head = bx == 0;
         const int t = t_base + (int)tz;
-        const uint32_t numAtoms = meta[t].numAtoms, t0_data = meta[t].t0_data;
+        const uint32_t numAtoms = desc[b].numAtoms, t0_data = desc[b].t0_data;
         const double *Pt = P + (size_t)t * TCW_NCH * ppad;
         const uint32_t m0 = by * TCW_RECTP_ROWS;
         const uint32_t d0 = head ? 0u : DD + (bx - 1) * DT;
@@ -260,12 +277,16 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
         float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
         uint32_t *gm = groupmax ? groupmax + ((size_t)tz * gx_total + bx) * n_grp + (size_t)by * TCW_RECTP_GROUPS : nullptr;
         uint32_t degenerate = 0;
+        // the ticket of the NEXT row group is drawn before the current one is processed, so that the
+        // shared-memory atomic's latency never sits between two groups
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&desc[b].next, 1u);
 #pragma unroll 1
         for (;;) {
-            uint32_t grp = 0;
-            if (lane == 0) grp = atomicAdd(&desc[b].next, 1u);
-            grp = __shfl_sync(0xffffffffu, grp, 0);
+            const uint32_t grp = __shfl_sync(0xffffffffu, ticket, 0);
             if (grp >= TCW_RECTP_GROUPS) break;
+            if (lane == 0) ticket = atomicAdd(&desc[b].next, 1u);
+            const bool noguard = (noguard_mask >> grp) & 1u;
             const uint32_t grow = grp * R;
             if (m0 + grow < w.N_t0) {
                 float vgrp = -1.0f;
@@ -328,6 +349,9 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);  // this row group no longer reads the buffer
         }
+        // every warp also checks out of the tile: the buffer (and its ticket counter) is not recycled
+        // while a late warp may still draw from it
+        if (lane == 0) mbar_arrive(&bar_empty[b]);
         if (__any_sync(0xffffffffu, degenerate != 0u) && lane == 0) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
     }
 }

@@ -13,7 +13,8 @@
 //   d_W      [n_tiles][KW][64] float32  exponential-window weight table (cached per window)
 //   d_Fmn    [T][N_t0][N_tau] float32   only with TCW_WANT_FMN; else a sub-batch scratch
 //                                       sized to stay L2-resident when lnBtSG needs a 2nd pass
-//   d_maxkey [T] u64, d_rowsum [T][N_t0] f64, d_colsum [T][N_tau] f64, d_results [T]
+//   d_zero   one zero-initialised region per map: max keys [T] u64, lnBtSG marginals [T][N_t0] and
+//            [T][N_tau] (64-bit fixed point), flags [T], tile-queue counters; d_results [T]
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -70,8 +71,10 @@ struct tcw_handle {
     uint32_t Nmax = 0, xpad = 0, ppad = 0;
     bool uniform = true;  // all templates share (t0_data, numAtoms)
     std::vector<TplMeta> meta;
-    DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_maxkey, d_rowsum, d_colsum,
-        d_flags, d_results, d_W, d_Kn, d_lut, d_flush, d_wins, d_tilemax, d_counter;
+    // d_zero: everything a map needs zero-initialised -- max keys, lnBtSG marginals, flags, tile-queue
+    // counters -- in ONE region, cleared by one memset per map
+    DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
+        d_wins, d_tilemax;
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -364,8 +367,8 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
-                      &h->d_maxkey, &h->d_rowsum, &h->d_colsum, &h->d_flags, &h->d_results, &h->d_W,
-                      &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins, &h->d_tilemax, &h->d_counter})
+                      &h->d_zero, &h->d_results, &h->d_W, &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins,
+                      &h->d_tilemax})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -831,13 +834,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     const bool need_P = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
     if (need_X8 && (rc = ensure(h, h->d_X8, (size_t)T * 8 * h->xpad * sizeof(float)))) return rc;
     if (need_P && (rc = ensure(h, h->d_P, (size_t)T * TCW_NCH * h->ppad * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->d_maxkey, (size_t)T * sizeof(unsigned long long)))) return rc;
-    if ((rc = ensure(h, h->d_flags, (size_t)T * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(h, h->d_results, (size_t)T * sizeof(tcw_result)))) return rc;
-    if (want_btsg) {
-        if ((rc = ensure(h, h->d_rowsum, (size_t)T * w.N_t0 * sizeof(double)))) return rc;
-        if ((rc = ensure(h, h->d_colsum, (size_t)T * w.N_tau * sizeof(double)))) return rc;
-    }
     // templates per sub-batch: with lnBtSG the F_mn of a sub-batch is written by the map kernel
     // and re-read by the BtSG pass.  Measured (60 d rect, T=64): 64 MB sub-batches (L2-resident
     // scratch, one template per launch) 1.8e11 cells/s, 2-4 GB sub-batches 3.0e11 cells/s --
@@ -883,7 +880,6 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 if ((rc = ensure(h, h->d_tilemax, n_entries * sizeof(uint32_t)))) return rc;
                 groupmax = (uint32_t *)h->d_tilemax.p;
             }
-            if (rect_p && (rc = ensure(h, h->d_counter, (size_t)n_sub * sizeof(uint32_t)))) return rc;
         }
     }
     const bool need_P2 = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
@@ -902,16 +898,30 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         h->ev_sub.push_back(ev);
     }
 
+    // the zero-initialised region (one memset): 256-byte aligned sub-arrays
+    size_t zero_bytes = 0;
+    auto zero_take = [&zero_bytes](size_t bytes) {
+        const size_t o = zero_bytes;
+        zero_bytes += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_maxkey = zero_take((size_t)T * sizeof(unsigned long long));
+    const size_t o_rowsum = zero_take(want_btsg ? (size_t)T * w.N_t0 * sizeof(unsigned long long) : 0);
+    const size_t o_colsum = zero_take(want_btsg ? (size_t)T * w.N_tau * sizeof(unsigned long long) : 0);
+    const size_t o_flags = zero_take((size_t)T * sizeof(uint32_t));
+    const size_t o_counter = zero_take((size_t)n_sub * sizeof(uint32_t));
+    if ((rc = ensure(h, h->d_zero, zero_bytes))) return rc;
+    unsigned char *zbase = (unsigned char *)h->d_zero.p;
+    unsigned long long *p_maxkey = (unsigned long long *)(zbase + o_maxkey);
+    unsigned long long *p_rowsum = (unsigned long long *)(zbase + o_rowsum);
+    unsigned long long *p_colsum = (unsigned long long *)(zbase + o_colsum);
+    uint32_t *p_flags = (uint32_t *)(zbase + o_flags);
+    uint32_t *p_counter = (uint32_t *)(zbase + o_counter);
+
     cudaStream_t st = h->stream;
     h->stage_valid = false;
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[0], st));
-    CUDA_TRY(h, cudaMemsetAsync(h->d_maxkey.p, 0, (size_t)T * sizeof(unsigned long long), st));
-    CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, (size_t)T * sizeof(uint32_t), st));
-    if (rect_p) CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, (size_t)n_sub * sizeof(uint32_t), st));
-    if (want_btsg) {
-        CUDA_TRY(h, cudaMemsetAsync(h->d_rowsum.p, 0, (size_t)T * w.N_t0 * sizeof(double), st));
-        CUDA_TRY(h, cudaMemsetAsync(h->d_colsum.p, 0, (size_t)T * w.N_tau * sizeof(double), st));
-    }
+    CUDA_TRY(h, cudaMemsetAsync(h->d_zero.p, 0, zero_bytes, st));
 
     // ---- stage 1: exponential-window weight table (cached across calls) ----
     uint32_t exp_TM = 0, exp_TN = 0;
@@ -977,12 +987,21 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         const int cnt = std::min(S, T - t_base);
         if (host_atoms) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_up[sb], 0));
         // merge detectors, transpose to channels, FP64 prefix scan
-        tcw_prep_kernel<<<cnt, TCW_PREP_THREADS, 0, st>>>(
-            (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p, t_base,
-            h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, need_X8 ? (float *)h->d_X8.p : nullptr, h->xpad,
-            need_P2 ? (double *)h->d_P.p : nullptr, h->ppad, (uint32_t *)h->d_flags.p);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
+        {
+            dim3 grid_m((h->xpad + TCW_PREP_THREADS - 1) / TCW_PREP_THREADS, cnt);
+            tcw_prep_merge_kernel<<<grid_m, TCW_PREP_THREADS, 0, st>>>(
+                (const tcw_atom *)h->d_atoms.p, (const uint32_t *)h->d_natoms.p, (const TplMeta *)h->d_meta.p, t_base,
+                h->numDet, h->stride, TAtom, g.md, (float *)h->d_X.p, need_X8 ? (float *)h->d_X8.p : nullptr, h->xpad,
+                p_flags);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+            if (need_P2) {
+                tcw_prep_scan_kernel<<<dim3(TCW_NCH, cnt), TCW_PREP_THREADS, 0, st>>>(
+                    (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, (double *)h->d_P.p, h->ppad);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+            }
+        }
         if (sb == 0) CUDA_TRY(h, cudaEventRecord(h->ev_stage[1], st));
         float *fmn = fmn_full ? fmn_full + (size_t)t_base * pcells : fmn_scratch;
         CUDA_TRY(h, cudaEventRecord(h->ev_sub[3 * sb + 0], st));
@@ -997,13 +1016,13 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         if (warp_per_cell)                                                                                  \
             tcw_map_generic_warp_kernel<WT, EX><<<grid, TCW_GENERIC_WARP_THREADS, 0, st>>>(                 \
                 (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
-                (int)none_window, g, lut, fmn, (unsigned long long *)h->d_maxkey.p,  \
-                (uint32_t *)h->d_flags.p);                                                                  \
+                (int)none_window, g, lut, fmn, p_maxkey,  \
+                p_flags);                                                                  \
         else                                                                                                \
             tcw_map_generic_kernel<WT, EX><<<grid, TCW_GENERIC_THREADS, 0, st>>>(                           \
                 (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, w, d_wins,          \
-                (int)none_window, g, lut, fmn, (unsigned long long *)h->d_maxkey.p,  \
-                (uint32_t *)h->d_flags.p);                                                                  \
+                (int)none_window, g, lut, fmn, p_maxkey,  \
+                p_flags);                                                                  \
     } while (0)
             if (w.type == TCW_WINDOW_RECT) LAUNCH_GENERIC(TCW_WINDOW_RECT, false);
             else if (exact) LAUNCH_GENERIC(TCW_WINDOW_EXP, true);
@@ -1025,23 +1044,23 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
                 tcw_rect_map_p_kernel<<<ctas, TCW_RECTP_THREADS, TCW_RECTP_SMEM, st>>>(
                     (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT, n_reg, n_gy,
-                    n_tiles, (uint32_t *)h->d_counter.p + sb, fmn, (unsigned long long *)h->d_maxkey.p, groupmax,
-                    (uint32_t *)h->d_flags.p);
+                    n_tiles, p_counter + sb, fmn, p_maxkey, groupmax,
+                    p_flags);
             }
 #define LAUNCH_RECT(RR, STG)                                                                               \
     do {                                                                                                   \
         if (!rect_p)                                                                                       \
             tcw_rect_map_kernel<RR, STG><<<grid, TCW_RECT_THREADS, smem, st>>>(                            \
                 (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
-                rect_G, gx_total, fmn, (unsigned long long *)h->d_maxkey.p, groupmax,                      \
-                (uint32_t *)h->d_flags.p);                                                                 \
+                rect_G, gx_total, fmn, p_maxkey, groupmax,                      \
+                p_flags);                                                                 \
         if (groupmax) {                                                                                    \
             h->launches++;                                                                                 \
             CUDA_TRY(h, cudaGetLastError());                                                               \
             tcw_rect_locate_kernel<RR, STG><<<cnt, TCW_RECT_THREADS, smem, st>>>(                          \
                 (const double *)h->d_P.p, h->ppad, (const TplMeta *)h->d_meta.p, t_base, w, g, DD, DT,     \
-                rect_G, gx_total, grid.y, (unsigned long long *)h->d_maxkey.p, groupmax,                   \
-                (uint32_t *)h->d_flags.p);                                                                 \
+                rect_G, gx_total, grid.y, p_maxkey, groupmax,                   \
+                p_flags);                                                                 \
         }                                                                                                  \
     } while (0)
             if (rect_R == 4 && rect_staged) LAUNCH_RECT(4, true);
@@ -1054,8 +1073,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
 #define LAUNCH_EXP(CFG)                                                                                   \
     tcw_exp_map_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                                     \
         (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,    \
-        (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, (unsigned long long *)h->d_maxkey.p,        \
-        (uint32_t *)h->d_flags.p)
+        (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, p_maxkey,        \
+        p_flags)
             if (h->exp_variant == 0) LAUNCH_EXP(ExpCfgA);
             else if (h->exp_variant == 2) LAUNCH_EXP(ExpCfgC);
             else LAUNCH_EXP(ExpCfgB);
@@ -1072,8 +1091,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             const bool locate = path == PATH_FAST && w.type == TCW_WINDOW_RECT;
 #define LAUNCH_BTSG(KERNEL, EX, LOC, SMEM)                                                            \
     KERNEL<EX, LOC><<<grid, TCW_BTSG_THREADS, SMEM, st>>>(                                            \
-        fmn, t_base, w.N_t0, w.N_tau, w.pitch, n_ct, (unsigned long long *)h->d_maxkey.p, lut, fx_scale, \
-        (unsigned long long *)h->d_rowsum.p, (unsigned long long *)h->d_colsum.p)
+        fmn, t_base, w.N_t0, w.N_tau, w.pitch, n_ct, p_maxkey, lut, fx_scale, \
+        p_rowsum, p_colsum)
             if (btsg_table) {
                 const size_t smem = TCW_BTSG_TABLE_SMEM(h->lut_len);
                 if (locate) LAUNCH_BTSG(tcw_btsg_table_kernel, false, true, smem);
@@ -1092,8 +1111,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
 
     // ---- stage 4: one result record per template ----
     tcw_finalize_kernel<<<T, TCW_FIN_THREADS, 0, st>>>(
-        (const unsigned long long *)h->d_maxkey.p, (const uint32_t *)h->d_flags.p,
-        (const unsigned long long *)h->d_rowsum.p, (const unsigned long long *)h->d_colsum.p, 1.0 / fx_scale,
+        p_maxkey, p_flags,
+        p_rowsum, p_colsum, 1.0 / fx_scale,
         (const TplMeta *)h->d_meta.p, w, d_wins, (int)none_window, TAtom, (int)want_btsg,
         (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)path, (tcw_result *)h->d_results.p);
     h->launches++;

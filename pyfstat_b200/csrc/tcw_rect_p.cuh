@@ -7,11 +7,11 @@
 // samples sit in that prologue and its barriers, during which the SM runs on the other CTA's 8
 // warps alone; the narrow head-strip tiles (the diagonal) are almost all prologue.  Here ONE CTA
 // per SM lives for the whole launch and splits into
-//   * 1 producer warp: fetches the next tile (global atomic counter), issue the 1-D TMA bulk copies
+//   * 2 producer warps: fetch the next tile (global atomic counter), issue the 1-D TMA bulk copies
 //     of its FP64 prefix slice (cp.async.bulk -> UBLKCP), build the end-index table and the
 //     per-row terms, convert the slice in place -- into the OTHER of two shared-memory tile
 //     buffers, and
-//   * 15 consumer warps that never leave the F-stat loops (rect_rows of tcw_rect.cuh, unchanged
+//   * 14 consumer warps that never leave the F-stat loops (rect_rows of tcw_rect.cuh, unchanged
 //     arithmetic).  The 32 row groups (4 rows each) of a 128-row tile are handed out through a
 //     shared-memory counter: warp schedulers hosting a producer warp run 3 consumer warps, the
 //     others 4, so equal static shares left the faster warps waiting ~10 % of the time (ncu
@@ -39,8 +39,10 @@
 #include "tcw_rect.cuh"
 
 #ifndef TCW_RECTP_CWARPS
-#define TCW_RECTP_CWARPS 15  // measured (60 d, T = 64, F_mn stored): see DESIGN.md section 5
-#define TCW_RECTP_PWARPS 1
+// measured (60 d, T = 64, F_mn stored, map stage): 14 + 2 warps 0.614 ms, 15 + 1 warps 0.638 ms (one
+// producer warp cannot keep up on the cheap head tiles); one-tile-per-CTA kernel 0.635 ms
+#define TCW_RECTP_CWARPS 14
+#define TCW_RECTP_PWARPS 2
 #endif
 #define TCW_RECTP_THREADS ((TCW_RECTP_CWARPS + TCW_RECTP_PWARPS) * 32)
 #define TCW_RECTP_PTHREADS (TCW_RECTP_PWARPS * 32)
@@ -192,7 +194,8 @@ tcw_rect_map_p_kernel(const double *__restrict__ P, uint32_t ppad, const TplMeta
             } else {
                 // conditioning certificate per row group (lane g <-> group g; 12 FP64 loads each): every
                 // window of the group contains [s_hi, e_lo] and lies inside [s_lo, e_hi]
-                if (pt < TCW_RECTP_GROUPS) {
+                if (pt < 32) {  // the first producer warp: lane g <-> row group g
+                    static_assert(TCW_RECTP_GROUPS == 32, "one lane per row group");
                     const uint32_t r0 = m0 + pt * R;
                     bool ok = false;
                     if (r0 < w.N_t0) {

@@ -74,7 +74,7 @@ struct tcw_handle {
     // d_zero: everything a map needs zero-initialised -- max keys, lnBtSG marginals, flags, tile-queue
     // counters -- in ONE region, cleared by one memset per map
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
-        d_wins, d_tilemax;
+        d_wins, d_tilemax, d_shift;
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -86,7 +86,7 @@ struct tcw_handle {
     // exp weight-table cache key
     bool w_valid = false;
     tcw_window_range w_key = {};
-    uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_i00 = 0, w_TN = 0;
+    uint32_t w_t0_data = 0, w_TAtom = 0, w_KW = 0, w_TN = 0;
     // XLALFastNegExp table geometry (runtime: tcw_set_exp_lut)
     double lut_xmax = 0.0;
     uint32_t lut_len = 0;
@@ -348,12 +348,15 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     RECT_ATTR(1, true);
     RECT_ATTR(1, false);
 #undef RECT_ATTR
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ExpCfgA::kSmem));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ExpCfgB::kSmem));
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<ExpCfgC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ExpCfgC::kSmem));
+#define EXP_ATTR(CFG)                                                                                          \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, true>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem));          \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, false>,                                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem))
+    EXP_ATTR(ExpCfgA);
+    EXP_ATTR(ExpCfgB);
+    EXP_ATTR(ExpCfgC);
+#undef EXP_ATTR
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECTP_SMEM));
@@ -368,7 +371,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_zero, &h->d_results, &h->d_W, &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins,
-                      &h->d_tilemax})
+                      &h->d_tilemax, &h->d_shift})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -483,8 +486,8 @@ static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n
     h->TAtom = TAtom;
     h->Nmax = Nmax;
     h->uniform = uniform;
-    // zero padding: the exp tiles read up to TM + KC + 4 atoms past the last needed one
-    h->xpad = ((Nmax + 64 /* max exp tile rows */ + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
+    // zero padding: an exp tile reads up to (TM - 1) * A + KC + 8 atoms past the last needed one (A <= 4)
+    h->xpad = ((Nmax + 64 /* max exp tile rows */ * TCW_EXP_AMAX + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
     h->ppad = ((Nmax + 1 + 8) + 1u) & ~1u;
     const size_t n_vec = (size_t)T * numDet;
     int rc;
@@ -535,9 +538,12 @@ static bool no_wrap(const MapWindow &w, uint32_t ef, uint32_t slack_n, const Tpl
 
 struct ExpPlan {
     bool ok = false;
-    uint32_t i00 = 0, KW = 0;
-    int32_t delta = 0;
-    std::vector<int32_t> Kn;
+    bool slide = true;   // A == 1: register sliding-window kernel
+    uint32_t KW = 0;
+    ExpClasses ec = {};
+    int32_t delta[TCW_EXP_PMAX] = {0, 0, 0, 0};
+    std::vector<int32_t> Kn;     // [P][N_tau]
+    std::vector<int32_t> shift;  // [T]: (t0_data of template 0 - t0_data of template t) / TAtom
 };
 
 static void exp_tile_dims(int variant, uint32_t *TM, uint32_t *TN) {
@@ -548,38 +554,75 @@ static void exp_tile_dims(int variant, uint32_t *TM, uint32_t *TN) {
     }
 }
 
+static uint32_t gcd_u32(uint32_t a, uint32_t b) {
+    while (b) {
+        const uint32_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// Host certificate + geometry of the tiled exponential-window kernel (tcw_exp.cuh): no uint32
+// wrap-around anywhere in the map; rows fall into P <= 4 classes of equal (t0_m - t0_data) mod
+// TAtom, consecutive rows of a class A <= 4 atoms apart; the templates' t0_data differ by whole
+// atoms (per-template index shift); the `< 0 -> 0` clamp of i_t1 never engages.  Rows whose start
+// index lies at or beyond the last atom are fine (zero sums -> the F = 2 fallback, as in the
+// reference).  Anything else goes to the generic kernels.
 static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     ExpPlan p;
     const uint32_t TAtom = h->TAtom;
-    if (w.dt0 != TAtom) return p;  // rows must advance by exactly one atom (sliding window)
+    const uint32_t rem = w.dt0 % TAtom;
+    const uint32_t P = rem ? TAtom / gcd_u32(rem, TAtom) : 1u;
+    if (P > TCW_EXP_PMAX) return p;
+    const uint64_t A64 = (uint64_t)P * w.dt0 / TAtom;  // exact by construction
+    if (A64 < 1 || A64 > TCW_EXP_AMAX) return p;
     const uint32_t t0_data = h->meta[0].t0_data;
+    p.shift.resize(h->T);
     for (int t = 0; t < h->T; t++) {
-        if (h->meta[t].t0_data != t0_data) return p;  // the weight table depends on t0 - t0_data
+        const int64_t d = (int64_t)t0_data - (int64_t)h->meta[t].t0_data;
+        if (d % (int64_t)TAtom != 0) return p;  // the weight tables depend on (t0 - t0_data) mod TAtom
+        p.shift[t] = (int32_t)(d / (int64_t)TAtom);
         if (!no_wrap(w, TCW_EXP_EFOLDING, 0, h->meta[t], TAtom)) return p;
     }
     const int64_t half = TAtom / 2;
-    const int64_t x0 = (int64_t)w.t0 - t0_data + half;
-    const int64_t i00 = x0 / TAtom;
-    for (int t = 0; t < h->T; t++)  // i_t0 must never hit the numAtoms-1 clamp
-        if (i00 + (int64_t)w.N_t0 - 1 > (int64_t)h->meta[t].numAtoms - 1) return p;
-    p.Kn.resize(w.N_tau);
+    const int64_t x0 = (int64_t)w.t0 - t0_data + half;  // >= 0 by no_wrap
+    uint32_t TM, TN;
+    exp_tile_dims(h->exp_variant, &TM, &TN);
+    p.ec.P = P;
+    p.ec.A = (uint32_t)A64;
+    p.slide = A64 == 1;
+    p.Kn.resize((size_t)P * w.N_tau);
     int64_t Kmax = -1;
-    for (uint32_t n = 0; n < w.N_tau; n++) {
-        const int64_t tau_n = (int64_t)w.tau + (int64_t)n * w.dtau;
-        const int64_t K = (x0 + (int64_t)TCW_EXP_EFOLDING * tau_n) / TAtom - 1 - i00;  // unclamped i_t1 - i_t0
-        p.Kn[n] = (int32_t)K;
-        Kmax = std::max(Kmax, K);
+    uint32_t ytiles = 0;
+    for (uint32_t r = 0; r < P; r++) {
+        const int64_t x0r = x0 + (int64_t)r * w.dt0;
+        const int64_t i00 = x0r / TAtom;
+        p.ec.i00[r] = (uint32_t)i00;
+        p.delta[r] = (int32_t)((int64_t)t0_data + i00 * TAtom - ((int64_t)w.t0 + (int64_t)r * w.dt0));
+        p.ec.ybeg[r] = ytiles;
+        const uint32_t n_rows = r < w.N_t0 ? (w.N_t0 - r + P - 1) / P : 0u;
+        ytiles += (n_rows + TM - 1) / TM;
+        bool i00_zero = false;  // some template's first row of this class starts at atom 0
+        for (int t = 0; t < h->T; t++) {
+            if (i00 + p.shift[t] < 0) return p;
+            i00_zero = i00_zero || (i00 + p.shift[t] == 0);
+        }
+        for (uint32_t n = 0; n < w.N_tau; n++) {
+            const int64_t tau_n = (int64_t)w.tau + (int64_t)n * w.dtau;
+            const int64_t K = (x0r + (int64_t)TCW_EXP_EFOLDING * tau_n) / TAtom - 1 - i00;  // unclamped i_t1 - i_t0
+            if (K < 0 && i00_zero) return p;  // the `< 0 -> 0` clamp of i_t1 would engage
+            p.Kn[(size_t)r * w.N_tau + n] = (int32_t)K;
+            Kmax = std::max(Kmax, K);
+        }
     }
-    if (i00 == 0 && p.Kn[0] < 0) return p;  // the `< 0 -> 0` clamp of i_t1 would engage
+    for (uint32_t r = P; r <= TCW_EXP_PMAX; r++) p.ec.ybeg[r] = ytiles;
+    if (ytiles > 65535u) return p;  // grid.y limit -> generic kernels
     if (Kmax > (int64_t)h->Nmax + 64) Kmax = (int64_t)h->Nmax + 64;  // never need k beyond the data
     for (auto &K : p.Kn) K = (int32_t)std::min<int64_t>(K, Kmax);
     p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
-    uint32_t TM, TN;
-    exp_tile_dims(h->exp_variant, &TM, &TN);
     const uint64_t n_tiles = (w.N_tau + TN - 1) / TN;
-    if (n_tiles * p.KW * TN * 4ull > (8ull << 30)) return p;  // table too large
-    p.i00 = (uint32_t)i00;
-    p.delta = (int32_t)((int64_t)t0_data + i00 * TAtom - (int64_t)w.t0);
+    if ((uint64_t)P * n_tiles * p.KW * TN * 4ull > (8ull << 30)) return p;  // table too large
     p.ok = true;
     return p;
 }
@@ -820,9 +863,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             if (ok) path = PATH_FAST;
         } else {
             ep = plan_exp(h, w);
-            uint32_t TM, TN;
-            exp_tile_dims(h->exp_variant, &TM, &TN);
-            if (ep.ok && (w.N_t0 + TM - 1) / TM <= 65535u) path = PATH_FAST;  // grid.y limit -> generic kernels
+            if (ep.ok) path = PATH_FAST;
         }
     }
 
@@ -932,11 +973,12 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
-            const size_t total = (size_t)n_tiles * ep.KW * exp_TN;
+            const size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;
             if ((rc = ensure(h, h->d_W, total * sizeof(float)))) return rc;
-            if ((rc = ensure(h, h->d_Kn, (size_t)w.N_tau * sizeof(int32_t)))) return rc;
+            if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
+            h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
-            CUDA_TRY(h, cudaMemcpyAsync(h->d_Kn.p, h->w_Kn.data(), (size_t)w.N_tau * sizeof(int32_t),
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_Kn.p, h->w_Kn.data(), h->w_Kn.size() * sizeof(int32_t),
                                         cudaMemcpyHostToDevice, st));
             ExpTableGeom eg;
             eg.N_tau = w.N_tau;
@@ -946,10 +988,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             eg.tau = w.tau;
             eg.dtau = w.dtau;
             eg.TAtom = TAtom;
-            eg.delta = ep.delta;
+            eg.P = ep.ec.P;
+            for (int r = 0; r < TCW_EXP_PMAX; r++) eg.delta[r] = ep.delta[r];
             const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->prop.multiProcessorCount * 16);
-            tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg,
-                                                         lut, (int)exact);
+            tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg, lut,
+                                                         (int)exact);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
@@ -959,9 +1002,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             h->w_TAtom = TAtom;
             h->w_exact = (int)exact;
             h->w_KW = ep.KW;
-            h->w_i00 = ep.i00;
             h->w_TN = exp_TN;
         }
+        // per-template index shift (whole atoms between the templates' first timestamps)
+        if ((rc = ensure(h, h->d_shift, (size_t)T * sizeof(int32_t)))) return rc;
+        unsigned char *stg = nullptr;
+        if ((rc = small_stage(h, 1, (size_t)T * sizeof(int32_t), &stg))) return rc;
+        memcpy(stg, ep.shift.data(), (size_t)T * sizeof(int32_t));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_shift.p, stg, (size_t)T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaEventRecord(h->ev_small[1], st));
+        h->small_pending[1] = true;
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_stage[2], st));
 
@@ -1069,12 +1119,20 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             else LAUNCH_RECT(1, false);
 #undef LAUNCH_RECT
         } else {
-            dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, (w.N_t0 + exp_TM - 1) / exp_TM, cnt);
-#define LAUNCH_EXP(CFG)                                                                                   \
-    tcw_exp_map_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                                     \
-        (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW,    \
-        (const TplMeta *)h->d_meta.p, t_base, w, ep.i00, fmn, p_maxkey,        \
-        p_flags)
+            dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, ep.ec.ybeg[TCW_EXP_PMAX], cnt);
+#define LAUNCH_EXP(CFG)                                                                                        \
+    do {                                                                                                       \
+        if (ep.slide)                                                                                          \
+            tcw_exp_map_kernel<CFG, true><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                            \
+                (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
+                (const TplMeta *)h->d_meta.p, (const int32_t *)h->d_shift.p, t_base, w, ep.ec, fmn, p_maxkey,  \
+                p_flags);                                                                                      \
+        else                                                                                                   \
+            tcw_exp_map_kernel<CFG, false><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                           \
+                (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
+                (const TplMeta *)h->d_meta.p, (const int32_t *)h->d_shift.p, t_base, w, ep.ec, fmn, p_maxkey,  \
+                p_flags);                                                                                      \
+    } while (0)
             if (h->exp_variant == 0) LAUNCH_EXP(ExpCfgA);
             else if (h->exp_variant == 2) LAUNCH_EXP(ExpCfgC);
             else LAUNCH_EXP(ExpCfgB);

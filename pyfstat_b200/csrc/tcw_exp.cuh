@@ -4,8 +4,12 @@
 // Replaces pyCUDAkernels/cudaTransientFstatExpWindow.cu (one thread per cell, every thread
 // re-reading its whole atom range from global memory and calling exp() per atom visit).
 //
-// When t0 - t0_data advances in whole atoms (dt0 == TAtom; host certificate in tcw_b200.cu),
-// the window weight of atom i for cell (m,n) depends only on k = i - i_t0(m) and n:
+// Row classes.  The window weight of atom i for cell (m,n) is a function of t_i - t0_m.  Rows whose
+// t0_m - t0_data are congruent modulo TAtom share it: with P = TAtom / gcd(dt0 mod TAtom, TAtom)
+// (P = 1 when dt0 is a whole number of atoms) the rows m = r, r + P, r + 2P, ... of class r start
+// A = P dt0 / TAtom atoms apart and see the same offsets (host certificate in tcw_b200.cu: P <= 4,
+// A <= 4; templates may differ in t0_data by whole atoms; rows starting beyond the data end read
+// zero padding).  Within a class the weight depends only on k = i - i_t0(m) and n:
 //     w(k,n) = e^{-(k*TAtom + delta)/tau_n}   for 0 <= k*TAtom + delta <= 3 tau_n, k <= K_n
 // (delta = offset of the first summed atom from t0; K_n = i_t1 - i_t0, Exp.cu:27-65), and not
 // on the template.  It is tabulated once per window range -- in `lal` mode with bit-exact
@@ -38,6 +42,8 @@
 #define TCW_EXP_STAGES 3    // measured: 2, 3 and 4 stages give the same time (41.2 ms / 128 30-d maps): staging is fully hidden
 #endif
 #define TCW_EXP_TNT 16     // threads along tau per CTA (fixed); a warp = 2 (t0) x 16 (tau) threads
+#define TCW_EXP_AMAX 4     // max atoms between consecutive rows of a row class
+#define TCW_EXP_PMAX 4     // max row classes
 
 // Tile configuration: NT threads, RM x RN cells per thread.
 //   tile = (NT/16 * RM) rows x (16 * RN) columns
@@ -47,12 +53,15 @@ struct ExpCfg {
     static constexpr int kRM = RM, kRN = RN;
     static constexpr int kTM = NT / TCW_EXP_TNT * RM;
     static constexpr int kTN = TCW_EXP_TNT * RN;
-    static constexpr int kXS = kTM + TCW_EXP_KC + 4;  // staged atoms (32-byte records: 7 channels + pad)
+    // staged atoms (32-byte records: 7 channels + pad): rows of a class are A atoms apart
+    static constexpr int kXS1 = kTM + TCW_EXP_KC + 4;                             // A == 1
+    static constexpr int kXS = (kTM - 1) * TCW_EXP_AMAX + 1 + TCW_EXP_KC + 4 + 3;  // A <= AMAX (multiple of 4)
     static constexpr int kWBytes = TCW_EXP_KC * kTN * 4;
     static constexpr int kXBytes = kXS * 32;
+    static constexpr int kXBytes1 = kXS1 * 32;
     static constexpr int kStageBytes = kWBytes + kXBytes;
     static constexpr int kSmem = TCW_EXP_STAGES * kStageBytes;
-    static_assert(kXS % 4 == 0 && kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
+    static_assert(kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
     static_assert(RM == 4, "the register sliding window is written for 4 rows per thread");
     static_assert(RN == 4 || RN == 2, "weights are fetched as float4 / float2");
 };
@@ -61,41 +70,55 @@ struct ExpTableGeom {
     uint32_t N_tau, n_tiles, KW;  // KW: table rows per column tile (multiple of KC)
     uint32_t TN;                  // columns per tile
     uint32_t tau, dtau, TAtom;
-    int32_t delta;  // (t0_data + i00*TAtom) - t0, in (-TAtom/2, TAtom/2]
+    uint32_t P;                       // row classes
+    int32_t delta[TCW_EXP_PMAX];      // per class: (t0_data + i00*TAtom) - t0_m, in (-TAtom/2, TAtom/2]
 };
 
-// W[nt][k][TN]: weight of relative atom k for column n = nt*TN + j.
+// geometry of the row classes for the map kernel
+struct ExpClasses {
+    uint32_t P, A;                    // classes; atoms between consecutive rows of a class
+    uint32_t ybeg[TCW_EXP_PMAX + 1];  // first row tile (blockIdx.y) of each class
+    uint32_t i00[TCW_EXP_PMAX];       // i_t0 of the class's first row, for the reference template
+};
+
+// W[class][nt][k][TN]: weight of relative atom k for column n = nt*TN + j; Kn[class][N_tau].
 __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__restrict__ Kn,
                                      ExpTableGeom eg, const ExpLut lut, int exact) {
-    const size_t total = (size_t)eg.n_tiles * eg.KW * eg.TN;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t per_class = (size_t)eg.n_tiles * eg.KW * eg.TN;
+    const size_t total = per_class * eg.P;
+    for (size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total;
+         idx0 += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t cls = (uint32_t)(idx0 / per_class);
+        const size_t idx = idx0 - (size_t)cls * per_class;
         const uint32_t j = (uint32_t)(idx % eg.TN);
         const size_t rest = idx / eg.TN;
         const uint32_t k = (uint32_t)(rest % eg.KW);
         const uint32_t nt = (uint32_t)(rest / eg.KW);
         const uint32_t n = nt * eg.TN + j;
         float wv = 0.0f;
-        if (n < eg.N_tau && (int32_t)k <= Kn[n]) {
+        if (n < eg.N_tau && (int32_t)k <= Kn[(size_t)cls * eg.N_tau + n]) {
             const uint32_t tau_n = eg.tau + n * eg.dtau;
-            const long long t_rel = (long long)k * eg.TAtom + eg.delta;  // t_i - t0_m
+            const long long t_rel = (long long)k * eg.TAtom + eg.delta[cls];  // t_i - t0_m
             if (t_rel >= 0 && t_rel <= (long long)TCW_EXP_EFOLDING * tau_n) {
                 // REAL8 x = 1.0*(t_i - t0)/tau; XLALFastNegExp(x)
                 const double x = __ddiv_rn((double)t_rel, (double)tau_n);
                 wv = (float)(exact ? exp(-x) : fast_neg_exp_lut(x, lut));
             }
         }
-        W[idx] = wv;
+        W[idx0] = wv;
     }
 }
 
-template <class Cfg>
+// SLIDE = true: A == 1, the rows of a thread are consecutive atoms -- their 4 atoms per channel form
+// a register sliding window (one new 32-byte record per k step).  SLIDE = false: rows are A <= 4
+// atoms apart; every row fetches its own record per step (2 broadcast LDS.128 each).
+template <class Cfg, bool SLIDE>
 __global__ void __launch_bounds__(Cfg::kThreads, (Cfg::kThreads == 256 ? (Cfg::kRN == 4 ? 1 : 2) : 3))
 tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__restrict__ W,
                    const int32_t *__restrict__ Kn, uint32_t KW, const TplMeta *__restrict__ meta,
-                   int t_base, MapWindow w, uint32_t i00, float *__restrict__ Fmn,
-                   unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
-    constexpr int TM = Cfg::kTM, TN = Cfg::kTN, RM = Cfg::kRM, RN = Cfg::kRN, XS = Cfg::kXS;
+                   const int32_t *__restrict__ shift, int t_base, MapWindow w, ExpClasses ec,
+                   float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+    constexpr int TM = Cfg::kTM, TN = Cfg::kTN, RM = Cfg::kRM, RN = Cfg::kRN;
     constexpr int NT = Cfg::kThreads;
     extern __shared__ __align__(128) unsigned char tcw_exp_smem[];
     __shared__ __align__(8) uint64_t full[TCW_EXP_STAGES];
@@ -104,14 +127,31 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
     const int tz = blockIdx.z;
     const int t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
-    const uint32_t nt = blockIdx.x, mt = blockIdx.y;
-    const uint32_t m0 = mt * TM, n0 = nt * TN;
-    const uint32_t s_base = i00 + m0;  // i_t0 of the tile's first row (dt0 == TAtom)
+    const uint32_t nt = blockIdx.x;
+    // row class of this row tile and the tile's first row within the class (selects, not indexing:
+    // a dynamically indexed kernel parameter would be copied to local memory)
+    uint32_t cls = 0, ybeg = 0, i00c = ec.i00[0];
+#pragma unroll
+    for (int c = 1; c < TCW_EXP_PMAX; c++)
+        if ((uint32_t)c < ec.P && blockIdx.y >= ec.ybeg[c]) {
+            cls = c;
+            ybeg = ec.ybeg[c];
+            i00c = ec.i00[c];
+        }
+    const uint32_t A = SLIDE ? 1u : ec.A;
+    const uint32_t j0 = (blockIdx.y - ybeg) * TM;                // row index within the class
+    const uint32_t n_rows = (w.N_t0 - cls + ec.P - 1) / ec.P;    // rows of the class
+    const uint32_t n0 = nt * TN;
+    const int64_t s_base64 = (int64_t)i00c + shift[t] + (int64_t)j0 * A;  // i_t0 of the tile's first row
+    const uint32_t s_base = (uint32_t)s_base64;
     const uint32_t n_last = min(n0 + TN, w.N_tau) - 1;
-    const int k_end = min(Kn[n_last] + 1, (int)numAtoms - (int)s_base);
+    const int32_t *Knc = Kn + (size_t)cls * w.N_tau;
+    const int k_end = (int)min((int64_t)Knc[n_last] + 1, (int64_t)numAtoms - s_base64);
     const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
     const float *Xt = X8 + ((size_t)t * xpad + s_base) * 8;  // 32-byte atom records: always 16-byte aligned
-    const float *Wt = W + (size_t)nt * KW * TN;
+    const uint32_t n_tiles = (w.N_tau + TN - 1) / TN;
+    const float *Wt = W + ((size_t)cls * n_tiles + nt) * KW * TN;
+    constexpr int XBYTES = SLIDE ? Cfg::kXBytes1 : Cfg::kXBytes;
 
     const int tid = threadIdx.x;
     const int tm = tid >> 4, tn = tid & 15;
@@ -119,9 +159,9 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
     auto issue = [&](int chunk) {
         const int s = chunk % TCW_EXP_STAGES;
         unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+        mbar_arrive_expect_tx(&full[s], Cfg::kWBytes + XBYTES);
         bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
-        bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, Cfg::kXBytes, &full[s]);
+        bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, XBYTES, &full[s]);
     };
 
     if (tid == 0) {
@@ -150,29 +190,57 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         const int s = chunk % TCW_EXP_STAGES;
         mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
         const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes);
-        const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
-        const float *wrow = Ws + tn * RN;                                                         // + k*TN
+        const float *wrow = Ws + tn * RN;  // + k*TN
 
-        // sliding window of 4 consecutive atoms per channel: value with relative index q
-        // lives in slot q & 3
-        float xr[TCW_NCH][4];
+        if (SLIDE) {
+            const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
+            // sliding window of 4 consecutive atoms per channel: value with relative index q
+            // lives in slot q & 3
+            float xr[TCW_NCH][4];
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const float4 lo = xrow[2 * q], hi = xrow[2 * q + 1];
-            xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
-            xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
-        }
+            for (int q = 0; q < 3; q++) {
+                const float4 lo = xrow[2 * q], hi = xrow[2 * q + 1];
+                xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+                xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+            }
 #pragma unroll 1
-        for (int kk = 0; kk < TCW_EXP_KC; kk += 4) {
+            for (int kk = 0; kk < TCW_EXP_KC; kk += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int k = kk + u;
-                {  // the one new atom of this step: all 7 channels in two 128-bit loads
-                    const float4 lo = xrow[2 * (k + 3)], hi = xrow[2 * (k + 3) + 1];
-                    const int q = (u + 3) & 3;
-                    xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
-                    xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+                for (int u = 0; u < 4; u++) {
+                    const int k = kk + u;
+                    {  // the one new atom of this step: all 7 channels in two 128-bit loads
+                        const float4 lo = xrow[2 * (k + 3)], hi = xrow[2 * (k + 3) + 1];
+                        const int q = (u + 3) & 3;
+                        xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+                        xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+                    }
+                    float2 w1[RN / 2], w2[RN / 2];
+                    if (RN == 4) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                        w1[0] = make_float2(wv.x, wv.y);
+                        w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
+                    } else {
+                        w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                    }
+#pragma unroll
+                    for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+#pragma unroll
+                    for (int c = 0; c < TCW_NCH; c++)
+#pragma unroll
+                        for (int r = 0; r < RM; r++) {
+                            const float xv = xr[c][(u + r) & 3];
+                            const float2 xx = make_float2(xv, xv);
+#pragma unroll
+                            for (int j = 0; j < RN / 2; j++)
+                                acc[c][r][j] = __ffma2_rn(xx, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
+                        }
                 }
+            }
+        } else {
+            // rows A atoms apart: record of (row r, step k) = staged atom (tm*RM + r)*A + k
+            const float4 *xbase = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + (size_t)tm * RM * A * 2;
+#pragma unroll 1
+            for (int k = 0; k < TCW_EXP_KC; k++) {
                 float2 w1[RN / 2], w2[RN / 2];
                 if (RN == 4) {
                     const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
@@ -184,15 +252,17 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
 #pragma unroll
                 for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
 #pragma unroll
-                for (int c = 0; c < TCW_NCH; c++)
+                for (int r = 0; r < RM; r++) {
+                    const float4 lo = xbase[2 * (r * A + k)], hi = xbase[2 * (r * A + k) + 1];
+                    const float xv[TCW_NCH] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z};
 #pragma unroll
-                    for (int r = 0; r < RM; r++) {
-                        const float xv = xr[c][(u + r) & 3];
-                        const float2 xx = make_float2(xv, xv);
+                    for (int c = 0; c < TCW_NCH; c++) {
+                        const float2 xx = make_float2(xv[c], xv[c]);
 #pragma unroll
                         for (int j = 0; j < RN / 2; j++)
                             acc[c][r][j] = __ffma2_rn(xx, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
                     }
+                }
             }
         }
         __syncthreads();  // everyone is done with stage s before it is refilled
@@ -205,11 +275,12 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
     bool degenerate = false;
 #pragma unroll
     for (int r = 0; r < RM; r++) {
-        const uint32_t m = m0 + tm * RM + r;
+        const uint32_t jrow = j0 + tm * RM + r;   // row within the class
+        const uint32_t m = cls + ec.P * jrow;     // row of the map
 #pragma unroll
         for (int j = 0; j < RN; j++) {
             const uint32_t n = n0 + tn * RN + j;
-            if (m < w.N_t0 && n < w.N_tau) {
+            if (jrow < n_rows && n < w.N_tau) {
 #define ACC(c_) ((j & 1) ? acc[c_][r][j >> 1].y : acc[c_][r][j >> 1].x)
                 const float F = fstat_fast(ACC(0), ACC(1), ACC(2), ACC(3), ACC(4), ACC(5), ACC(6));
 #undef ACC
@@ -219,9 +290,11 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
                     best = F;
                     best_flat = flat;
                 }
-                const int K = Kn[n];
-                const uint32_t s_m = i00 + m;
-                if (K >= 0 && (K == 0 || s_m == numAtoms - 1)) degenerate = true;
+                // i_t1 == i_t0 after the reference's clamps: a one-atom window, or a start at / beyond
+                // the last atom
+                const int K = Knc[n];
+                const int64_t s_m = s_base64 + (int64_t)(tm * RM + r) * A;
+                if (K >= 0 && (K == 0 || s_m >= (int64_t)numAtoms - 1)) degenerate = true;
             }
         }
     }

@@ -590,7 +590,7 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
     tile shape; generic otherwise), F_mn stays within tolerance of the oracle, the fused argmax
     equals np.argmax of the GPU's own map in all three reduction modes, and the status matches."""
     rng = np.random.default_rng(20261017)
-    n_fast = 0
+    n_fast = n_exp = n_exp_fast = 0
     for trial in range(160):
         n = int(rng.choice([60, 97, 200, 333, 640, 900]))
         b = synth_atoms(1, n, ("H1", "L1"), seed=1000 + trial, gap_fraction=float(rng.choice([0.0, 0.0, 0.08])))
@@ -614,6 +614,8 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
         Fo = o["F_mn"]
         rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
         n_fast += int(res["path"][0])
+        n_exp += wtype == 2
+        n_exp_fast += (wtype == 2) and int(res["path"][0])
         # two-detector data with gaps has single-detector (ill-conditioned) bins: allow the
         # documented O(eps cond) noise on the few cells near the conditioning cut
         bad = rel > RTOL
@@ -635,6 +637,9 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
         tol = ATOL_LNB if rel.size >= 2000 else 1.0 / 256
         assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=tol), (trial, w, rel.size)
     assert n_fast >= 100, "most of the sweep must exercise the tiled kernels"
+    # exponential window: every t0 step commensurate with TAtom (1, 2, 3 atoms, 1/2, 3/2 atom) is tiled;
+    # 1 trial in 8 draws dt0 = 1801 s, whose rows share no weight table, and wrapped ranges stay generic
+    assert n_exp_fast >= 0.75 * n_exp, (n_exp_fast, n_exp)
 
 
 @pytest.mark.gpu
@@ -947,3 +952,51 @@ def test_rect_persistent_kernel(gpu_persist, oracle, dets, n, gap, tau0, T):
         strict_p = run_gpu(hp, b, w, 0)[0]
         strict_0 = run_gpu(h0, b, w, 0)[0]
         assert np.all(strict_p["status"] == L.E_DEGENERATE) and np.all(strict_0["status"] == L.E_DEGENERATE)
+
+
+# ---- tiled exponential-window kernel beyond dt0 == TAtom (row classes, per-template shifts, clamps) ----
+
+EXP_WIDE_CASES = [
+    # (dt0, t0 offset, t0Band in atoms, tau, dtau, tauBand in atoms, expected tiled)
+    (2 * 1800, 0, 150, 3600, 1800, 40, True),        # rows 2 atoms apart (P = 1, A = 2)
+    (3 * 1800, 700, 150, 3600, 1800, 40, True),      # A = 3, window grid offset by 700 s
+    (4 * 1800, 0, 120, 5000, 2700, 40, True),        # A = 4, dtau != dt0
+    (900, 0, 100, 3600, 1800, 40, True),             # half-atom steps: 2 row classes, A = 1
+    (2700, -900, 150, 3600, 900, 30, True),          # 1.5-atom steps: 2 row classes, A = 3; t0 half an atom early
+    (600, 0, 60, 3600, 1800, 30, True),              # third-atom steps: 3 row classes, A = 1
+    (1800, 0, 230, 3600, 1800, 40, True),            # t0 range running past the data end (clamped starts)
+    (2 * 1800, 0, 260, 3600, 1800, 40, True),        # the same with A = 2
+    (5 * 1800, 0, 150, 3600, 1800, 40, False),       # A = 5 > 4: generic kernels
+    (1801, 0, 100, 3600, 1800, 30, False),           # incommensurate with TAtom: no shared weight table
+]
+
+
+@pytest.mark.parametrize("dt0,off,t0b,tau,dtau,taub,tiled", EXP_WIDE_CASES)
+def test_exp_tiled_row_classes(gpu, oracle, dt0, off, t0b, tau, dtau, taub, tiled):
+    """Exponential window on t0 grids other than one atom per row, templates whose data start on
+    different atoms, and t0 ranges reaching past the data: the tiled kernel (path 1) within RTOL of
+    the oracle, same argmax and degenerate status; exact-exp mode too."""
+    n = 200
+    full = synth_atoms(3, n, ("H1", "L1"), seed=400 + dt0 % 997)
+    # template 1 lost its first 7 atoms in both detectors, template 2 its first 3 in H1 only
+    tpls = [full.template(0), [a[7:] for a in full.template(1)], [full.template(2)[0][3:], full.template(2)[1]]]
+    b = batch_from_detector_lists(tpls, 1800)
+    w = TransientWindowRange(2, 10**9 + 7 * 1800 + off, t0b * 1800, dt0, tau, taub * 1800, dtau)
+    for exact in (0, L.EXP_EXACT):
+        res, F = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE)
+        assert np.all(res["path"] == (1 if tiled else 0)), res["path"]
+        strict = run_gpu(gpu, b, w, exact, fmn=False)[0]
+        for t in range(b.T):
+            o = oracle.compute_map(b.template(t), 1800, w, exact_exp=bool(exact), allow_degenerate=True)
+            Fo = o["F_mn"]
+            rel = np.abs(F[t] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+            assert rel.max() <= RTOL, (t, exact, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+            flat = int(np.argmax(F[t]))
+            assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
+            top2 = np.sort(Fo.ravel())[-2:]
+            if (top2[1] - top2[0]) > 2 * RTOL * top2[1]:
+                assert_records_match(res, t, o, w, check_mp=False)
+            o_strict = oracle.compute_map(b.template(t), 1800, w, exact_exp=bool(exact), want_btsg=False)
+            assert int(strict["status"][t]) == o_strict["status"], (t, exact)
+            assert float(res["lnBtSG"][t]) == pytest.approx(
+                oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=not exact)["lnBtSG"], abs=ATOL_PASS)

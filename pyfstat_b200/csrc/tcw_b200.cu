@@ -350,7 +350,7 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
 #undef RECT_ATTR
 #define EXP_ATTR(CFG)                                                                                          \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, true>,                                      \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem));          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem1));         \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, false>,                                     \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem))
     EXP_ATTR(ExpCfgA);
@@ -1123,7 +1123,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
 #define LAUNCH_EXP(CFG)                                                                                        \
     do {                                                                                                       \
         if (ep.slide)                                                                                          \
-            tcw_exp_map_kernel<CFG, true><<<grid, CFG::kThreads, CFG::kSmem, st>>>(                            \
+            tcw_exp_map_kernel<CFG, true><<<grid, CFG::kThreads, CFG::kSmem1, st>>>(                           \
                 (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
                 (const TplMeta *)h->d_meta.p, (const int32_t *)h->d_shift.p, t_base, w, ep.ec, fmn, p_maxkey,  \
                 p_flags);                                                                                      \

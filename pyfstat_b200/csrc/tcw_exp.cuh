@@ -59,8 +59,10 @@ struct ExpCfg {
     static constexpr int kWBytes = TCW_EXP_KC * kTN * 4;
     static constexpr int kXBytes = kXS * 32;
     static constexpr int kXBytes1 = kXS1 * 32;
-    static constexpr int kStageBytes = kWBytes + kXBytes;
+    static constexpr int kStageBytes = kWBytes + kXBytes;    // rows A atoms apart
+    static constexpr int kStageBytes1 = kWBytes + kXBytes1;  // sliding window (A == 1)
     static constexpr int kSmem = TCW_EXP_STAGES * kStageBytes;
+    static constexpr int kSmem1 = TCW_EXP_STAGES * kStageBytes1;
     static_assert(kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
     static_assert(RM == 4, "the register sliding window is written for 4 rows per thread");
     static_assert(RN == 4 || RN == 2, "weights are fetched as float4 / float2");
@@ -152,13 +154,14 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
     const uint32_t n_tiles = (w.N_tau + TN - 1) / TN;
     const float *Wt = W + ((size_t)cls * n_tiles + nt) * KW * TN;
     constexpr int XBYTES = SLIDE ? Cfg::kXBytes1 : Cfg::kXBytes;
+    constexpr int STAGE = SLIDE ? Cfg::kStageBytes1 : Cfg::kStageBytes;
 
     const int tid = threadIdx.x;
     const int tm = tid >> 4, tn = tid & 15;
 
     auto issue = [&](int chunk) {
         const int s = chunk % TCW_EXP_STAGES;
-        unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes;
+        unsigned char *st = tcw_exp_smem + (size_t)s * STAGE;
         mbar_arrive_expect_tx(&full[s], Cfg::kWBytes + XBYTES);
         bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
         bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, XBYTES, &full[s]);
@@ -189,7 +192,7 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         if (tid == 0 && chunk + TCW_EXP_STAGES - 1 < nchunks) issue(chunk + TCW_EXP_STAGES - 1);
         const int s = chunk % TCW_EXP_STAGES;
         mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
-        const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes);
+        const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * STAGE);
         const float *wrow = Ws + tn * RN;  // + k*TN
 
         if (SLIDE) {

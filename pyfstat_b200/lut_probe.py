@@ -43,30 +43,36 @@ def _bisect_last_true(pred, lo: float, hi: float, iters: int = 200) -> float:
     return lo
 
 
-def measure_exp_lut(f, max_length: int = 1 << 22):
+def measure_exp_lut(f, max_length: int = 1 << 22, tol: float = 0.0):
     """``(xmax, length, table)`` of a nearest-point negative-exponential table ``f(x)``.
 
-    Raises ``ValueError`` if ``f`` does not behave like one (no cut-off, no steps, inconsistent
-    step positions) -- the caller then keeps the configured default.
+    ``tol``: absolute tolerance below which two values of ``f`` count as equal (0 for a direct
+    view of the table; ~1e-12 when ``f`` is recovered through another computation).
+    Raises ``ValueError`` if ``f`` does not behave like a nearest-point table (no cut-off, no
+    steps, inconsistent step positions) -- the caller then keeps the configured default.
     """
+
+    def same(a, b):
+        return abs(a - b) <= tol
+
     f0 = float(f(0.0))
-    if f0 != 1.0:
+    if not same(f0, 1.0):
         raise ValueError(f"f(0) = {f0!r}, expected 1")
     # cut-off: f(x) == 0 for x > xmax
     hi = 1.0
-    while float(f(hi)) != 0.0:
+    while not same(float(f(hi)), 0.0):
         hi *= 2.0
         if hi > 1e6:
             raise ValueError("no cut-off found: f(x) > 0 up to 1e6")
-    xmax = _bisect_last_true(lambda x: float(f(x)) != 0.0, 0.0, hi)
+    xmax = _bisect_last_true(lambda x: not same(float(f(x)), 0.0), 0.0, hi)
     if abs(xmax - round(xmax)) < 1e-9 * max(1.0, xmax):
         xmax = float(round(xmax))
     # first two jumps of the step function: x = dx/2 and 3 dx/2
-    j1 = _bisect_last_true(lambda x: float(f(x)) == f0, 0.0, xmax)
+    j1 = _bisect_last_true(lambda x: same(float(f(x)), f0), 0.0, xmax)
     f1 = float(f(math.nextafter(j1, math.inf)))
-    if f1 == f0 or f1 == 0.0:
+    if same(f1, f0) or same(f1, 0.0):
         raise ValueError("no first step found")
-    j2 = _bisect_last_true(lambda x: float(f(x)) == f1, math.nextafter(j1, math.inf), xmax)
+    j2 = _bisect_last_true(lambda x: same(float(f(x)), f1), math.nextafter(j1, math.inf), xmax)
     dx = j2 - j1
     if not (dx > 0) or abs(2.0 * j1 - dx) > 1e-6 * dx:
         raise ValueError(f"step positions {j1!r}, {j2!r} are not dx/2, 3dx/2: not a nearest-point table")
@@ -79,24 +85,49 @@ def measure_exp_lut(f, max_length: int = 1 << 22):
     for i in (1, 2, length // 3, length // 2, length - 1):
         for off in (-0.49, 0.0, 0.49):
             x = (i + off) * dx
-            if 0.0 <= x <= xmax and float(f(x)) != table[i]:
+            if 0.0 <= x <= xmax and not same(float(f(x)), table[i]):
                 raise ValueError(f"f({x!r}) != table[{i}]: not a nearest-point table with dx = {dx!r}")
     return xmax, length, table
 
 
-def probe_lalpulsar():
-    """``(xmax, length, table)`` measured from ``lalpulsar.FastNegExp`` (the SWIG name of
-    ``XLALFastNegExp``), or ``None`` when lalpulsar is not importable / does not export it."""
-    try:
-        import lalpulsar  # noqa: PLC0415
-    except Exception:  # noqa: BLE001 -- absent in the build container
-        return None
+def neg_exp_through_bstat(lalpulsar):
+    """``f(x) = XLALFastNegExp(x)`` recovered WITHOUT a direct binding: lalpulsar's own
+    ``ComputeTransientBstat`` (the call of the reference's ``lal`` path, tcw:578-580) on a 1 x 2 map
+    ``F_mn = [[0, -x]]`` returns ``ln(70/2) + ln(1 + FastNegExp(x))``.  Values are good to ~1e-15
+    absolute, enough to find the cut-off and the step positions; the table entries themselves are
+    then taken as ``exp(-i dx)`` (canonical)."""
+    fm = lalpulsar.CreateTransientFstatMap(1, 2)
+    wr = lalpulsar.transientWindowRange_t()
+    wr.type = lalpulsar.TRANSIENT_RECTANGULAR
+    wr.t0, wr.t0Band, wr.dt0 = 0, 0, 1
+    wr.tau, wr.tauBand, wr.dtau = 1, 1, 1
+
+    def f(x):
+        fm.F_mn.data[0, 0] = 0.0
+        fm.F_mn.data[0, 1] = -float(x)
+        fm.maxF = 0.0
+        return math.expm1(float(lalpulsar.ComputeTransientBstat(wr, fm)) - math.log(35.0))
+
+    return f
+
+
+def probe_lalpulsar(module=None):
+    """``(xmax, length, table)`` measured from lalpulsar: through ``lalpulsar.FastNegExp`` (the SWIG
+    name of ``XLALFastNegExp``) when it is exported, else through ``ComputeTransientBstat``
+    (:func:`neg_exp_through_bstat`; entries then canonical, ``table`` is ``None``).  ``None`` when
+    lalpulsar is not importable or neither route works."""
+    lalpulsar = module
+    if lalpulsar is None:
+        try:
+            import lalpulsar  # noqa: PLC0415
+        except Exception:  # noqa: BLE001 -- absent in the build container
+            return None
     f = getattr(lalpulsar, "FastNegExp", None)
-    if f is None:
-        logger.warning("lalpulsar does not export FastNegExp: keeping the configured exp-table geometry")
-        return None
     try:
-        return measure_exp_lut(f)
+        if f is not None:
+            return measure_exp_lut(f)
+        xmax, length, _ = measure_exp_lut(neg_exp_through_bstat(lalpulsar), tol=1e-12)
+        return xmax, length, None
     except Exception as e:  # noqa: BLE001
         logger.warning("could not measure lalpulsar's FastNegExp table (%s): keeping the configured geometry", e)
         return None

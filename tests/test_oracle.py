@@ -289,3 +289,31 @@ def test_lut_vs_exact_matters_at_1e4(oracle):
     exact = oracle.compute_map(b.template(0), 1800, w, want_btsg=False, exact_exp=True)["F_mn"]
     rel = np.abs(lut - exact) / np.abs(exact)
     assert 1e-4 < np.median(rel) < 2e-2
+
+
+def test_lut_probe_through_bstat_route(oracle, explut):
+    """When lalpulsar does not export FastNegExp, the table geometry is recovered from its
+    ComputeTransientBstat on a 1 x 2 map (lut_probe.neg_exp_through_bstat) -- exercised here with a
+    stand-in module whose Bstat is the oracle's restatement."""
+    import types
+
+    from pyfstat_b200 import lut_probe
+
+    class Map:
+        def __init__(self):
+            self.F_mn = types.SimpleNamespace(data=np.zeros((1, 2)))
+            self.maxF = 0.0
+
+    win = TransientWindowRange(1, 0, 0, 1, 1, 1, 1)
+    fake = types.SimpleNamespace(
+        TRANSIENT_RECTANGULAR=1,
+        CreateTransientFstatMap=lambda n_t0, n_tau: Map(),
+        transientWindowRange_t=lambda: types.SimpleNamespace(),
+        ComputeTransientBstat=lambda wr, fm: oracle.bstat(fm.F_mn.data, fm.maxF, win, use_lut=True)["lnBtSG"],
+    )
+    xmax, length, table = lut_probe.probe_lalpulsar(fake)
+    assert (xmax, length) == explut and table is None
+    fake.FastNegExp = oracle.fast_neg_exp  # the direct route wins when it exists, and returns the entries
+    xmax, length, table = lut_probe.probe_lalpulsar(fake)
+    assert (xmax, length) == explut and np.array_equal(table, oracle.exp_lut())
+    assert lut_probe.probe_lalpulsar(types.SimpleNamespace()) is None  # neither route: keep the default

@@ -9,7 +9,9 @@ DESIGN.md's "parity unpinned" into pinned:
 * ``b200`` vs ``lal`` through the reference's dispatcher on identical atoms: F_mn within 1e-4
   relative, maxF / t0_ML / tau_ML equal (argmax identical except documented near-ties),
   lnBtSG within 1e-4 absolute, t0_MP / tau_MP equal -- rect and exp, one and two detectors;
-* the recalled constants of Appendix F: XLALFastNegExp's table (20 / 2000, nearest point),
+* the constants of Appendix F: XLALFastNegExp's table geometry is MEASURED from lalpulsar
+  (pyfstat_b200.lut_probe) and must be what the registered backend's handle emulates -- the test
+  also prints which of the two recollections on file (20 / 5120, 20 / 2000) is the true one;
   sizeof(FstatAtom) == 32 (the one-block SWIG ingest must verify and be used), the enum values.
 """
 
@@ -61,6 +63,23 @@ def registered():
     feats, _ = tcw.init_transient_fstat_map_features("b200")
     yield feats
     pyfstat_b200.unregister(tcw)
+
+
+def test_exp_lut_geometry_measured_from_lalpulsar(registered):
+    """The table the backend emulates is the one lalpulsar uses: measured, not recalled."""
+    from pyfstat_b200 import backend, lut_probe
+
+    probed = lut_probe.probe_lalpulsar()
+    assert probed is not None, "neither lalpulsar.FastNegExp nor the ComputeTransientBstat route worked"
+    xmax, length, table = probed
+    print(f"lalpulsar XLALFastNegExp table: xmax = {xmax}, {length} steps (1/dx = {length / xmax})")
+    assert (xmax, length) in ((20.0, 5120), (20.0, 2000)), "a third geometry: update DESIGN.md L1"
+    if table is not None:
+        dx = xmax / length
+        assert np.allclose(table, np.exp(-dx * np.arange(length + 1)), rtol=1e-14, atol=0)
+    h = backend.get_handle(-1)
+    assert h.get_exp_lut()[:2] == (xmax, length), "the handle must have been configured from the probe"
+    assert backend.exp_lut_geometry()[3].startswith("measured")
 
 
 def test_enums_and_struct_layout():

@@ -349,6 +349,8 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     RECT_ATTR(1, false);
 #undef RECT_ATTR
 #define EXP_ATTR(CFG)                                                                                          \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_canon_kernel<CFG>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem1));         \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, true>,                                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem1));         \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, false>,                                     \
@@ -487,7 +489,11 @@ static int upload_common(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n
     h->Nmax = Nmax;
     h->uniform = uniform;
     // zero padding: an exp tile reads up to (TM - 1) * A + KC + 8 atoms past the last needed one (A <= 4)
+#ifdef TCW_XPAD_OLD  // development: the round-1 padding (valid for A == 1 only)
+    h->xpad = ((Nmax + 64 + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
+#else
     h->xpad = ((Nmax + 64 /* max exp tile rows */ * TCW_EXP_AMAX + 2 * TCW_EXP_KC + 8) + 3u) & ~3u;
+#endif
     h->ppad = ((Nmax + 1 + 8) + 1u) & ~1u;
     const size_t n_vec = (size_t)T * numDet;
     int rc;
@@ -539,6 +545,7 @@ static bool no_wrap(const MapWindow &w, uint32_t ef, uint32_t slack_n, const Tpl
 struct ExpPlan {
     bool ok = false;
     bool slide = true;   // A == 1: register sliding-window kernel
+    bool canon = false;  // one class, A == 1, no shifts, no start beyond the data end: round 1's kernel
     uint32_t KW = 0;
     ExpClasses ec = {};
     int32_t delta[TCW_EXP_PMAX] = {0, 0, 0, 0};
@@ -623,6 +630,9 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
     const uint64_t n_tiles = (w.N_tau + TN - 1) / TN;
     if ((uint64_t)P * n_tiles * p.KW * TN * 4ull > (8ull << 30)) return p;  // table too large
+    p.canon = P == 1 && A64 == 1;
+    for (int t = 0; t < h->T && p.canon; t++)
+        p.canon = p.shift[t] == 0 && (int64_t)p.ec.i00[0] + (int64_t)w.N_t0 - 1 <= (int64_t)h->meta[t].numAtoms - 1;
     p.ok = true;
     return p;
 }
@@ -1122,7 +1132,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, ep.ec.ybeg[TCW_EXP_PMAX], cnt);
 #define LAUNCH_EXP(CFG)                                                                                        \
     do {                                                                                                       \
-        if (ep.slide)                                                                                          \
+        if (ep.canon)                                                                                          \
+            tcw_exp_map_canon_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem1, st>>>(                           \
+                (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
+                (const TplMeta *)h->d_meta.p, t_base, w, ep.ec.i00[0], fmn, p_maxkey, p_flags);                \
+        else if (ep.slide)                                                                                     \
             tcw_exp_map_kernel<CFG, true><<<grid, CFG::kThreads, CFG::kSmem1, st>>>(                           \
                 (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
                 (const TplMeta *)h->d_meta.p, (const int32_t *)h->d_shift.p, t_base, w, ep.ec, fmn, p_maxkey,  \

@@ -111,6 +111,153 @@ __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__res
     }
 }
 
+// The canonical case -- one row class, rows one atom apart, every template starting on the same
+// atom, no start beyond the data end (dt0 == TAtom grids: every BASELINE config) -- keeps round 1's
+// kernel VERBATIM: the generalised kernel below has the same main loop (224 FFMA2, 18 LDS.128, 8 FMUL2
+// per 4 k-steps), but nvcc schedules it differently around the extra tile geometry (131 instead of 146
+// operand-reuse hints) and it measures 2.4 % slower (42.22 vs 41.20 ms per 128 x 30-d maps,
+// 79.7 vs 77.9 ms per 4 x 120-d maps) whatever is done to the prologue / epilogue.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, (Cfg::kThreads == 256 ? (Cfg::kRN == 4 ? 1 : 2) : 3))
+tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__restrict__ W,
+                   const int32_t *__restrict__ Kn, uint32_t KW, const TplMeta *__restrict__ meta,
+                   int t_base, MapWindow w, uint32_t i00, float *__restrict__ Fmn,
+                   unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+    constexpr int TM = Cfg::kTM, TN = Cfg::kTN, RM = Cfg::kRM, RN = Cfg::kRN, XS = Cfg::kXS1;
+    constexpr int NT = Cfg::kThreads;
+    extern __shared__ __align__(128) unsigned char tcw_exp_smem[];
+    __shared__ __align__(8) uint64_t full[TCW_EXP_STAGES];
+    __shared__ unsigned long long red[NT / 32];
+
+    const int tz = blockIdx.z;
+    const int t = t_base + tz;
+    const uint32_t numAtoms = meta[t].numAtoms;
+    const uint32_t nt = blockIdx.x, mt = blockIdx.y;
+    const uint32_t m0 = mt * TM, n0 = nt * TN;
+    const uint32_t s_base = i00 + m0;  // i_t0 of the tile's first row (dt0 == TAtom)
+    const uint32_t n_last = min(n0 + TN, w.N_tau) - 1;
+    const int k_end = min(Kn[n_last] + 1, (int)numAtoms - (int)s_base);
+    const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
+    const float *Xt = X8 + ((size_t)t * xpad + s_base) * 8;  // 32-byte atom records: always 16-byte aligned
+    const float *Wt = W + (size_t)nt * KW * TN;
+
+    const int tid = threadIdx.x;
+    const int tm = tid >> 4, tn = tid & 15;
+
+    auto issue = [&](int chunk) {
+        const int s = chunk % TCW_EXP_STAGES;
+        unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes1;
+        mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes1);
+        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
+        bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, Cfg::kXBytes1, &full[s]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TCW_EXP_STAGES; s++) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < TCW_EXP_STAGES - 1 && c < nchunks; c++) issue(c);
+    }
+
+    // accumulators are pairs of adjacent tau columns: one FFMA2 (fma.rn.f32x2, Blackwell packed
+    // FP32) updates two cells, halving the issue slots of the inner loop
+    float2 acc[TCW_NCH][RM][RN / 2];
+#pragma unroll
+    for (int c = 0; c < TCW_NCH; c++)
+#pragma unroll
+        for (int r = 0; r < RM; r++)
+#pragma unroll
+            for (int j = 0; j < RN / 2; j++) acc[c][r][j] = make_float2(0.0f, 0.0f);
+
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        // refill the stage consumed in the previous iteration (all threads passed its sync)
+        if (tid == 0 && chunk + TCW_EXP_STAGES - 1 < nchunks) issue(chunk + TCW_EXP_STAGES - 1);
+        const int s = chunk % TCW_EXP_STAGES;
+        mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
+        const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes1);
+        const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
+        const float *wrow = Ws + tn * RN;                                                         // + k*TN
+
+        // sliding window of 4 consecutive atoms per channel: value with relative index q
+        // lives in slot q & 3
+        float xr[TCW_NCH][4];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const float4 lo = xrow[2 * q], hi = xrow[2 * q + 1];
+            xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+            xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+        }
+#pragma unroll 1
+        for (int kk = 0; kk < TCW_EXP_KC; kk += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int k = kk + u;
+                {  // the one new atom of this step: all 7 channels in two 128-bit loads
+                    const float4 lo = xrow[2 * (k + 3)], hi = xrow[2 * (k + 3) + 1];
+                    const int q = (u + 3) & 3;
+                    xr[0][q] = lo.x; xr[1][q] = lo.y; xr[2][q] = lo.z; xr[3][q] = lo.w;
+                    xr[4][q] = hi.x; xr[5][q] = hi.y; xr[6][q] = hi.z;
+                }
+                float2 w1[RN / 2], w2[RN / 2];
+                if (RN == 4) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                    w1[0] = make_float2(wv.x, wv.y);
+                    w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
+                } else {
+                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                }
+#pragma unroll
+                for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++)
+#pragma unroll
+                    for (int r = 0; r < RM; r++) {
+                        const float xv = xr[c][(u + r) & 3];
+                        const float2 xx = make_float2(xv, xv);
+#pragma unroll
+                        for (int j = 0; j < RN / 2; j++)
+                            acc[c][r][j] = __ffma2_rn(xx, c < 3 ? w2[j] : w1[j], acc[c][r][j]);
+                    }
+            }
+        }
+        __syncthreads();  // everyone is done with stage s before it is refilled
+    }
+
+    // ---- fused epilogue: F, optional store, max/argmax, degenerate flag ----
+    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
+    float best = -1.0f;
+    uint32_t best_flat = 0;
+    bool degenerate = false;
+#pragma unroll
+    for (int r = 0; r < RM; r++) {
+        const uint32_t m = m0 + tm * RM + r;
+#pragma unroll
+        for (int j = 0; j < RN; j++) {
+            const uint32_t n = n0 + tn * RN + j;
+            if (m < w.N_t0 && n < w.N_tau) {
+#define ACC(c_) ((j & 1) ? acc[c_][r][j >> 1].y : acc[c_][r][j >> 1].x)
+                const float F = fstat_fast(ACC(0), ACC(1), ACC(2), ACC(3), ACC(4), ACC(5), ACC(6));
+#undef ACC
+                const uint32_t flat = m * w.N_tau + n;
+                if (Ft) Ft[(size_t)m * w.pitch + n] = F;
+                if (F > best) {
+                    best = F;
+                    best_flat = flat;
+                }
+                const int K = Kn[n];
+                const uint32_t s_m = i00 + m;
+                if (K >= 0 && (K == 0 || s_m == numAtoms - 1)) degenerate = true;
+            }
+        }
+    }
+    if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
+    const unsigned long long key = best > -1.0f ? pack_key(best, best_flat) : 0ull;
+    block_atomic_max_key<NT / 32>(key, &maxkey[t], red);
+}
+
 // SLIDE = true: A == 1, the rows of a thread are consecutive atoms -- their 4 atoms per channel form
 // a register sliding window (one new 32-byte record per k step).  SLIDE = false: rows are A <= 4
 // atoms apart; every row fetches its own record per step (2 broadcast LDS.128 each).

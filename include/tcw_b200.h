@@ -214,6 +214,10 @@ int tcw_upload_atoms(tcw_handle *h, const tcw_atom *atoms, const uint32_t *n_ato
 int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags);
 /* Waits for the stream, copies the T records to the host. */
 int tcw_fetch_results(tcw_handle *h, tcw_result *results);
+/* Device address of the T result records of the last map (valid until the next map / upload call on
+ * this handle; final once tcw_fetch_results / tcw_map_batch / tcw_wait has returned).  Lets a
+ * multi-GPU driver hand the records to a collective (NCCL all_gather) without a host round trip. */
+int tcw_results_device(tcw_handle *h, void **ptr, uint64_t *n_records);
 /* Copies F_mn of resident template t (after a TCW_WANT_FMN run) to the host. */
 int tcw_fetch_fmn(tcw_handle *h, int t, float *F_mn_out);
 /* Copies the merged (binned) atoms of resident template t as 7 float32 channel arrays of

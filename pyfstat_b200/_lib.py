@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = (
     "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
     "tcw_host_alloc",
     "tcw_host_free", "tcw_cell_index_range", "tcw_set_exp_lut", "tcw_get_exp_lut",
-    "tcw_device_count", "tcw_device_name_of",
+    "tcw_device_count", "tcw_device_name_of", "tcw_results_device",
 )
 
 
@@ -132,6 +132,7 @@ def load_library(build_if_missing: bool = True):
     L.tcw_wait.argtypes = [vp, vp, vp]
     L.tcw_fetch_results.argtypes = [vp, vp]
     L.tcw_fetch_fmn.argtypes = [vp, i32, vp]
+    L.tcw_results_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.tcw_fetch_merged.argtypes = [vp, i32, vp, u32]
     L.tcw_synchronize.argtypes = [vp]
     L.tcw_timer_start.argtypes = [vp]
@@ -204,6 +205,14 @@ class PinnedBuffer:
         ptr, self._ptr = getattr(self, "_ptr", None), None
         if ptr and _lib is not None:
             _lib.tcw_host_free(ptr)
+
+
+class DeviceBytes:
+    """A span of device memory for zero-copy hand-over to torch (``__cuda_array_interface__`` v2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+        self.nbytes = nbytes
 
 
 class Handle:
@@ -381,6 +390,14 @@ class Handle:
         results = np.zeros(self._T, dtype=RESULT_DTYPE)
         self._check(self.L.tcw_fetch_results(self._h, results.ctypes.data), not raise_on_degenerate)
         return results
+
+    def results_device(self):
+        """The last map's result records where they lie in device memory, as an object exposing
+        ``__cuda_array_interface__`` (uint8, ``T * itemsize`` bytes): ``torch.as_tensor(view, device="cuda")``
+        wraps it without a copy.  Valid until the next map / upload call on this handle."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.L.tcw_results_device(self._h, C.byref(p), C.byref(n)))
+        return DeviceBytes(p.value, int(n.value) * RESULT_DTYPE.itemsize)
 
     def fetch_fmn(self, t: int, N_t0: int, N_tau: int) -> np.ndarray:
         F = np.empty((N_t0, N_tau), dtype=np.float32)

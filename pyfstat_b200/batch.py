@@ -76,9 +76,17 @@ def shard_range(T: int, rank: int, world_size: int):
     return (rank * T) // world_size, ((rank + 1) * T) // world_size
 
 
-def gather_records(local: np.ndarray, T: int, group=None) -> np.ndarray:
+_gather_cache = {}
+
+
+def gather_records(local: np.ndarray, T: int, group=None, device_src=None) -> np.ndarray:
     """``all_gather`` of per-template records over the ranks of ``group``; every rank returns
-    the ``T`` records in template order.  Falls back to identity without a process group."""
+    the ``T`` records in template order.  Falls back to identity without a process group.
+
+    One collective per call on preallocated buffers.  With NCCL and ``device_src`` (the records
+    where the kernels left them in device memory, ``Handle.results_device()``) the shard goes from
+    device memory straight into the collective -- no host-to-device hop; the gathered records come
+    back in one device-to-host copy."""
     import torch
     import torch.distributed as dist
 
@@ -95,15 +103,28 @@ def gather_records(local: np.ndarray, T: int, group=None) -> np.ndarray:
     max_shard = max(shard_range(T, r, world)[1] - shard_range(T, r, world)[0] for r in range(world))
     use_cuda = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
-    send = torch.zeros(max_shard * itemsize, dtype=torch.uint8)
-    if len(local):
-        send[: len(local) * itemsize] = torch.from_numpy(
-            np.ascontiguousarray(local).view(np.uint8).reshape(-1).copy()
-        )
-    send = send.to(dev)
-    recv = torch.empty(world * max_shard * itemsize, dtype=torch.uint8, device=dev)
+    key = (world, max_shard * itemsize, str(dev))
+    bufs = _gather_cache.get(key)
+    if bufs is None:
+        send = torch.zeros(max_shard * itemsize, dtype=torch.uint8, device=dev)
+        recv = torch.empty(world * max_shard * itemsize, dtype=torch.uint8, device=dev)
+        stage = torch.zeros(max_shard * itemsize, dtype=torch.uint8, pin_memory=use_cuda)
+        host = torch.empty(world * max_shard * itemsize, dtype=torch.uint8, pin_memory=use_cuda)
+        bufs = _gather_cache[key] = (send, recv, stage, host)
+    send, recv, stage, host = bufs
+    nb = len(local) * itemsize
+    if use_cuda and device_src is not None and device_src.nbytes >= nb:
+        if nb:
+            send[:nb].copy_(torch.as_tensor(device_src, device=dev)[:nb], non_blocking=True)  # device to device
+    else:
+        if nb:
+            stage[:nb] = torch.from_numpy(np.ascontiguousarray(local).view(np.uint8).reshape(-1))
+        send.copy_(stage, non_blocking=use_cuda)
     dist.all_gather_into_tensor(recv, send, group=group)
-    raw = recv.cpu().numpy().reshape(world, max_shard * itemsize)
+    host.copy_(recv, non_blocking=use_cuda)
+    if use_cuda:
+        torch.cuda.current_stream().synchronize()
+    raw = host.numpy().reshape(world, max_shard * itemsize)
     out = np.zeros(T, dtype=local.dtype)
     for r in range(world):
         a, b = shard_range(T, r, world)
@@ -129,6 +150,7 @@ def map_sharded(make_shard, T: int, window, BtSG: bool = False, *, group=None, c
     else:
         rank, world = 0, 1
     lo, hi = shard_range(T, rank, world)
+    default_compute = compute is None
     if compute is None:
         def compute(batch):  # noqa: E306
             return map_batch(batch, window, BtSG, device=device, raise_on_degenerate=False)[0]
@@ -138,4 +160,7 @@ def map_sharded(make_shard, T: int, window, BtSG: bool = False, *, group=None, c
         b = min(a + step, hi)
         parts.append(np.asarray(compute(make_shard(a, b))))
     local = np.concatenate(parts) if parts else np.zeros(0, dtype=_lib.RESULT_DTYPE)
-    return gather_records(local, T, group)
+    # one launch computed the whole shard: its records still sit in device memory, hand them to the
+    # collective from there
+    device_src = get_handle(device).results_device() if (default_compute and len(parts) == 1 and world > 1) else None
+    return gather_records(local, T, group, device_src=device_src)

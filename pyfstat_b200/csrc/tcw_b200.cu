@@ -1262,6 +1262,14 @@ extern "C" int tcw_fetch_results(tcw_handle *h, tcw_result *results) {
     return worst;
 }
 
+extern "C" int tcw_results_device(tcw_handle *h, void **ptr, uint64_t *n_records) {
+    if (!h || !ptr || !n_records) return TCW_E_INVALID;
+    if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_results_device: no map has been run");
+    *ptr = h->d_results.p;
+    *n_records = (uint64_t)h->T;
+    return TCW_OK;
+}
+
 extern "C" int tcw_fetch_fmn(tcw_handle *h, int t, float *out) {
     if (!h || !out) return TCW_E_INVALID;
     if (!h->have_fmn) return fail(h, TCW_E_STATE, "tcw_fetch_fmn: last map did not materialise F_mn");

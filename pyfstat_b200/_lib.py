@@ -211,7 +211,7 @@ class DeviceBytes:
     """A span of device memory for zero-copy hand-over to torch (``__cuda_array_interface__`` v2)."""
 
     def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 2}
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
         self.nbytes = nbytes
 
 

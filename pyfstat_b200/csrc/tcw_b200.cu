@@ -350,7 +350,7 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
 #undef RECT_ATTR
 #define EXP_ATTR(CFG)                                                                                          \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_canon_kernel<CFG>,                                      \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem1));         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmemC));         \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, true>,                                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kSmem1));         \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_map_kernel<CFG, false>,                                     \
@@ -629,7 +629,7 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     for (auto &K : p.Kn) K = (int32_t)std::min<int64_t>(K, Kmax);
     p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
     const uint64_t n_tiles = (w.N_tau + TN - 1) / TN;
-    if ((uint64_t)P * n_tiles * p.KW * TN * 4ull > (8ull << 30)) return p;  // table too large
+    if ((uint64_t)P * n_tiles * p.KW * TN * 4ull * TCW_EXP_WP > (8ull << 30)) return p;  // table too large
     p.canon = P == 1 && A64 == 1;
     for (int t = 0; t < h->T && p.canon; t++)
         p.canon = p.shift[t] == 0 && (int64_t)p.ec.i00[0] + (int64_t)w.N_t0 - 1 <= (int64_t)h->meta[t].numAtoms - 1;
@@ -983,8 +983,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
-            const size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;
-            if ((rc = ensure(h, h->d_W, total * sizeof(float)))) return rc;
+            const size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
+            if ((rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
             if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
             h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -1133,7 +1133,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
 #define LAUNCH_EXP(CFG)                                                                                        \
     do {                                                                                                       \
         if (ep.canon)                                                                                          \
-            tcw_exp_map_canon_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmem1, st>>>(                           \
+            tcw_exp_map_canon_kernel<CFG><<<grid, CFG::kThreads, CFG::kSmemC, st>>>(                          \
                 (const float *)h->d_X8.p, h->xpad, (const float *)h->d_W.p, (const int32_t *)h->d_Kn.p, ep.KW, \
                 (const TplMeta *)h->d_meta.p, t_base, w, ep.ec.i00[0], fmn, p_maxkey, p_flags);                \
         else if (ep.slide)                                                                                     \

@@ -41,6 +41,28 @@
 #ifndef TCW_EXP_STAGES
 #define TCW_EXP_STAGES 3    // measured: 2, 3 and 4 stages give the same time (41.2 ms / 128 30-d maps): staging is fully hidden
 #endif
+// canonical kernel: stages of its ring and how many chunks ahead the refills run.  Measured (B200,
+// 128 x 30-d / 4 x 120-d maps): barrier per chunk + w^2 by FMUL2 41.21 / 77.86 ms; decoupled ring alone
+// 43.81 / 82.66; w^2 plane alone 40.96 / 76.11; both 39.20 / 73.96 ms (the default).
+#ifndef TCW_EXP_NO_DECOUPLE
+#define TCW_EXP_DECOUPLE 1
+#endif
+#ifndef TCW_EXP_NO_W2TAB
+#define TCW_EXP_W2TAB 1
+#endif
+#ifdef TCW_EXP_DECOUPLE
+#define TCW_EXP_CSTAGES 4
+#define TCW_EXP_PREFETCH 2
+#else
+#define TCW_EXP_CSTAGES TCW_EXP_STAGES
+#define TCW_EXP_PREFETCH (TCW_EXP_STAGES - 1)
+#endif
+// weight planes per table row: 1 = w only (w^2 by one FMUL2 per column pair and k step), 2 = [w | w^2]
+#ifdef TCW_EXP_W2TAB
+#define TCW_EXP_WP 2
+#else
+#define TCW_EXP_WP 1
+#endif
 #define TCW_EXP_TNT 16     // threads along tau per CTA (fixed); a warp = 2 (t0) x 16 (tau) threads
 #define TCW_EXP_AMAX 4     // max atoms between consecutive rows of a row class
 #define TCW_EXP_PMAX 4     // max row classes
@@ -56,13 +78,14 @@ struct ExpCfg {
     // staged atoms (32-byte records: 7 channels + pad): rows of a class are A atoms apart
     static constexpr int kXS1 = kTM + TCW_EXP_KC + 4;                             // A == 1
     static constexpr int kXS = (kTM - 1) * TCW_EXP_AMAX + 1 + TCW_EXP_KC + 4 + 3;  // A <= AMAX (multiple of 4)
-    static constexpr int kWBytes = TCW_EXP_KC * kTN * 4;
+    static constexpr int kWBytes = TCW_EXP_KC * kTN * 4 * TCW_EXP_WP;
     static constexpr int kXBytes = kXS * 32;
     static constexpr int kXBytes1 = kXS1 * 32;
     static constexpr int kStageBytes = kWBytes + kXBytes;    // rows A atoms apart
     static constexpr int kStageBytes1 = kWBytes + kXBytes1;  // sliding window (A == 1)
     static constexpr int kSmem = TCW_EXP_STAGES * kStageBytes;
     static constexpr int kSmem1 = TCW_EXP_STAGES * kStageBytes1;
+    static constexpr int kSmemC = TCW_EXP_CSTAGES * kStageBytes1;  // canonical kernel
     static_assert(kWBytes % 16 == 0, "bulk copies need 16-byte multiples");
     static_assert(RM == 4, "the register sliding window is written for 4 rows per thread");
     static_assert(RN == 4 || RN == 2, "weights are fetched as float4 / float2");
@@ -107,7 +130,10 @@ __global__ void tcw_exp_table_kernel(float *__restrict__ W, const int32_t *__res
                 wv = (float)(exact ? exp(-x) : fast_neg_exp_lut(x, lut));
             }
         }
-        W[idx0] = wv;
+        // row layout of the table: [TN values of w][TN values of w^2] when TCW_EXP_WP == 2
+        const size_t row = idx0 / eg.TN;
+        W[row * (eg.TN * TCW_EXP_WP) + j] = wv;
+        if (TCW_EXP_WP == 2) W[row * (eg.TN * TCW_EXP_WP) + eg.TN + j] = __fmul_rn(wv, wv);
     }
 }
 
@@ -126,7 +152,10 @@ tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const floa
     constexpr int TM = Cfg::kTM, TN = Cfg::kTN, RM = Cfg::kRM, RN = Cfg::kRN, XS = Cfg::kXS1;
     constexpr int NT = Cfg::kThreads;
     extern __shared__ __align__(128) unsigned char tcw_exp_smem[];
-    __shared__ __align__(8) uint64_t full[TCW_EXP_STAGES];
+    __shared__ __align__(8) uint64_t full[TCW_EXP_CSTAGES];
+#ifdef TCW_EXP_DECOUPLE
+    __shared__ __align__(8) uint64_t empty[TCW_EXP_CSTAGES];
+#endif
     __shared__ unsigned long long red[NT / 32];
 
     const int tz = blockIdx.z;
@@ -139,27 +168,30 @@ tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const floa
     const int k_end = min(Kn[n_last] + 1, (int)numAtoms - (int)s_base);
     const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
     const float *Xt = X8 + ((size_t)t * xpad + s_base) * 8;  // 32-byte atom records: always 16-byte aligned
-    const float *Wt = W + (size_t)nt * KW * TN;
+    const float *Wt = W + (size_t)nt * KW * TN * TCW_EXP_WP;
 
     const int tid = threadIdx.x;
     const int tm = tid >> 4, tn = tid & 15;
 
     auto issue = [&](int chunk) {
-        const int s = chunk % TCW_EXP_STAGES;
+        const int s = chunk % TCW_EXP_CSTAGES;
         unsigned char *st = tcw_exp_smem + (size_t)s * Cfg::kStageBytes1;
         mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes1);
-        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
+        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN * TCW_EXP_WP, Cfg::kWBytes, &full[s]);
         bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, Cfg::kXBytes1, &full[s]);
     };
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < TCW_EXP_STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < TCW_EXP_CSTAGES; s++) mbar_init(&full[s], 1);
+#ifdef TCW_EXP_DECOUPLE
+        for (int s = 0; s < TCW_EXP_CSTAGES; s++) mbar_init(&empty[s], NT / 32);
+#endif
         mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
-        for (int c = 0; c < TCW_EXP_STAGES - 1 && c < nchunks; c++) issue(c);
+        for (int c = 0; c < TCW_EXP_PREFETCH && c < nchunks; c++) issue(c);
     }
 
     // accumulators are pairs of adjacent tau columns: one FFMA2 (fma.rn.f32x2, Blackwell packed
@@ -173,12 +205,24 @@ tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const floa
             for (int j = 0; j < RN / 2; j++) acc[c][r][j] = make_float2(0.0f, 0.0f);
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
+#ifdef TCW_EXP_DECOUPLE
+        // no CTA-wide barrier per chunk: every warp signals `empty` when it is done with a stage, and
+        // the refill goes into the stage consumed TWO iterations ago (its `empty` phase has normally
+        // completed long before), so the warps of a CTA may drift apart by a chunk
+        if (tid == 0 && chunk + TCW_EXP_PREFETCH < nchunks) {
+            const int cn = chunk + TCW_EXP_PREFETCH;  // uses the stage of chunk cn - CSTAGES
+            if (cn >= TCW_EXP_CSTAGES)
+                mbar_wait(&empty[cn % TCW_EXP_CSTAGES], (uint32_t)(((cn / TCW_EXP_CSTAGES) - 1) & 1));
+            issue(cn);
+        }
+#else
         // refill the stage consumed in the previous iteration (all threads passed its sync)
-        if (tid == 0 && chunk + TCW_EXP_STAGES - 1 < nchunks) issue(chunk + TCW_EXP_STAGES - 1);
-        const int s = chunk % TCW_EXP_STAGES;
-        mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_STAGES) & 1));
+        if (tid == 0 && chunk + TCW_EXP_PREFETCH < nchunks) issue(chunk + TCW_EXP_PREFETCH);
+#endif
+        const int s = chunk % TCW_EXP_CSTAGES;
+        mbar_wait(&full[s], (uint32_t)((chunk / TCW_EXP_CSTAGES) & 1));
         const float *Ws = reinterpret_cast<const float *>(tcw_exp_smem + (size_t)s * Cfg::kStageBytes1);
-        const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
+        const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN * TCW_EXP_WP) + tm * RM * 2;  // + 2*(k + r)
         const float *wrow = Ws + tn * RN;                                                         // + k*TN
 
         // sliding window of 4 consecutive atoms per channel: value with relative index q
@@ -203,14 +247,22 @@ tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const floa
                 }
                 float2 w1[RN / 2], w2[RN / 2];
                 if (RN == 4) {
-                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP);
                     w1[0] = make_float2(wv.x, wv.y);
                     w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
+                    if (TCW_EXP_WP == 2) {
+                        const float4 wq = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP + TN);
+                        w2[0] = make_float2(wq.x, wq.y);
+                        w2[RN / 2 - 1] = make_float2(wq.z, wq.w);
+                    }
                 } else {
-                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP);
+                    if (TCW_EXP_WP == 2) w2[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP + TN);
                 }
+                if (TCW_EXP_WP == 1) {
 #pragma unroll
-                for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                    for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                }
 #pragma unroll
                 for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
@@ -223,7 +275,12 @@ tcw_exp_map_canon_kernel(const float *__restrict__ X8, uint32_t xpad, const floa
                     }
             }
         }
+#ifdef TCW_EXP_DECOUPLE
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_plain(&empty[s]);
+#else
         __syncthreads();  // everyone is done with stage s before it is refilled
+#endif
     }
 
     // ---- fused epilogue: F, optional store, max/argmax, degenerate flag ----
@@ -299,7 +356,7 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
     const int nchunks = k_end > 0 ? (k_end + TCW_EXP_KC - 1) / TCW_EXP_KC : 0;
     const float *Xt = X8 + ((size_t)t * xpad + s_base) * 8;  // 32-byte atom records: always 16-byte aligned
     const uint32_t n_tiles = (w.N_tau + TN - 1) / TN;
-    const float *Wt = W + ((size_t)cls * n_tiles + nt) * KW * TN;
+    const float *Wt = W + ((size_t)cls * n_tiles + nt) * KW * TN * TCW_EXP_WP;
     constexpr int XBYTES = SLIDE ? Cfg::kXBytes1 : Cfg::kXBytes;
     constexpr int STAGE = SLIDE ? Cfg::kStageBytes1 : Cfg::kStageBytes;
 
@@ -310,7 +367,7 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         const int s = chunk % TCW_EXP_STAGES;
         unsigned char *st = tcw_exp_smem + (size_t)s * STAGE;
         mbar_arrive_expect_tx(&full[s], Cfg::kWBytes + XBYTES);
-        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN, Cfg::kWBytes, &full[s]);
+        bulk_g2s(st, Wt + (size_t)chunk * TCW_EXP_KC * TN * TCW_EXP_WP, Cfg::kWBytes, &full[s]);
         bulk_g2s(st + Cfg::kWBytes, Xt + (size_t)chunk * TCW_EXP_KC * 8, XBYTES, &full[s]);
     };
 
@@ -343,7 +400,7 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
         const float *wrow = Ws + tn * RN;  // + k*TN
 
         if (SLIDE) {
-            const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + tm * RM * 2;  // + 2*(k + r)
+            const float4 *xrow = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN * TCW_EXP_WP) + tm * RM * 2;  // + 2*(k + r)
             // sliding window of 4 consecutive atoms per channel: value with relative index q
             // lives in slot q & 3
             float xr[TCW_NCH][4];
@@ -366,14 +423,22 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
                     }
                     float2 w1[RN / 2], w2[RN / 2];
                     if (RN == 4) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                        const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP);
                         w1[0] = make_float2(wv.x, wv.y);
                         w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
+                        if (TCW_EXP_WP == 2) {
+                            const float4 wq = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP + TN);
+                            w2[0] = make_float2(wq.x, wq.y);
+                            w2[RN / 2 - 1] = make_float2(wq.z, wq.w);
+                        }
                     } else {
-                        w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                        w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP);
+                        if (TCW_EXP_WP == 2) w2[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP + TN);
                     }
+                    if (TCW_EXP_WP == 1) {
 #pragma unroll
-                    for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                        for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                    }
 #pragma unroll
                     for (int c = 0; c < TCW_NCH; c++)
 #pragma unroll
@@ -388,19 +453,27 @@ tcw_exp_map_kernel(const float *__restrict__ X8, uint32_t xpad, const float *__r
             }
         } else {
             // rows A atoms apart: record of (row r, step k) = staged atom (tm*RM + r)*A + k
-            const float4 *xbase = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN) + (size_t)tm * RM * A * 2;
+            const float4 *xbase = reinterpret_cast<const float4 *>(Ws + TCW_EXP_KC * TN * TCW_EXP_WP) + (size_t)tm * RM * A * 2;
 #pragma unroll 1
             for (int k = 0; k < TCW_EXP_KC; k++) {
                 float2 w1[RN / 2], w2[RN / 2];
                 if (RN == 4) {
-                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN);
+                    const float4 wv = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP);
                     w1[0] = make_float2(wv.x, wv.y);
                     w1[RN / 2 - 1] = make_float2(wv.z, wv.w);
+                    if (TCW_EXP_WP == 2) {
+                        const float4 wq = *reinterpret_cast<const float4 *>(wrow + k * TN * TCW_EXP_WP + TN);
+                        w2[0] = make_float2(wq.x, wq.y);
+                        w2[RN / 2 - 1] = make_float2(wq.z, wq.w);
+                    }
                 } else {
-                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN);
+                    w1[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP);
+                    if (TCW_EXP_WP == 2) w2[0] = *reinterpret_cast<const float2 *>(wrow + k * TN * TCW_EXP_WP + TN);
                 }
+                if (TCW_EXP_WP == 1) {
 #pragma unroll
-                for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                    for (int j = 0; j < RN / 2; j++) w2[j] = __fmul2_rn(w1[j], w1[j]);
+                }
 #pragma unroll
                 for (int r = 0; r < RM; r++) {
                     const float4 lo = xbase[2 * (r * A + k)], hi = xbase[2 * (r * A + k) + 1];

@@ -65,6 +65,11 @@ extern "C" {
                                       recomputing the looked-up entry e^{-i0 dx} on the fly (same
                                       table index, value to ~3e-7 relative).  Implied when a
                                       non-canonical table was installed with tcw_set_exp_lut    */
+#define TCW_EXP_DIRECT       0x40u /* exponential window: always the tiled direct sum over the atoms
+                                      (Exp.cu:82-102 restructured).  Without it, canonical grids
+                                      (rows one atom apart) run the FP64 recurrence down the rows,
+                                      plus -- in lookup-table mode -- the tensor-core pass for the
+                                      table's deviation from the exact exponential             */
 
 /* Default geometry of the emulated XLALFastNegExp table (lalpulsar/lib/TransientCW_utils.c,
  * not in the reference tree): e^{-x} on [0, XMAX] in LENGTH steps, nearest-point lookup
@@ -113,7 +118,8 @@ typedef struct tcw_result {
     uint32_t numAtoms;       /* merged atoms on the TAtom grid (tcw:706-709) */
     uint32_t t0_data;        /* first merged timestamp (tcw:725) */
     int32_t status;          /* TCW_OK or TCW_E_DEGENERATE for this template */
-    uint32_t path;           /* 0 = generic kernels, 1 = tiled fast kernels (informational) */
+    uint32_t path;           /* 0 = generic kernels, 1 = tiled fast kernels, 2 = exp-window recurrence
+                                (+ tensor-core correction) (informational) */
     uint32_t reserved;
 } tcw_result;
 

@@ -27,6 +27,7 @@ EXP_EXACT = 0x4
 ALLOW_DEGENERATE = 0x8
 FORCE_GENERIC = 0x10
 BTSG_TABLE = 0x20
+EXP_DIRECT = 0x40
 
 # default geometry of the emulated XLALFastNegExp table (TCW_EXPLUT_DEFAULT_* in the header)
 EXPLUT_DEFAULT = (20.0, 5120)

@@ -29,6 +29,7 @@
 #include "tcw_btsg.cuh"
 #include "tcw_common.cuh"
 #include "tcw_exp.cuh"
+#include "tcw_exp_rec.cuh"
 #include "tcw_generic.cuh"
 #include "tcw_prep.cuh"
 #include "tcw_rect.cuh"
@@ -74,7 +75,7 @@ struct tcw_handle {
     // d_zero: everything a map needs zero-initialised -- max keys, lnBtSG marginals, flags, tile-queue
     // counters -- in ONE region, cleared by one memset per map
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
-        d_wins, d_tilemax, d_shift;
+        d_wins, d_tilemax, d_shift, d_G, d_C;
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -93,6 +94,7 @@ struct tcw_handle {
     bool lut_canonical = false;
     int exp_variant = 1;  // ExpCfgB: measured fastest (r01: A 14.70 ms, B 13.77 ms, C 13.80 ms per 32 x 30-d templates)
     int w_exact = -1;
+    int w_kind = -1;  // what d_W holds: 0 direct-sum weights, 1 tensor-core correction weights, 2 nothing (exact recurrence)
     std::vector<int32_t> w_Kn;
 };
 
@@ -360,6 +362,7 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     EXP_ATTR(ExpCfgC);
 #undef EXP_ATTR
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECTP_SMEM));
     if (const char *v = getenv("TCW_RECT_PERSIST")) h->rect_persist = atoi(v);
@@ -373,7 +376,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_zero, &h->d_results, &h->d_W, &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins,
-                      &h->d_tilemax, &h->d_shift})
+                      &h->d_tilemax, &h->d_shift, &h->d_G, &h->d_C})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -876,6 +879,13 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             if (ep.ok) path = PATH_FAST;
         }
     }
+    // exponential window on a canonical grid: FP64 recurrence down the rows (+ the tensor-core correction
+    // in lookup-table mode), tcw_exp_rec.cuh; TCW_EXP_DIRECT keeps the tiled direct sum
+    const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT);
+    const bool exp_tc = exp_rec && !exact;
+    const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + TCX_SPAN - 1) / TCX_SPAN;
+    const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + 31) / 32 + 10;
+    const size_t tc_c_per_tpl = (size_t)TCW_NCH * w.N_t0 * tc_cpitch * sizeof(float);
 
     // ---- buffers ----
     int rc;
@@ -898,6 +908,12 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         int chunks = 2;  // measured: MCMC step (23.6 MB, little compute) 1.29 ms with 1-2 chunks, 1.48 with 4, 1.92 with 8
         if (const char *env = getenv("TCW_UPLOAD_CHUNKS")) chunks = std::max(1, atoi(env));
         S = std::min(S, std::max(8, (T + chunks - 1) / chunks));
+    }
+    if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (28 B per cell): cap it at 4 GB
+        S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (4ull << 30) / tc_c_per_tpl));
+        if ((uint64_t)S * tc_n_nt * tc_n_mb * 4ull >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
+        if ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl))) return rc;
+        if ((rc = ensure(h, h->d_G, (size_t)S * 2048 * tc_U * sizeof(float)))) return rc;
     }
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
     if (want_fmn) {
@@ -978,13 +994,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     uint32_t exp_TM = 0, exp_TN = 0;
     exp_tile_dims(h->exp_variant, &exp_TM, &exp_TN);
     if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
+        const int kind = exp_tc ? 1 : exp_rec ? 2 : 0;
         const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
-                         h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom &&
+                         h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom && h->w_kind == kind &&
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
-            const size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
-            if ((rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
+            size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
+            if (kind == 1) total = (size_t)tc_n_nt * (ep.KW / TCX_KC) * 4096;
+            if (kind == 0 && (rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
+            if (kind == 1 && (rc = ensure(h, h->d_W, total * 2 * sizeof(float)))) return rc;
             if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
             h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -1001,9 +1020,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             eg.P = ep.ec.P;
             for (int r = 0; r < TCW_EXP_PMAX; r++) eg.delta[r] = ep.delta[r];
             const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->prop.multiProcessorCount * 16);
-            tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg, lut,
-                                                         (int)exact);
-            h->launches++;
+            if (kind == 0)
+                tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg, lut,
+                                                             (int)exact);
+            else if (kind == 1)
+                tcw_exptc_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau,
+                                                               tc_n_nt, ep.KW / TCX_KC, w.tau, w.dtau, TAtom, ep.delta[0],
+                                                               lut);
+            if (kind != 2) h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
             h->w_valid = true;
@@ -1011,6 +1035,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             h->w_t0_data = h->meta[0].t0_data;
             h->w_TAtom = TAtom;
             h->w_exact = (int)exact;
+            h->w_kind = kind;
             h->w_KW = ep.KW;
             h->w_TN = exp_TN;
         }
@@ -1128,6 +1153,33 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             else if (rect_staged) LAUNCH_RECT(1, true);
             else LAUNCH_RECT(1, false);
 #undef LAUNCH_RECT
+        } else if (exp_rec) {
+            const float *corr = nullptr;
+            if (exp_tc) {
+                tcw_exptc_atoms_kernel<<<dim3(std::min<uint32_t>((2048u * tc_U + 255u) / 256u, 1024u), cnt), 256, 0, st>>>(
+                    (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0], tc_U,
+                    (float *)h->d_G.p);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+                const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * 4u;
+                const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
+                tcw_exptc_map_kernel<<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
+                    (const float *)h->d_G.p, tc_U, (const float *)h->d_W.p, ep.KW / TCX_KC, (const int32_t *)h->d_Kn.p,
+                    (const TplMeta *)h->d_meta.p, t_base, (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles,
+                    (float *)h->d_C.p, tc_cpitch);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+                corr = (const float *)h->d_C.p;
+            }
+            dim3 grid((w.N_tau + TCX_WALK_THREADS - 1) / TCX_WALK_THREADS, cnt);
+            if (exp_tc)
+                tcw_exp_walk_kernel<true><<<grid, TCX_WALK_THREADS, 0, st>>>(
+                    (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w,
+                    ep.ec.i00[0], ep.delta[0], TAtom, corr, tc_cpitch, fmn, p_maxkey, p_flags);
+            else
+                tcw_exp_walk_kernel<false><<<grid, TCX_WALK_THREADS, 0, st>>>(
+                    (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w,
+                    ep.ec.i00[0], ep.delta[0], TAtom, nullptr, 0, fmn, p_maxkey, p_flags);
         } else {
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, ep.ec.ybeg[TCW_EXP_PMAX], cnt);
 #define LAUNCH_EXP(CFG)                                                                                        \
@@ -1186,7 +1238,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         p_maxkey, p_flags,
         p_rowsum, p_colsum, 1.0 / fx_scale,
         (const TplMeta *)h->d_meta.p, w, d_wins, (int)none_window, TAtom, (int)want_btsg,
-        (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)path, (tcw_result *)h->d_results.p);
+        (int)((flags & TCW_ALLOW_DEGENERATE) != 0), (uint32_t)(exp_rec ? 2 : path), (tcw_result *)h->d_results.p);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev_fin, st));

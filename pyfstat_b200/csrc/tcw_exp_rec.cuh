@@ -1,0 +1,419 @@
+// tcw_exp_rec.cuh -- exponential-window map as an FP64 recurrence (+ a tensor-core correction in
+// `lal` lookup-table mode).  Canonical grids only (one row class, rows one atom apart, every
+// template starting on the same atom, no start beyond the data end: tcw_b200.cu plan_exp `canon`).
+//
+// Exp.cu:82-102 sums, per cell, K ~ 3 tau / TAtom weighted atoms:  O(N_t0 N_tau K).  With rows one
+// atom apart the weight of atom i for row m depends on k = i - i_t0(m) only, and for EXACT
+// exponentials it is geometric in k:  w(k,n) = w0_n rho_n^(k - ka),  rho_n = e^{-TAtom/tau_n},
+// k in [ka, kb_n].  Then
+//     U_c[m,n] = sum_{j=0}^{L-1} X_c[s_m + ka + j] rho^(p_c j)            (L = kb - ka + 1)
+//              = X_c[s_m + ka] + rho^p U_c[m+1,n] - rho^(pL) X_c[s_m + kb + 1]
+// is a first-order recurrence down the rows of a column: O(1) per cell and channel instead of O(K).
+// north_star allows a recurrence "only where it is shown to be numerically safe"; this one is:
+//   * it is a CONTRACTION (0 < rho < 1): a rounding error made at row m is multiplied by rho at
+//     every later row, so the accumulated error is bounded by eps * sum_j |X| rho^j -- the size of
+//     the sum's own terms -- and does not grow with the number of rows walked;
+//   * U is carried in FP64 (eps = 1.1e-16).  The atom that leaves the window was added with weight
+//     1 and has been multiplied L times by rho; removing it with rho^L leaves a residue of
+//     ~L eps |X| rho^L, 1e-12 relative at L = 17 000;
+//   * measured (tests/test_gpu_parity.py::test_exp_recurrence_*): the FP64 recurrence agrees with
+//     FP64 direct sums to 1e-13 and is CLOSER to them than the reference's sequential FP32 sums are.
+// The sums then go through the same FP32 F-statistic epilogue as the other kernels.
+//
+// `lal` mode weighs atoms with XLALFastNegExp, a nearest-point table: w_lut(k,n) = e^{-x} (1 + d),
+// |d| <= dx/2 (0.2 % at dx = 1/256), a sawtooth that no recurrence reproduces.  Split
+//     sum_k X w_lut = sum_k X w_exact  +  sum_k X (w_lut - w_exact)
+// The first term is the recurrence; the second is a Hankel contraction whose weights are <= 2e-3 of
+// the first term's, so it needs 3 significant digits, not 7: it runs on the 5th-gen tensor cores in
+// one TF32 pass (tcgen05.mma kind::tf32, FP32 accumulation in TMEM).  TF32 rounding of X and V
+// (2^-11 each) and the tensor core's truncating accumulation (measured 6e-6 of sum|terms| at
+// K = 5760, profiles/r02_tc_probe.txt) are multiplied by the 2e-3 and land below 1e-8 of the sums.
+//
+// Tensor-core kernel.  D_c[(i), n] = sum_k X_c[s0 + 4 i + k] V[k, n]: in the no-swizzle K-major
+// canonical layout a row is 16 bytes = 4 TF32 values and the 8 rows of a core matrix are 16 bytes
+// apart, so a descriptor laid over the plain atom array IS the Hankel operand for the rows
+// m = m0 + r + 4 i of row class r (tools/tc_probe/hankel_tf32.cu).  Channels are stacked in M: the
+// 128 lanes of an MMA are 2 channels x 64 rows, each 8-row group reading its own 256-byte chunk of
+// atoms (32 rows' span + 32 k), the chunks 256 bytes apart (SBO); a prep kernel lays the atoms out
+// in that chunked form -- per class r, channel pair p and 32-atom block u: [c'][64 floats] -- so a
+// stage's A operand is four contiguous 4-KB bulk copies.  N = 128 window lengths.  The four channel
+// pairs (a2,b2 | ab,- | Fa | Fb) own 4 x 128 TMEM columns = all 512; per 32-k stage 16 MMAs
+// (M128 N128 K8).  Warp roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C);
+// persistent CTAs, one per SM, static round-robin over tiles ordered by decreasing k range.
+#pragma once
+#include "tcw_common.cuh"
+#include "tcw_generic.cuh"
+
+#define TCX_KC 32        // k per stage
+#define TCX_TAUS 128     // window lengths per tile (MMA N)
+#define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + 4 i)
+#define TCX_SPAN 256     // map rows spanned by a tile
+#define TCX_STAGES 4
+#define TCX_A_BYTES 16384  // 4 pairs x 16 chunks x 256 B
+#define TCX_B_BYTES 32768  // 2 tables x 128 taus x 32 k x 4 B
+#define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)
+#define TCX_THREADS 192
+#define TCX_SMEM (TCX_STAGES * TCX_STAGE_BYTES + 128)
+#define TCX_WALK_THREADS 64
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// channel of (pair p, slot c'): a2,b2 | ab,- | Fa_re,Fa_im | Fb_re,Fb_im ; -1 = unused slot
+__device__ __forceinline__ int tcx_channel(int p, int cp) {
+    const int ch = 2 * p + cp - (p >= 2 ? 1 : 0);
+    return (p == 1 && cp == 1) ? -1 : ch;
+}
+
+// ---- atoms in chunked TF32 form: G[tz][r][p][u][c'][64],  value = X_ch[i00 + r + 32 u + e] ----
+__global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
+                                       int t_base, uint32_t i00, uint32_t U, float *__restrict__ G) {
+    const int tz = blockIdx.y, t = t_base + tz;
+    const uint32_t numAtoms = meta[t].numAtoms;
+    const size_t per_tpl = (size_t)2048 * U;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_tpl; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = (uint32_t)idx & 63u, cp = ((uint32_t)idx >> 6) & 1u;
+        size_t rest = idx >> 7;
+        const uint32_t u = (uint32_t)(rest % U);
+        rest /= U;
+        const uint32_t p = (uint32_t)rest & 3u, r = (uint32_t)rest >> 2;
+        const int ch = tcx_channel((int)p, (int)cp);
+        const uint64_t j = (uint64_t)i00 + r + 32ull * u + e;
+        float v = 0.0f;
+        if (ch >= 0 && j < numAtoms) v = tf32_rna(__ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j));
+        G[(size_t)tz * per_tpl + idx] = v;
+    }
+}
+
+// ---- correction weights V = w_lut - w_exact (table 0) and w_lut^2 - w_exact^2 (table 1), TF32,
+//      in the MMA's canonical layout: Vt[nt][chunk][table][kq 8][ng 16][nr 8][kk 4] ----
+__global__ void tcw_exptc_table_kernel(float *__restrict__ Vt, const int32_t *__restrict__ Kn, uint32_t N_tau,
+                                       uint32_t n_nt, uint32_t n_chunks, uint32_t tau, uint32_t dtau, uint32_t TAtom,
+                                       int32_t delta, const ExpLut lut) {
+    const size_t total = (size_t)n_nt * n_chunks * 4096;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t off = (uint32_t)idx & 4095u;
+        const uint32_t kk = off & 3u, nr = (off >> 2) & 7u, ng = (off >> 5) & 15u, kq = off >> 9;
+        const size_t rest = idx >> 12;
+        const uint32_t chunk = (uint32_t)(rest % n_chunks), nt = (uint32_t)(rest / n_chunks);
+        const uint32_t k = chunk * TCX_KC + kq * 4 + kk, n = nt * TCX_TAUS + ng * 8 + nr;
+        float v1 = 0.0f, v2 = 0.0f;
+        if (n < N_tau && (int32_t)k <= Kn[n]) {
+            const uint32_t tau_n = tau + n * dtau;
+            const long long t_rel = (long long)k * TAtom + delta;  // t_i - t0_m
+            if (t_rel >= 0 && t_rel <= (long long)TCW_EXP_EFOLDING * tau_n) {
+                const double x = __ddiv_rn((double)t_rel, (double)tau_n);
+                const double wl = fast_neg_exp_lut(x, lut), we = exp(-x);
+                v1 = tf32_rna((float)(wl - we));
+                v2 = tf32_rna((float)((wl - we) * (wl + we)));
+            }
+        }
+        float *base = Vt + rest * 8192;
+        base[off] = v1;
+        base[4096 + off] = v2;
+    }
+}
+
+// ---- tcgen05 helpers ----
+__device__ __forceinline__ uint64_t tcx_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;  // no-swizzle K-major: start, leading (K) and stride (M/N) byte offsets in 16-byte units
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
+    return d;
+}
+// kind::tf32, D = F32, A and B K-major
+__host__ __device__ constexpr uint32_t tcx_idesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void tcx_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tcx_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tcx_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcx_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct TcxTile {
+    uint32_t tz, r, mb, nt;
+    int nchunks;
+};
+__device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n_mb, uint32_t n_nt, const MapWindow &w,
+                                            uint32_t i00, const TplMeta *__restrict__ meta, int t_base,
+                                            const int32_t *__restrict__ Kn) {
+    TcxTile tl;
+    tl.tz = j % cnt;
+    uint32_t rest = j / cnt;
+    tl.r = rest & 3u;
+    rest >>= 2;
+    tl.mb = rest % n_mb;
+    tl.nt = n_nt - 1u - rest / n_mb;  // widest windows first
+    const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
+    const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
+    const long long s_first = (long long)i00 + (long long)tl.mb * TCX_SPAN + tl.r;
+    const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
+    const bool rows = tl.mb * TCX_SPAN + tl.r < w.N_t0;
+    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + TCX_KC - 1) / TCX_KC) : 0;
+    return tl;
+}
+
+// C[tz][ch][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128)
+__global__ void __launch_bounds__(TCX_THREADS, 1)
+tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__restrict__ Vt, uint32_t n_chunks_tab,
+                     const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
+                     MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles, float *__restrict__ C,
+                     uint32_t cpitch) {
+    extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
+    __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full, tmem_empty;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TCX_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tmem_full, 1);
+        mbar_init(&tmem_empty, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcx_fence_before();
+    __syncthreads();
+    tcx_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer ----
+            uint32_t it = 0;
+            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+                const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                const float *gA = G + (((size_t)tl.tz * 4 + tl.r) * 4 * U + 8ull * tl.mb) * 128;  // + (p U + c) * 128
+                const float *gB = Vt + (size_t)tl.nt * n_chunks_tab * 8192;                     // + c * 8192
+                for (int c = 0; c < tl.nchunks; c++, it++) {
+                    const uint32_t s = it % TCX_STAGES;
+                    mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
+                    unsigned char *st = smem + (size_t)s * TCX_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
+#pragma unroll
+                    for (int p = 0; p < 4; p++)
+                        bulk_g2s(st + p * 4096, gA + ((size_t)p * U + c) * 128, 4096, &full[s]);
+                    bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 8192, TCX_B_BYTES, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS);
+            const uint64_t da = tcx_desc(0, 16, 256);      // A: K halves 16 B apart, 8-row groups = chunks 256 B apart
+            const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][4]: K quarters 2 KB apart, 8-column groups 128 B
+            uint32_t it = 0, tl_i = 0;
+            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x, tl_i++) {
+                const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                mbar_wait(&tmem_empty, (tl_i & 1u) ^ 1u);
+                tcx_fence_after();
+                for (int c = 0; c < tl.nchunks; c++, it++) {
+                    const uint32_t s = it % TCX_STAGES;
+                    mbar_wait(&full[s], (it / TCX_STAGES) & 1u);
+                    tcx_fence_after();
+                    const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
+#pragma unroll
+                    for (int q = 0; q < TCX_KC / 8; q++) {
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            const uint64_t ad = da | (uint64_t)(((a0 + p * 4096 + q * 32) >> 4) & 0x3FFF);
+                            const uint64_t bd = db | (uint64_t)(((b0 + (p < 2 ? 16384 : 0) + q * 4096) >> 4) & 0x3FFF);
+                            tcx_mma(tmem + p * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
+                        }
+                    }
+                    tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
+                }
+                if (tl.nchunks > 0) tcx_commit(&tmem_full);
+                else mbar_arrive_plain(&tmem_full);
+            }
+        }
+    } else {  // ---- epilogue warps: TMEM -> C ----
+        const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
+        const uint32_t L = q * 32 + lane;
+        const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
+        uint32_t tl_i = 0;
+        for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x, tl_i++) {
+            const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+            mbar_wait(&tmem_full, tl_i & 1u);
+            tcx_fence_after();
+            const uint32_t m = tl.mb * TCX_SPAN + tl.r + 4 * i;
+#pragma unroll 1
+            for (int p = 0; p < 4; p++) {
+                const int ch = tcx_channel(p, (int)cp);
+                float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
+                const bool store = ch >= 0 && m < w.N_t0;
+#pragma unroll 1
+                for (int cb = 0; cb < 4; cb++) {
+                    uint32_t v[32];
+                    if (tl.nchunks > 0) {
+                        const uint32_t taddr = tmem + ((q * 32u) << 16) + (uint32_t)(p * 128 + cb * 32);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 32; x++) v[x] = 0u;
+                    }
+                    if (store) {
+                        uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
+#pragma unroll
+                        for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                    }
+                }
+            }
+            tcx_fence_before();
+            mbar_arrive_plain(&tmem_empty);
+        }
+    }
+    tcx_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// ---- the walk: one thread per (template, window length), rows from the data end down ----
+template <bool HAS_C>
+__global__ void __launch_bounds__(TCX_WALK_THREADS)
+tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *__restrict__ Kn,
+                    const TplMeta *__restrict__ meta, int t_base, MapWindow w, uint32_t i00, int32_t delta, uint32_t TAtom,
+                    const float *__restrict__ C, uint32_t cpitch, float *__restrict__ Fmn,
+                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+    __shared__ unsigned long long red[TCX_WALK_THREADS / 32];
+    const int tz = blockIdx.y, t = t_base + tz;
+    const uint32_t numAtoms = meta[t].numAtoms;
+    const uint32_t n = blockIdx.x * TCX_WALK_THREADS + threadIdx.x;
+    const bool active = n < w.N_tau;
+    const float4 *Xt = reinterpret_cast<const float4 *>(X8 + (size_t)t * xpad * 8);
+
+    // the column's window: k in [ka, kb], weights w0 rho^(k - ka)
+    const uint32_t nn = active ? n : w.N_tau - 1;
+    const int K = Kn[nn];
+    const long long tau_n = (long long)w.tau + (long long)nn * w.dtau;
+    const int ka = delta < 0 ? 1 : 0;
+    const long long num = (long long)TCW_EXP_EFOLDING * tau_n - delta;  // t_rel <= 3 tau
+    const int kb = (int)min((long long)K, num >= 0 ? num / (long long)TAtom : -1ll);
+    const int L = kb - ka + 1;
+    const bool empty_win = L <= 0;
+    const double inv_tau = 1.0 / (double)tau_n;
+    const double rho = exp(-(double)TAtom * inv_tau), rho2 = rho * rho;
+    const double w0 = empty_win ? 0.0 : exp(-((double)ka * TAtom + (double)delta) * inv_tau), w02 = w0 * w0;
+    const double rhoL = empty_win ? 0.0 : exp(-(double)L * (double)TAtom * inv_tau);
+    const float rL = (float)rhoL, rL2 = (float)(rhoL * rhoL);
+    const float a0 = empty_win ? 0.0f : 1.0f;
+
+    double U[TCW_NCH];
+#pragma unroll
+    for (int c = 0; c < TCW_NCH; c++) U[c] = 0.0;
+
+    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
+    const float *Ct = HAS_C ? C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + nn : nullptr;
+    float best = -1.0f;
+    uint32_t best_flat = 0;
+    bool degenerate = false;
+
+    auto step = [&](int m) {
+        const uint32_t s = i00 + (uint32_t)m;
+        const uint32_t j0 = s + ka, j1 = s + (uint32_t)(kb + 1);
+        float4 lo0 = make_float4(0.f, 0.f, 0.f, 0.f), hi0 = lo0, lo1 = lo0, hi1 = lo0;
+        if (j0 < numAtoms) {
+            lo0 = __ldg(Xt + 2 * (size_t)j0);
+            hi0 = __ldg(Xt + 2 * (size_t)j0 + 1);
+        }
+        if (!empty_win && j1 < numAtoms) {
+            lo1 = __ldg(Xt + 2 * (size_t)j1);
+            hi1 = __ldg(Xt + 2 * (size_t)j1 + 1);
+        }
+        // d = X[s + ka] - rho^(pL) X[s + kb + 1] in FP32 (one rounding), U = rho^p U + d in FP64
+        U[0] = fma(rho2, U[0], (double)fmaf(-rL2, lo1.x, a0 * lo0.x));
+        U[1] = fma(rho2, U[1], (double)fmaf(-rL2, lo1.y, a0 * lo0.y));
+        U[2] = fma(rho2, U[2], (double)fmaf(-rL2, lo1.z, a0 * lo0.z));
+        U[3] = fma(rho, U[3], (double)fmaf(-rL, lo1.w, a0 * lo0.w));
+        U[4] = fma(rho, U[4], (double)fmaf(-rL, hi1.x, a0 * hi0.x));
+        U[5] = fma(rho, U[5], (double)fmaf(-rL, hi1.y, a0 * hi0.y));
+        U[6] = fma(rho, U[6], (double)fmaf(-rL, hi1.z, a0 * hi0.z));
+    };
+    auto cell = [&](int m, const float *cc) {
+        float S[TCW_NCH];
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++) {
+            S[c] = (float)((c < 3 ? w02 : w0) * U[c]);
+            if (HAS_C) S[c] += cc[c];
+        }
+        const float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+        if (active) {
+            if (Ft) Ft[(size_t)m * w.pitch + n] = F;
+            if (F > best) {
+                best = F;
+                best_flat = (uint32_t)m * w.N_tau + n;
+            }
+            if (K >= 0 && (K == 0 || i00 + (uint32_t)m == numAtoms - 1)) degenerate = true;
+        }
+    };
+
+    // rows beyond the map (the canonical plan guarantees i00 + N_t0 - 1 <= numAtoms - 1): no output
+    int m = (int)numAtoms - (int)i00 - 1;
+    for (; m >= (int)w.N_t0; m--) step(m);
+
+    if (HAS_C) {
+        // correction sums are fetched 4 rows ahead (HBM latency vs. the serial walk)
+        float cbuf[4][TCW_NCH];
+        const size_t cstride = (size_t)w.N_t0 * cpitch;
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) cbuf[u][c] = (m - u >= 0) ? __ldg(Ct + c * cstride + (size_t)(m - u) * cpitch) : 0.0f;
+        for (; m >= 3; m -= 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                step(m - u);
+                cell(m - u, cbuf[u]);
+                const int mn = m - u - 4;
+                if (mn >= 0) {
+#pragma unroll
+                    for (int c = 0; c < TCW_NCH; c++) cbuf[u][c] = __ldg(Ct + c * cstride + (size_t)mn * cpitch);
+                }
+            }
+        }
+        // remaining 0..3 rows: cbuf[u] holds row m - u
+        if (m >= 0) { step(m); cell(m, cbuf[0]); }
+        if (m >= 1) { step(m - 1); cell(m - 1, cbuf[1]); }
+        if (m >= 2) { step(m - 2); cell(m - 2, cbuf[2]); }
+    } else {
+        for (; m >= 0; m--) {
+            step(m);
+            cell(m, nullptr);
+        }
+    }
+    if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
+    const unsigned long long key = (active && best > -1.0f) ? pack_key(best, best_flat) : 0ull;
+    block_atomic_max_key<TCX_WALK_THREADS / 32>(key, &maxkey[t], red);
+}

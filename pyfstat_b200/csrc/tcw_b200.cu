@@ -363,6 +363,14 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
 #undef EXP_ATTR
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
+#define WALK_ATTR(NS)                                                                                              \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           WalkCfg<NS>::kEBytes + WalkCfg<NS>::kRingBytes))
+    WALK_ATTR(1);
+    WALK_ATTR(2);
+    WALK_ATTR(4);
+    WALK_ATTR(8);
+#undef WALK_ATTR
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECTP_SMEM));
     if (const char *v = getenv("TCW_RECT_PERSIST")) h->rect_persist = atoi(v);
@@ -1171,15 +1179,32 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 CUDA_TRY(h, cudaGetLastError());
                 corr = (const float *)h->d_C.p;
             }
-            dim3 grid((w.N_tau + TCX_WALK_THREADS - 1) / TCX_WALK_THREADS, cnt);
-            if (exp_tc)
-                tcw_exp_walk_kernel<true><<<grid, TCX_WALK_THREADS, 0, st>>>(
-                    (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w,
-                    ep.ec.i00[0], ep.delta[0], TAtom, corr, tc_cpitch, fmn, p_maxkey, p_flags);
-            else
-                tcw_exp_walk_kernel<false><<<grid, TCX_WALK_THREADS, 0, st>>>(
-                    (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w,
-                    ep.ec.i00[0], ep.delta[0], TAtom, nullptr, 0, fmn, p_maxkey, p_flags);
+            // row segments per column: enough threads to fill the GPU (pass 1 of the segmented walk costs
+            // about a third of a walk, so none when the batch alone fills it)
+            int nseg = 1;
+            while (nseg < 8 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 1280) nseg *= 2;
+            if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(8, atoi(env)));
+#define LAUNCH_WALK(HASC, NS)                                                                                      \
+    do {                                                                                                           \
+        using WC = WalkCfg<NS>;                                                                                    \
+        const size_t smem = (NS > 1 || HASC ? WC::kEBytes : 0) + (HASC ? WC::kRingBytes : 0);                      \
+        dim3 grid((w.N_tau + 32 * WC::kCG - 1) / (32 * WC::kCG), cnt);                                             \
+        tcw_exp_walk_kernel<HASC, NS><<<grid, WC::kThreads, smem, st>>>(                                           \
+            (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w, \
+            ep.ec.i00[0], ep.delta[0], TAtom, corr, tc_cpitch, fmn, p_maxkey, p_flags);                            \
+    } while (0)
+            if (exp_tc) {
+                if (nseg == 1) LAUNCH_WALK(true, 1);
+                else if (nseg == 2) LAUNCH_WALK(true, 2);
+                else if (nseg == 4) LAUNCH_WALK(true, 4);
+                else LAUNCH_WALK(true, 8);
+            } else {
+                if (nseg == 1) LAUNCH_WALK(false, 1);
+                else if (nseg == 2) LAUNCH_WALK(false, 2);
+                else if (nseg == 4) LAUNCH_WALK(false, 4);
+                else LAUNCH_WALK(false, 8);
+            }
+#undef LAUNCH_WALK
         } else {
             dim3 grid((w.N_tau + exp_TN - 1) / exp_TN, ep.ec.ybeg[TCW_EXP_PMAX], cnt);
 #define LAUNCH_EXP(CFG)                                                                                        \

@@ -48,13 +48,12 @@
 #define TCX_TAUS 128     // window lengths per tile (MMA N)
 #define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + 4 i)
 #define TCX_SPAN 256     // map rows spanned by a tile
-#define TCX_STAGES 4
-#define TCX_A_BYTES 16384  // 4 pairs x 16 chunks x 256 B
-#define TCX_B_BYTES 32768  // 2 tables x 128 taus x 32 k x 4 B
+#define TCX_STAGES 8
+#define TCX_A_BYTES 8192   // 2 pairs x 16 chunks x 256 B
+#define TCX_B_BYTES 16384  // 128 taus x 32 k x 4 B (one table)
 #define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)
 #define TCX_THREADS 192
 #define TCX_SMEM (TCX_STAGES * TCX_STAGE_BYTES + 128)
-#define TCX_WALK_THREADS 64
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
@@ -167,14 +166,17 @@ __device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n
     return tl;
 }
 
-// C[tz][ch][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128)
+// C[tz][ch][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128).
+// A tile is processed as two UNITS -- channel pairs (a2,b2 | ab,-) with the w^2 table, then (Fa | Fb) with
+// the w table; no operand is shared between them, so the split costs no traffic -- each accumulating into
+// one half of TMEM (2 x 128 columns): the epilogue warps drain unit u while the MMAs of unit u + 1 run.
 __global__ void __launch_bounds__(TCX_THREADS, 1)
 tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__restrict__ Vt, uint32_t n_chunks_tab,
                      const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
                      MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles, float *__restrict__ C,
                      uint32_t cpitch) {
     extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
-    __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full, tmem_empty;
+    __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -185,8 +187,11 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&tmem_full, 1);
-        mbar_init(&tmem_empty, 128);
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 128);
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -205,17 +210,18 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
             for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
                 const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
                 const float *gA = G + (((size_t)tl.tz * 4 + tl.r) * 4 * U + 8ull * tl.mb) * 128;  // + (p U + c) * 128
-                const float *gB = Vt + (size_t)tl.nt * n_chunks_tab * 8192;                     // + c * 8192
-                for (int c = 0; c < tl.nchunks; c++, it++) {
-                    const uint32_t s = it % TCX_STAGES;
-                    mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
-                    unsigned char *st = smem + (size_t)s * TCX_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
+                const float *gB = Vt + (size_t)tl.nt * n_chunks_tab * 8192;                     // + c * 8192 (+ 4096: w^2)
+                for (int hh = 0; hh < 2; hh++)
+                    for (int c = 0; c < tl.nchunks; c++, it++) {
+                        const uint32_t s = it % TCX_STAGES;
+                        mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
+                        unsigned char *st = smem + (size_t)s * TCX_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
 #pragma unroll
-                    for (int p = 0; p < 4; p++)
-                        bulk_g2s(st + p * 4096, gA + ((size_t)p * U + c) * 128, 4096, &full[s]);
-                    bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 8192, TCX_B_BYTES, &full[s]);
-                }
+                        for (int pl = 0; pl < 2; pl++)
+                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 128, 4096, &full[s]);
+                        bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 8192 + (hh == 0 ? 4096 : 0), TCX_B_BYTES, &full[s]);
+                    }
             }
         }
     } else if (warp == 1) {
@@ -223,75 +229,82 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
             constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS);
             const uint64_t da = tcx_desc(0, 16, 256);      // A: K halves 16 B apart, 8-row groups = chunks 256 B apart
             const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][4]: K quarters 2 KB apart, 8-column groups 128 B
-            uint32_t it = 0, tl_i = 0;
-            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x, tl_i++) {
+            uint32_t it = 0, unit = 0;
+            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
                 const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-                mbar_wait(&tmem_empty, (tl_i & 1u) ^ 1u);
-                tcx_fence_after();
-                for (int c = 0; c < tl.nchunks; c++, it++) {
-                    const uint32_t s = it % TCX_STAGES;
-                    mbar_wait(&full[s], (it / TCX_STAGES) & 1u);
+                for (int hh = 0; hh < 2; hh++, unit++) {
+                    const uint32_t buf = unit & 1u;
+                    mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
                     tcx_fence_after();
-                    const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
+                    const uint32_t d0 = tmem + buf * 256u;
+                    for (int c = 0; c < tl.nchunks; c++, it++) {
+                        const uint32_t s = it % TCX_STAGES;
+                        mbar_wait(&full[s], (it / TCX_STAGES) & 1u);
+                        tcx_fence_after();
+                        const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
 #pragma unroll
-                    for (int q = 0; q < TCX_KC / 8; q++) {
+                        for (int q = 0; q < TCX_KC / 8; q++) {
+                            const uint64_t bd = db | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
 #pragma unroll
-                        for (int p = 0; p < 4; p++) {
-                            const uint64_t ad = da | (uint64_t)(((a0 + p * 4096 + q * 32) >> 4) & 0x3FFF);
-                            const uint64_t bd = db | (uint64_t)(((b0 + (p < 2 ? 16384 : 0) + q * 4096) >> 4) & 0x3FFF);
-                            tcx_mma(tmem + p * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
+                            for (int pl = 0; pl < 2; pl++) {
+                                const uint64_t ad = da | (uint64_t)(((a0 + pl * 4096 + q * 32) >> 4) & 0x3FFF);
+                                tcx_mma(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
+                            }
                         }
+                        tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
                     }
-                    tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
+                    if (tl.nchunks > 0) tcx_commit(&tmem_full[buf]);
+                    else mbar_arrive_plain(&tmem_full[buf]);
                 }
-                if (tl.nchunks > 0) tcx_commit(&tmem_full);
-                else mbar_arrive_plain(&tmem_full);
             }
         }
     } else {  // ---- epilogue warps: TMEM -> C ----
         const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
         const uint32_t L = q * 32 + lane;
         const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
-        uint32_t tl_i = 0;
-        for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x, tl_i++) {
+        uint32_t unit = 0;
+        for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
             const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-            mbar_wait(&tmem_full, tl_i & 1u);
-            tcx_fence_after();
             const uint32_t m = tl.mb * TCX_SPAN + tl.r + 4 * i;
+            for (int hh = 0; hh < 2; hh++, unit++) {
+                const uint32_t buf = unit & 1u;
+                mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
+                tcx_fence_after();
 #pragma unroll 1
-            for (int p = 0; p < 4; p++) {
-                const int ch = tcx_channel(p, (int)cp);
-                float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
-                const bool store = ch >= 0 && m < w.N_t0;
+                for (int pl = 0; pl < 2; pl++) {
+                    const int ch = tcx_channel(2 * hh + pl, (int)cp);
+                    float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
+                    const bool store = ch >= 0 && m < w.N_t0;
 #pragma unroll 1
-                for (int cb = 0; cb < 4; cb++) {
-                    uint32_t v[32];
-                    if (tl.nchunks > 0) {
-                        const uint32_t taddr = tmem + ((q * 32u) << 16) + (uint32_t)(p * 128 + cb * 32);
-                        asm volatile(
-                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                              "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                              "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                              "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                            : "r"(taddr));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    } else {
+                    for (int cb = 0; cb < 4; cb++) {
+                        uint32_t v[32];
+                        if (tl.nchunks > 0) {
+                            const uint32_t taddr = tmem + ((q * 32u) << 16) + buf * 256u + (uint32_t)(pl * 128 + cb * 32);
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                : "r"(taddr));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        } else {
 #pragma unroll
-                        for (int x = 0; x < 32; x++) v[x] = 0u;
-                    }
-                    if (store) {
-                        uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
+                            for (int x = 0; x < 32; x++) v[x] = 0u;
+                        }
+                        if (store) {
+                            uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
 #pragma unroll
-                        for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                            for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                        }
                     }
                 }
+                tcx_fence_before();
+                mbar_arrive_plain(&tmem_empty[buf]);
             }
-            tcx_fence_before();
-            mbar_arrive_plain(&tmem_empty);
         }
     }
     tcx_fence_before();
@@ -300,17 +313,49 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
-// ---- the walk: one thread per (template, window length), rows from the data end down ----
-template <bool HAS_C>
-__global__ void __launch_bounds__(TCX_WALK_THREADS)
+// ---- the walk: a warp per (32 window lengths, row segment), rows from the segment's end down ----
+// The recurrence is linear, so the rows of a column split into NSEG segments walked concurrently
+// (NSEG chosen by the host so that the launch fills the GPU; 1 when the batch alone does):
+// pass 1 walks every segment from a zero state (no output) and leaves its end value E_s in shared memory;
+// the state entering segment s is then  sum_{s' > s} rho^(p SEG (s' - s - 1)) E_s'  (Horner, a few terms);
+// pass 2 walks the segment again from that state and emits the cells.
+// Correction sums (HAS_C) are prefetched TCX_WALK_DEPTH rows ahead into a per-warp shared-memory ring with
+// 4-byte cp.async copies (each lane fetches and later reads its own column: no barrier, no registers held
+// across the HBM latency of a serial walk).
+#define TCX_WALK_DEPTH 12
+template <int NSEG>
+struct WalkCfg {
+    static constexpr int kCG = NSEG >= 4 ? 1 : 4 / NSEG;  // column groups (of 32 window lengths) per CTA
+    static constexpr int kWarps = NSEG * kCG;
+    static constexpr int kThreads = 32 * kWarps;
+    static constexpr int kEBytes = kWarps * TCW_NCH * 32 * 8;
+    static constexpr int kRingBytes = kWarps * TCX_WALK_DEPTH * TCW_NCH * 32 * 4;
+};
+
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool HAS_C, int NSEG>
+__global__ void __launch_bounds__(WalkCfg<NSEG>::kThreads)
 tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *__restrict__ Kn,
                     const TplMeta *__restrict__ meta, int t_base, MapWindow w, uint32_t i00, int32_t delta, uint32_t TAtom,
                     const float *__restrict__ C, uint32_t cpitch, float *__restrict__ Fmn,
                     unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
-    __shared__ unsigned long long red[TCX_WALK_THREADS / 32];
+    using Cfg = WalkCfg<NSEG>;
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    __shared__ unsigned long long red[Cfg::kWarps];
+    double(*E)[TCW_NCH][32] = reinterpret_cast<double(*)[TCW_NCH][32]>(walk_smem);  // [warp][channel][lane]
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
-    const uint32_t n = blockIdx.x * TCX_WALK_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int seg = wi % NSEG, cg = wi / NSEG;
+    const uint32_t n = (blockIdx.x * Cfg::kCG + cg) * 32 + lane;
     const bool active = n < w.N_tau;
     const float4 *Xt = reinterpret_cast<const float4 *>(X8 + (size_t)t * xpad * 8);
 
@@ -330,12 +375,17 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
     const float rL = (float)rhoL, rL2 = (float)(rhoL * rhoL);
     const float a0 = empty_win ? 0.0f : 1.0f;
 
+    // rows 0 .. R-1 (rows >= N_t0 lie beyond the map -- the canonical plan guarantees R >= N_t0 -- and
+    // give no output); segment `seg` owns rows [lo, hi)
+    const int R = (int)numAtoms - (int)i00;
+    const int SEG = (R + NSEG - 1) / NSEG;
+    const int lo = min(seg * SEG, R), hi = min(lo + SEG, R);
+
     double U[TCW_NCH];
 #pragma unroll
     for (int c = 0; c < TCW_NCH; c++) U[c] = 0.0;
 
     float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
-    const float *Ct = HAS_C ? C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + nn : nullptr;
     float best = -1.0f;
     uint32_t best_flat = 0;
     bool degenerate = false;
@@ -366,12 +416,12 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) {
             S[c] = (float)((c < 3 ? w02 : w0) * U[c]);
-            if (HAS_C) S[c] += cc[c];
+            if (HAS_C) S[c] += cc[c * 32];
         }
         const float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
         if (active) {
             if (Ft) Ft[(size_t)m * w.pitch + n] = F;
-            if (F > best) {
+            if (F >= best) {  // rows are walked downwards: among equal F the smaller row wins (np.argmax order)
                 best = F;
                 best_flat = (uint32_t)m * w.N_tau + n;
             }
@@ -379,41 +429,58 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
         }
     };
 
-    // rows beyond the map (the canonical plan guarantees i00 + N_t0 - 1 <= numAtoms - 1): no output
-    int m = (int)numAtoms - (int)i00 - 1;
-    for (; m >= (int)w.N_t0; m--) step(m);
-
-    if (HAS_C) {
-        // correction sums are fetched 4 rows ahead (HBM latency vs. the serial walk)
-        float cbuf[4][TCW_NCH];
-        const size_t cstride = (size_t)w.N_t0 * cpitch;
+    if (NSEG > 1) {
+        // ---- pass 1: the segment from a zero state (nobody needs the lowest segment's end value) ----
+        if (seg > 0)
+            for (int m = hi - 1; m >= lo; m--) step(m);
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int c = 0; c < TCW_NCH; c++) E[wi][c][lane] = U[c];
+        __syncthreads();
+        // ---- state entering the segment ----
+        const double rS = exp(-(double)SEG * (double)TAtom * inv_tau), rS2 = rS * rS;
 #pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) cbuf[u][c] = (m - u >= 0) ? __ldg(Ct + c * cstride + (size_t)(m - u) * cpitch) : 0.0f;
-        for (; m >= 3; m -= 4) {
+        for (int c = 0; c < TCW_NCH; c++) U[c] = 0.0;
+        for (int sp = NSEG - 1; sp > seg; sp--) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                step(m - u);
-                cell(m - u, cbuf[u]);
-                const int mn = m - u - 4;
-                if (mn >= 0) {
-#pragma unroll
-                    for (int c = 0; c < TCW_NCH; c++) cbuf[u][c] = __ldg(Ct + c * cstride + (size_t)mn * cpitch);
-                }
-            }
+            for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rS2 : rS, U[c], E[cg * NSEG + sp][c][lane]);
         }
-        // remaining 0..3 rows: cbuf[u] holds row m - u
-        if (m >= 0) { step(m); cell(m, cbuf[0]); }
-        if (m >= 1) { step(m - 1); cell(m - 1, cbuf[1]); }
-        if (m >= 2) { step(m - 2); cell(m - 2, cbuf[2]); }
+    }
+
+    // ---- pass 2: the segment (again) from its true state, with output ----
+    int m = hi - 1;
+    for (; m >= lo && m >= (int)w.N_t0; m--) step(m);
+    if (HAS_C) {
+        float(*ring)[TCW_NCH][32] =
+            reinterpret_cast<float(*)[TCW_NCH][32]>(walk_smem + Cfg::kEBytes + (size_t)wi * TCX_WALK_DEPTH * TCW_NCH * 32 * 4);
+        const float *Ct = C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + nn;
+        const size_t cstride = (size_t)w.N_t0 * cpitch;
+        const int m_top = m;
+        auto fetch = [&](int row, int slot) {
+            if (row >= lo) {
+#pragma unroll
+                for (int c = 0; c < TCW_NCH; c++) cp_async4(&ring[slot][c][lane], Ct + c * cstride + (size_t)row * cpitch);
+            }
+            cp_async_commit();  // one group per row, also when empty: the group count stays uniform
+        };
+#pragma unroll 1
+        for (int r = 0; r < TCX_WALK_DEPTH; r++) fetch(m_top - r, r);
+        int slot = 0;
+#pragma unroll 1
+        for (; m >= lo; m--) {
+            cp_async_wait<TCX_WALK_DEPTH - 1>();  // the oldest row in flight has landed
+            step(m);
+            cell(m, &ring[slot][0][lane]);
+            fetch(m - TCX_WALK_DEPTH, slot);
+            slot = slot + 1 == TCX_WALK_DEPTH ? 0 : slot + 1;
+        }
+        cp_async_wait<0>();
     } else {
-        for (; m >= 0; m--) {
+        for (; m >= lo; m--) {
             step(m);
             cell(m, nullptr);
         }
     }
     if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
     const unsigned long long key = (active && best > -1.0f) ? pack_key(best, best_flat) : 0ull;
-    block_atomic_max_key<TCX_WALK_THREADS / 32>(key, &maxkey[t], red);
+    block_atomic_max_key<Cfg::kWarps>(key, &maxkey[t], red);
 }

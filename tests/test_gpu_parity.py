@@ -178,9 +178,17 @@ FAST_CASES = [
 def test_tiled_kernels_within_tolerance(gpu, oracle, win, dets, n, gap, seed):
     b = synth_atoms(2, n, dets, seed=seed, gap_fraction=gap)
     w = canonical_window(win, 10**9, n)
-    res, F = run_gpu(gpu, b, w, 0)
+    # exponential window: the recurrence + tensor-core path (default on canonical grids, path 2) and
+    # the tiled direct sum (TCW_EXP_DIRECT, path 1)
+    modes = [(0, 2), (L.EXP_DIRECT, 1)] if win == "exp" else [(0, 1)]
+    for flags, want_path in modes:
+        _check_fast_case(gpu, oracle, b, w, win, flags, want_path)
+
+
+def _check_fast_case(gpu, oracle, b, w, win, flags, want_path):
+    res, F = run_gpu(gpu, b, w, flags)
     for t in range(b.T):
-        assert int(res["path"][t]) == 1, "canonical windows must take the tiled kernels"
+        assert int(res["path"][t]) == want_path, "canonical windows must take the fast kernels"
         o = oracle.compute_map(b.template(t), b.TAtom, w, allow_degenerate=True)
         Fo = o["F_mn"]
         rel = np.abs(F[t] - Fo) / np.maximum(np.abs(Fo), 1e-30)
@@ -530,7 +538,7 @@ def test_full_size_exp_120d_config4_shape(gpu, oracle):
     b = synth_atoms(1, n, ("H1", "L1"), seed=151)
     w = canonical_window("exp", 10**9, n)
     res, F = run_gpu(gpu, b, w, 0)
-    assert F.shape == (1, n - 1, n + 1) and int(res["status"][0]) == 0 and int(res["path"][0]) == 1
+    assert F.shape == (1, n - 1, n + 1) and int(res["status"][0]) == 0 and int(res["path"][0]) == 2
     flat = int(np.argmax(F[0]))
     assert (int(res["m_ML"][0]), int(res["n_ML"][0])) == divmod(flat, n + 1)
     assert float(res["maxF"][0]) == float(F[0].max())
@@ -613,9 +621,9 @@ def test_random_window_sweep_default_dispatch(gpu, oracle):
         o = oracle.compute_map(b.template(0), TA, w, allow_degenerate=True)
         Fo = o["F_mn"]
         rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
-        n_fast += int(res["path"][0])
+        n_fast += int(res["path"][0]) > 0
         n_exp += wtype == 2
-        n_exp_fast += (wtype == 2) and int(res["path"][0])
+        n_exp_fast += (wtype == 2) and int(res["path"][0]) > 0
         # two-detector data with gaps has single-detector (ill-conditioned) bins: allow the
         # documented O(eps cond) noise on the few cells near the conditioning cut
         bad = rel > RTOL
@@ -649,13 +657,105 @@ def test_full_size_oracle_parity_exp_30d(gpu, oracle):
     n = 1440
     b = synth_atoms(1, n, ("H1", "L1"), seed=171)
     w = canonical_window("exp", 10**9, n)
-    res, F = run_gpu(gpu, b, w, 0)
-    assert int(res["path"][0]) == 1
     o = oracle.compute_map(b.template(0), b.TAtom, w)
-    rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
-    assert rel.max() <= RTOL
-    assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
-    assert_records_match(res, 0, o, w)
+    for flags, want_path in ((0, 2), (L.EXP_DIRECT, 1)):  # recurrence + tensor cores / tiled direct sum
+        res, F = run_gpu(gpu, b, w, flags)
+        assert int(res["path"][0]) == want_path
+        rel = np.abs(F[0] - o["F_mn"]) / np.abs(o["F_mn"])
+        assert rel.max() <= RTOL
+        assert float(res["lnBtSG"][0]) == pytest.approx(o["lnBtSG"], abs=ATOL_LNB)
+        assert_records_match(res, 0, o, w)
+
+
+def _fp64_exp_map(X, TAtom, w, i00, delta, lut=None):
+    """FP64 direct sums of the exponential-window map on a canonical grid (rows one atom apart) and the
+    F-statistic from them in FP64: the yardstick for the recurrence.  X: [N, 7] merged atoms."""
+    N = X.shape[0]
+    N_t0, N_tau = w.t0Band // w.dt0 + 1, w.tauBand // w.dtau + 1
+    Xp = np.vstack([X.astype(np.float64), np.zeros((4 * N + 64, 7))])
+    F = np.empty((N_t0, N_tau))
+    for nn in range(N_tau):
+        tau = w.tau + nn * w.dtau
+        k = np.arange(0, 3 * tau // TAtom + 3)
+        t_rel = k * TAtom + delta
+        # atoms of the window: i in [i_t0, i_t1] with t0 <= t_i <= t1 (Exp.cu:27-65, 84-90)
+        x0r = w.t0 - 10**9 + TAtom // 2
+        Kn = (x0r + 3 * tau) // TAtom - 1 - i00
+        ok = (k <= Kn) & (t_rel >= 0) & (t_rel <= 3 * tau)
+        x = t_rel / tau
+        if lut is None:
+            wv = np.where(ok, np.exp(-x), 0.0)
+        else:
+            tab, xmax, length = lut
+            wv = np.where(ok, tab[np.minimum((x * (length / xmax) + 0.5).astype(np.int64), length)], 0.0)
+        S = np.empty((N_t0, 7))
+        for c in range(7):
+            S[:, c] = np.correlate(Xp[i00 : i00 + N_t0 + len(k) - 1, c], wv**2 if c < 3 else wv, mode="valid")[:N_t0]
+        A, B, C, Far, Fai, Fbr, Fbi = S.T
+        F[:, nn] = (B * (Far**2 + Fai**2) + A * (Fbr**2 + Fbi**2) - 2 * C * (Far * Fbr + Fai * Fbi)) / (A * B - C * C)
+    return F
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("off", [0, 400, -400, 900])
+def test_exp_recurrence_is_numerically_safe(gpu, oracle, off):
+    """north_star: "a recurrence is allowed only where it is shown to be numerically safe".  The FP64
+    recurrence down the rows (exact exponentials) and, in lookup-table mode, recurrence + TF32 tensor-core
+    correction are compared with FP64 DIRECT sums of the same weights: the recurrence must be at least as close to
+    them as the reference's sequential float32 sums (the oracle) are, up to the float32 rounding of the
+    F-statistic epilogue itself; with the tensor-core pass the error must stay below half the parity bar
+    (rms below 5 % of it).  Grids offset from the atom grid exercise delta != 0 (the first atom of a
+    window may lie before t0 and drop out)."""
+    n, TA = 700, 1800
+    b = synth_atoms(1, n, ("H1", "L1"), seed=1077 + off)
+    w = TransientWindowRange(2, 10**9 + off, (n - 3) * TA, TA, 2 * TA, n * TA, TA)
+    x0 = off + TA // 2
+    i00 = x0 // TA
+    delta = i00 * TA - off
+    o = oracle.compute_map(b.template(0), TA, w, exact_exp=True, allow_degenerate=True)
+    X = oracle.merged_to_matrix(o["merged"])
+    for exact in (True, False):
+        lut = None if exact else (oracle.exp_lut(),) + tuple(oracle.get_exp_lut())
+        truth = _fp64_exp_map(X, TA, w, i00, delta, lut)
+        oo = o if exact else oracle.compute_map(b.template(0), TA, w, allow_degenerate=True)
+        res, F = run_gpu(gpu, b, w, (L.EXP_EXACT if exact else 0) | L.ALLOW_DEGENERATE)
+        assert int(res["path"][0]) == 2
+        good = oo["F_mn"] != 2.0
+        err_gpu = np.abs(F[0] - truth)[good] / np.abs(truth[good])
+        err_ref = np.abs(oo["F_mn"] - truth)[good] / np.abs(truth[good])
+        if exact:  # pure recurrence: as good as the reference's own float32 sums
+            assert err_gpu.max() <= max(1.5 * err_ref.max(), 2e-6), (exact, err_gpu.max(), err_ref.max())
+            assert np.sqrt(np.mean(err_gpu**2)) <= max(1.5 * np.sqrt(np.mean(err_ref**2)), 5e-7), (exact,)
+        else:  # + the TF32 pass for the table's deviation (2^-11 roundings of a <= 2e-3 correction)
+            assert err_gpu.max() <= 0.5 * RTOL, (exact, err_gpu.max(), err_ref.max())
+            assert np.sqrt(np.mean(err_gpu**2)) <= 0.05 * RTOL, (exact, np.sqrt(np.mean(err_gpu**2)))
+        assert (np.abs(F[0] - oo["F_mn"])[good] / np.abs(oo["F_mn"][good])).max() <= RTOL
+
+
+@pytest.mark.gpu
+def test_exp_recurrence_ragged_templates_and_segments(gpu, oracle):
+    """Templates of different lengths (same first atom) in one launch, maps whose row count is not a
+    multiple of anything (row segments of the walk, 256-row tensor-core tiles, 128-column tiles with a
+    ragged edge), three detectors; recurrence path vs the oracle and vs the tiled direct sum, both modes."""
+    n, TA = 523, 1800
+    full = synth_atoms(3, n, ("H1", "L1", "V1"), seed=909)
+    tpls = [full.template(0), [a[: n - 9] for a in full.template(1)], [a[: n - 1] for a in full.template(2)]]
+    b = batch_from_detector_lists(tpls, TA)
+    w = TransientWindowRange(2, 10**9, (n - 12) * TA, TA, 3 * TA, 400 * TA, TA)
+    for exact in (0, L.EXP_EXACT):
+        res, F = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE)
+        resd, Fd = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE | L.EXP_DIRECT)
+        assert np.all(res["path"] == 2) and np.all(resd["path"] == 1)
+        for t in range(b.T):
+            o = oracle.compute_map(b.template(t), TA, w, exact_exp=bool(exact), allow_degenerate=True)
+            rel = np.abs(F[t] - o["F_mn"]) / np.maximum(np.abs(o["F_mn"]), 1e-30)
+            assert rel.max() <= RTOL, (t, exact, rel.max())
+            assert (np.abs(F[t] - Fd[t]) / np.abs(Fd[t])).max() <= RTOL
+            flat = int(np.argmax(F[t]))
+            assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
+            assert float(res["lnBtSG"][t]) == pytest.approx(
+                oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=not exact)["lnBtSG"], abs=ATOL_PASS)
+            assert int(res["status"][t]) == int(resd["status"][t])
 
 
 @pytest.mark.gpu

@@ -107,4 +107,4 @@ def test_batched_grid_search_on_gpu(oracle, tmp_path, win):
     s.run()
     check_against_oracle(s, oracle, rtol=1e-4)
     check_file_format(s, tmp_path)
-    assert np.all(s.records["path"] == 1) and np.all(s.records["status"] == 0)
+    assert np.all(s.records["path"] >= 1) and np.all(s.records["status"] == 0)

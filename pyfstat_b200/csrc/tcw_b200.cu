@@ -75,7 +75,8 @@ struct tcw_handle {
     // d_zero: everything a map needs zero-initialised -- max keys, lnBtSG marginals, flags, tile-queue
     // counters -- in ONE region, cleared by one memset per map
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
-        d_wins, d_tilemax, d_shift, d_G, d_C;
+        d_wins, d_tilemax, d_shift, d_G, d_C, d_scale;
+    int tc_f16 = 1;  // tensor-core pass of the exp window: FP16 operands (default) or TF32 ($TCW_TC_TF32=1)
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -362,7 +363,9 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     EXP_ATTR(ExpCfgC);
 #undef EXP_ATTR
     if (const char *v = getenv("TCW_EXP_VARIANT")) h->exp_variant = atoi(v);
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
+    if (const char *v = getenv("TCW_TC_TF32")) h->tc_f16 = atoi(v) ? 0 : 1;
 #define WALK_ATTR(NS)                                                                                              \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            WalkCfg<NS>::kEBytes + WalkCfg<NS>::kRingBytes))
@@ -384,7 +387,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_zero, &h->d_results, &h->d_W, &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins,
-                      &h->d_tilemax, &h->d_shift, &h->d_G, &h->d_C})
+                      &h->d_tilemax, &h->d_shift, &h->d_G, &h->d_C, &h->d_scale})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -891,8 +894,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     // in lookup-table mode), tcw_exp_rec.cuh; TCW_EXP_DIRECT keeps the tiled direct sum
     const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT);
     const bool exp_tc = exp_rec && !exact;
-    const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + TCX_SPAN - 1) / TCX_SPAN;
-    const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + 31) / 32 + 10;
+    const bool tc_f16 = h->tc_f16 != 0;
+    const uint32_t tc_rs = tc_f16 ? TcxCfg<true>::kRowStep : TcxCfg<false>::kRowStep, tc_kc = 8 * tc_rs, tc_span = 64 * tc_rs;
+    const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + tc_span - 1) / tc_span;
+    const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + tc_kc - 1) / tc_kc + 10;
+    const uint32_t tc_chunks = path == PATH_FAST && w.type == TCW_WINDOW_EXP ? (ep.KW + tc_kc - 1) / tc_kc : 0;
     const size_t tc_c_per_tpl = (size_t)TCW_NCH * w.N_t0 * tc_cpitch * sizeof(float);
 
     // ---- buffers ----
@@ -919,9 +925,10 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     }
     if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (28 B per cell): cap it at 4 GB
         S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (4ull << 30) / tc_c_per_tpl));
-        if ((uint64_t)S * tc_n_nt * tc_n_mb * 4ull >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
+        if ((uint64_t)S * tc_n_nt * tc_n_mb * tc_rs >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
         if ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl))) return rc;
-        if ((rc = ensure(h, h->d_G, (size_t)S * 2048 * tc_U * sizeof(float)))) return rc;
+        if ((rc = ensure(h, h->d_G, (size_t)S * tc_rs * 4 * tc_U * 512))) return rc;
+        if ((rc = ensure(h, h->d_scale, (size_t)S * 4 * sizeof(float)))) return rc;
     }
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
     if (want_fmn) {
@@ -1002,16 +1009,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     uint32_t exp_TM = 0, exp_TN = 0;
     exp_tile_dims(h->exp_variant, &exp_TM, &exp_TN);
     if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
-        const int kind = exp_tc ? 1 : exp_rec ? 2 : 0;
+        const int kind = exp_tc ? (tc_f16 ? 3 : 1) : exp_rec ? 2 : 0;
         const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
                          h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom && h->w_kind == kind &&
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
             size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
-            if (kind == 1) total = (size_t)tc_n_nt * (ep.KW / TCX_KC) * 4096;
+            if (kind == 1 || kind == 3) total = (size_t)tc_n_nt * tc_chunks * (TCX_TAUS * tc_kc);
             if (kind == 0 && (rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
-            if (kind == 1 && (rc = ensure(h, h->d_W, total * 2 * sizeof(float)))) return rc;
+            if ((kind == 1 || kind == 3) && (rc = ensure(h, h->d_W, (size_t)tc_n_nt * tc_chunks * 32768))) return rc;
             if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
             h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -1032,9 +1039,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 tcw_exp_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, eg, lut,
                                                              (int)exact);
             else if (kind == 1)
-                tcw_exptc_table_kernel<<<blocks, 256, 0, st>>>((float *)h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau,
-                                                               tc_n_nt, ep.KW / TCX_KC, w.tau, w.dtau, TAtom, ep.delta[0],
-                                                               lut);
+                tcw_exptc_table_kernel<false><<<blocks, 256, 0, st>>>(h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
+                                                                      tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
+            else if (kind == 3)
+                tcw_exptc_table_kernel<true><<<blocks, 256, 0, st>>>(h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
+                                                                     tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
             if (kind != 2) h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
@@ -1164,17 +1173,33 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         } else if (exp_rec) {
             const float *corr = nullptr;
             if (exp_tc) {
-                tcw_exptc_atoms_kernel<<<dim3(std::min<uint32_t>((2048u * tc_U + 255u) / 256u, 1024u), cnt), 256, 0, st>>>(
-                    (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0], tc_U,
-                    (float *)h->d_G.p);
-                h->launches++;
-                CUDA_TRY(h, cudaGetLastError());
-                const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * 4u;
+                const uint32_t g_elems = tc_rs * 4 * tc_U * 2 * (2 * tc_kc);
+                const dim3 g_grid(std::min<uint32_t>((g_elems + 255u) / 256u, 1024u), cnt);
+                const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * tc_rs;
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
-                tcw_exptc_map_kernel<<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
-                    (const float *)h->d_G.p, tc_U, (const float *)h->d_W.p, ep.KW / TCX_KC, (const int32_t *)h->d_Kn.p,
-                    (const TplMeta *)h->d_meta.p, t_base, (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles,
-                    (float *)h->d_C.p, tc_cpitch);
+                if (tc_f16) {
+                    tcw_exptc_scale_kernel<<<cnt, 256, 0, st>>>((const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p,
+                                                                t_base, (float *)h->d_scale.p);
+                    h->launches++;
+                    tcw_exptc_atoms_kernel<true><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
+                                                                         (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
+                                                                         tc_U, (const float *)h->d_scale.p, h->d_G.p);
+                    h->launches++;
+                    CUDA_TRY(h, cudaGetLastError());
+                    tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
+                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,
+                        (float *)h->d_C.p, tc_cpitch);
+                } else {
+                    tcw_exptc_atoms_kernel<false><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
+                                                                          (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
+                                                                          tc_U, nullptr, h->d_G.p);
+                    h->launches++;
+                    CUDA_TRY(h, cudaGetLastError());
+                    tcw_exptc_map_kernel<false><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
+                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, nullptr, (float *)h->d_C.p, tc_cpitch);
+                }
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
                 corr = (const float *)h->d_C.p;

@@ -41,13 +41,13 @@
 // (M128 N128 K8).  Warp roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C);
 // persistent CTAs, one per SM, static round-robin over tiles ordered by decreasing k range.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "tcw_common.cuh"
 #include "tcw_generic.cuh"
 
-#define TCX_KC 32        // k per stage
 #define TCX_TAUS 128     // window lengths per tile (MMA N)
-#define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + 4 i)
-#define TCX_SPAN 256     // map rows spanned by a tile
+#define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + rowstep i)
 #define TCX_STAGES 8
 #define TCX_A_BYTES 8192   // 2 pairs x 16 chunks x 256 B
 #define TCX_B_BYTES 16384  // 128 taus x 32 k x 4 B (one table)
@@ -61,58 +61,124 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// Operand precision of the tensor-core pass.  Both have an 11-bit significand; what differs is how many
+// elements a 16-byte core-matrix row holds, i.e. the atom stride between consecutive MMA rows:
+//   TF32: 4 -> row classes r = 0..3, tile rows m = m0 + r + 4 i, 32 k per 24-KB stage
+//   FP16: 8 -> row classes r = 0..7, tile rows m = m0 + r + 8 i, 64 k per 24-KB stage: twice the MACs per
+//         shared-memory byte, and shared-memory bandwidth is what bounds this kernel.
+// FP16's range is handled by exact power-of-two scaling: atoms per template and channel group to
+// [2^13, 2^14), weights by 2^12; the scale is undone on the FP32 accumulators in the epilogue.
+template <bool F16>
+struct TcxCfg {
+    static constexpr int kRowStep = F16 ? 8 : 4;    // elements per 16 bytes = atoms between MMA rows = row classes
+    static constexpr int kKC = 8 * kRowStep;        // k per stage (= atoms per 8-row group)
+    static constexpr int kSpan = 64 * kRowStep;     // map rows spanned by a tile
+    static constexpr int kChunk = 2 * kKC;          // elements per 256-byte chunk (8 rows' span + one stage of k)
+    static constexpr int kElem = F16 ? 2 : 4;
+    static constexpr size_t kTableElems = (size_t)TCX_TAUS * kKC;  // one table of one (nt, chunk): 16 KB
+};
+#define TCX_VSCALE_LOG2 12
+
 // channel of (pair p, slot c'): a2,b2 | ab,- | Fa_re,Fa_im | Fb_re,Fb_im ; -1 = unused slot
 __device__ __forceinline__ int tcx_channel(int p, int cp) {
     const int ch = 2 * p + cp - (p >= 2 ? 1 : 0);
     return (p == 1 && cp == 1) ? -1 : ch;
 }
 
-// ---- atoms in chunked TF32 form: G[tz][r][p][u][c'][64],  value = X_ch[i00 + r + 32 u + e] ----
+// per template: power-of-two scales of the two channel groups (a2,b2,ab | Fa,Fb).  scale[tz][0..1] multiplies the
+// atoms into [2^13, 2^14); scale[tz][2..3] undoes it (and the weights' 2^12) on the accumulators.
+__global__ void tcw_exptc_scale_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
+                                       int t_base, float *__restrict__ scale) {
+    __shared__ float red[2][8];
+    const int tz = blockIdx.x, t = t_base + tz;
+    const uint32_t numAtoms = meta[t].numAtoms;
+    float mx[2] = {0.0f, 0.0f};
+    for (int c = 0; c < TCW_NCH; c++)
+        for (uint32_t j = threadIdx.x; j < numAtoms; j += blockDim.x)
+            mx[c >= 3] = fmaxf(mx[c >= 3], fabsf(__ldg(X + ((size_t)t * TCW_NCH + c) * xpad + j)));
+    for (int g = 0; g < 2; g++) {
+        float v = mx[g];
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0) red[g][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float v = 0.0f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) v = fmaxf(v, red[threadIdx.x][i]);
+        int e = 0;
+        if (v > 0.0f && v < INFINITY) {
+            frexpf(v, &e);  // v = f 2^e, f in [0.5, 1)
+            e -= 14;        // v 2^-e in [2^13, 2^14)
+        }
+        e = max(-100, min(100, e));
+        scale[4 * tz + threadIdx.x] = ldexpf(1.0f, -e);
+        scale[4 * tz + 2 + threadIdx.x] = ldexpf(1.0f, e - TCX_VSCALE_LOG2);
+    }
+}
+
+// ---- atoms in chunked form: G[tz][r][p][u][c'][kChunk],  value = X_ch[i00 + r + kKC u + e] ----
+template <bool F16>
 __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
-                                       int t_base, uint32_t i00, uint32_t U, float *__restrict__ G) {
+                                       int t_base, uint32_t i00, uint32_t U, const float *__restrict__ scale,
+                                       void *__restrict__ Gv) {
+    using Cfg = TcxCfg<F16>;
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
-    const size_t per_tpl = (size_t)2048 * U;
+    const size_t per_tpl = (size_t)Cfg::kRowStep * 4 * U * 2 * Cfg::kChunk;
+    const float s2 = F16 ? scale[4 * tz] : 1.0f, s1 = F16 ? scale[4 * tz + 1] : 1.0f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_tpl; idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t e = (uint32_t)idx & 63u, cp = ((uint32_t)idx >> 6) & 1u;
-        size_t rest = idx >> 7;
+        const uint32_t e = (uint32_t)(idx % Cfg::kChunk);
+        size_t rest = idx / Cfg::kChunk;
+        const uint32_t cp = (uint32_t)rest & 1u;
+        rest >>= 1;
         const uint32_t u = (uint32_t)(rest % U);
         rest /= U;
         const uint32_t p = (uint32_t)rest & 3u, r = (uint32_t)rest >> 2;
         const int ch = tcx_channel((int)p, (int)cp);
-        const uint64_t j = (uint64_t)i00 + r + 32ull * u + e;
+        const uint64_t j = (uint64_t)i00 + r + (uint64_t)Cfg::kKC * u + e;
         float v = 0.0f;
-        if (ch >= 0 && j < numAtoms) v = tf32_rna(__ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j));
-        G[(size_t)tz * per_tpl + idx] = v;
+        if (ch >= 0 && j < numAtoms) v = __ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j);
+        if (F16) reinterpret_cast<__half *>(Gv)[(size_t)tz * per_tpl + idx] = __float2half_rn(v * (ch < 3 ? s2 : s1));
+        else reinterpret_cast<float *>(Gv)[(size_t)tz * per_tpl + idx] = tf32_rna(v);
     }
 }
 
-// ---- correction weights V = w_lut - w_exact (table 0) and w_lut^2 - w_exact^2 (table 1), TF32,
-//      in the MMA's canonical layout: Vt[nt][chunk][table][kq 8][ng 16][nr 8][kk 4] ----
-__global__ void tcw_exptc_table_kernel(float *__restrict__ Vt, const int32_t *__restrict__ Kn, uint32_t N_tau,
+// ---- correction weights V = w_lut - w_exact (table 0) and w_lut^2 - w_exact^2 (table 1) in the MMA's
+//      canonical layout: Vt[nt][chunk][table][kq 8][ng 16][nr 8][kk kRowStep] (FP16: times 2^12) ----
+template <bool F16>
+__global__ void tcw_exptc_table_kernel(void *__restrict__ Vtv, const int32_t *__restrict__ Kn, uint32_t N_tau,
                                        uint32_t n_nt, uint32_t n_chunks, uint32_t tau, uint32_t dtau, uint32_t TAtom,
                                        int32_t delta, const ExpLut lut) {
-    const size_t total = (size_t)n_nt * n_chunks * 4096;
+    using Cfg = TcxCfg<F16>;
+    constexpr uint32_t TE = (uint32_t)Cfg::kTableElems;
+    const size_t total = (size_t)n_nt * n_chunks * TE;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t off = (uint32_t)idx & 4095u;
-        const uint32_t kk = off & 3u, nr = (off >> 2) & 7u, ng = (off >> 5) & 15u, kq = off >> 9;
-        const size_t rest = idx >> 12;
+        const uint32_t off = (uint32_t)(idx % TE);
+        const uint32_t kk = off % Cfg::kRowStep, nr = (off / Cfg::kRowStep) & 7u, ng = (off / (8 * Cfg::kRowStep)) & 15u,
+                       kq = off / (128 * Cfg::kRowStep);
+        const size_t rest = idx / TE;
         const uint32_t chunk = (uint32_t)(rest % n_chunks), nt = (uint32_t)(rest / n_chunks);
-        const uint32_t k = chunk * TCX_KC + kq * 4 + kk, n = nt * TCX_TAUS + ng * 8 + nr;
-        float v1 = 0.0f, v2 = 0.0f;
+        const uint32_t k = chunk * Cfg::kKC + kq * Cfg::kRowStep + kk, n = nt * TCX_TAUS + ng * 8 + nr;
+        double v1 = 0.0, v2 = 0.0;
         if (n < N_tau && (int32_t)k <= Kn[n]) {
             const uint32_t tau_n = tau + n * dtau;
             const long long t_rel = (long long)k * TAtom + delta;  // t_i - t0_m
             if (t_rel >= 0 && t_rel <= (long long)TCW_EXP_EFOLDING * tau_n) {
                 const double x = __ddiv_rn((double)t_rel, (double)tau_n);
                 const double wl = fast_neg_exp_lut(x, lut), we = exp(-x);
-                v1 = tf32_rna((float)(wl - we));
-                v2 = tf32_rna((float)((wl - we) * (wl + we)));
+                v1 = wl - we;
+                v2 = (wl - we) * (wl + we);
             }
         }
-        float *base = Vt + rest * 8192;
-        base[off] = v1;
-        base[4096 + off] = v2;
+        if (F16) {
+            __half *base = reinterpret_cast<__half *>(Vtv) + rest * 2 * TE;
+            base[off] = __float2half_rn((float)ldexp(v1, TCX_VSCALE_LOG2));
+            base[TE + off] = __float2half_rn((float)ldexp(v2, TCX_VSCALE_LOG2));
+        } else {
+            float *base = reinterpret_cast<float *>(Vtv) + rest * 2 * TE;
+            base[off] = tf32_rna((float)v1);
+            base[TE + off] = tf32_rna((float)v2);
+        }
     }
 }
 
@@ -125,16 +191,24 @@ __device__ __forceinline__ uint64_t tcx_desc(uint32_t saddr, uint32_t lbo, uint3
     d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
     return d;
 }
-// kind::tf32, D = F32, A and B K-major
-__host__ __device__ constexpr uint32_t tcx_idesc(uint32_t M, uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// D = F32, A and B K-major; operand format 2 = TF32 (kind::tf32), 0 = F16 (kind::f16)
+__host__ __device__ constexpr uint32_t tcx_idesc(uint32_t M, uint32_t N, bool f16) {
+    return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+template <bool F16>
 __device__ __forceinline__ void tcx_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
 }
 __device__ __forceinline__ void tcx_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -147,22 +221,24 @@ struct TcxTile {
     uint32_t tz, r, mb, nt;
     int nchunks;
 };
+template <bool F16>
 __device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n_mb, uint32_t n_nt, const MapWindow &w,
                                             uint32_t i00, const TplMeta *__restrict__ meta, int t_base,
                                             const int32_t *__restrict__ Kn) {
+    using Cfg = TcxCfg<F16>;
     TcxTile tl;
     tl.tz = j % cnt;
     uint32_t rest = j / cnt;
-    tl.r = rest & 3u;
-    rest >>= 2;
+    tl.r = rest % Cfg::kRowStep;
+    rest /= Cfg::kRowStep;
     tl.mb = rest % n_mb;
     tl.nt = n_nt - 1u - rest / n_mb;  // widest windows first
     const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
     const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
-    const long long s_first = (long long)i00 + (long long)tl.mb * TCX_SPAN + tl.r;
+    const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan + tl.r;
     const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
-    const bool rows = tl.mb * TCX_SPAN + tl.r < w.N_t0;
-    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + TCX_KC - 1) / TCX_KC) : 0;
+    const bool rows = tl.mb * Cfg::kSpan + tl.r < w.N_t0;
+    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
     return tl;
 }
 
@@ -170,16 +246,20 @@ __device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n
 // A tile is processed as two UNITS -- channel pairs (a2,b2 | ab,-) with the w^2 table, then (Fa | Fb) with
 // the w table; no operand is shared between them, so the split costs no traffic -- each accumulating into
 // one half of TMEM (2 x 128 columns): the epilogue warps drain unit u while the MMAs of unit u + 1 run.
+template <bool F16>
 __global__ void __launch_bounds__(TCX_THREADS, 1)
-tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__restrict__ Vt, uint32_t n_chunks_tab,
+tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__restrict__ Vtv, uint32_t n_chunks_tab,
                      const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
-                     MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles, float *__restrict__ C,
-                     uint32_t cpitch) {
+                     MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles,
+                     const float *__restrict__ scale, float *__restrict__ C, uint32_t cpitch) {
+    using Cfg = TcxCfg<F16>;
     extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
     __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned char *G = reinterpret_cast<const unsigned char *>(Gv);
+    const unsigned char *Vt = reinterpret_cast<const unsigned char *>(Vtv);
 
     if (tid == 0) {
 #pragma unroll
@@ -208,9 +288,10 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
         if (lane == 0) {  // ---- TMA producer ----
             uint32_t it = 0;
             for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-                const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-                const float *gA = G + (((size_t)tl.tz * 4 + tl.r) * 4 * U + 8ull * tl.mb) * 128;  // + (p U + c) * 128
-                const float *gB = Vt + (size_t)tl.nt * n_chunks_tab * 8192;                     // + c * 8192 (+ 4096: w^2)
+                const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                // chunks are 256 B; a stage's A operand of pair p: 16 chunks (8 u x 2 c') = 4 KB at u = 8 mb + c
+                const unsigned char *gA = G + (((size_t)tl.tz * Cfg::kRowStep + tl.r) * 4 * U + 8ull * tl.mb) * 512;  // + (p U + c) * 512
+                const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768;  // + c * 32 KB (+ 16 KB: w^2)
                 for (int hh = 0; hh < 2; hh++)
                     for (int c = 0; c < tl.nchunks; c++, it++) {
                         const uint32_t s = it % TCX_STAGES;
@@ -219,19 +300,19 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
                         mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
 #pragma unroll
                         for (int pl = 0; pl < 2; pl++)
-                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 128, 4096, &full[s]);
-                        bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 8192 + (hh == 0 ? 4096 : 0), TCX_B_BYTES, &full[s]);
+                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 512, 4096, &full[s]);
+                        bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX_B_BYTES, &full[s]);
                     }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
-            constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS);
+            constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS, F16);
             const uint64_t da = tcx_desc(0, 16, 256);      // A: K halves 16 B apart, 8-row groups = chunks 256 B apart
-            const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][4]: K quarters 2 KB apart, 8-column groups 128 B
+            const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][16 B]: K steps 2 KB apart, 8-column groups 128 B
             uint32_t it = 0, unit = 0;
             for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-                const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
                 for (int hh = 0; hh < 2; hh++, unit++) {
                     const uint32_t buf = unit & 1u;
                     mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
@@ -243,12 +324,12 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
                         tcx_fence_after();
                         const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
 #pragma unroll
-                        for (int q = 0; q < TCX_KC / 8; q++) {
+                        for (int q = 0; q < 4; q++) {  // 32 bytes of K per MMA: 8 TF32 / 16 FP16 values
                             const uint64_t bd = db | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
 #pragma unroll
                             for (int pl = 0; pl < 2; pl++) {
                                 const uint64_t ad = da | (uint64_t)(((a0 + pl * 4096 + q * 32) >> 4) & 0x3FFF);
-                                tcx_mma(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
+                                tcx_mma<F16>(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
                             }
                         }
                         tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
@@ -264,10 +345,11 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
         const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
         uint32_t unit = 0;
         for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-            const TcxTile tl = tcx_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-            const uint32_t m = tl.mb * TCX_SPAN + tl.r + 4 * i;
+            const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+            const uint32_t m = tl.mb * Cfg::kSpan + tl.r + Cfg::kRowStep * i;
             for (int hh = 0; hh < 2; hh++, unit++) {
                 const uint32_t buf = unit & 1u;
+                const float undo = F16 ? scale[4 * tl.tz + 2 + hh] : 1.0f;
                 mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
                 tcx_fence_after();
 #pragma unroll 1
@@ -291,6 +373,10 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
                                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                                 : "r"(taddr));
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            if (F16) {
+#pragma unroll
+                                for (int x = 0; x < 32; x++) v[x] = __float_as_uint(__uint_as_float(v[x]) * undo);
+                            }
                         } else {
 #pragma unroll
                             for (int x = 0; x < 32; x++) v[x] = 0u;
@@ -320,8 +406,9 @@ tcw_exptc_map_kernel(const float *__restrict__ G, uint32_t U, const float *__res
 // the state entering segment s is then  sum_{s' > s} rho^(p SEG (s' - s - 1)) E_s'  (Horner, a few terms);
 // pass 2 walks the segment again from that state and emits the cells.
 // Correction sums (HAS_C) are prefetched TCX_WALK_DEPTH rows ahead into a per-warp shared-memory ring with
-// 4-byte cp.async copies (each lane fetches and later reads its own column: no barrier, no registers held
-// across the HBM latency of a serial walk).
+// 16-byte cp.async.cg copies (a row of a warp = 7 channels x 128 B = 56 pieces, two per lane): no registers
+// held across the HBM latency of a serial walk, and the stream bypasses L1, which holds the atoms.  The
+// two atom records of the next row are fetched one row ahead.
 #define TCX_WALK_DEPTH 12
 template <int NSEG>
 struct WalkCfg {
@@ -332,8 +419,8 @@ struct WalkCfg {
     static constexpr int kRingBytes = kWarps * TCX_WALK_DEPTH * TCW_NCH * 32 * 4;
 };
 
-__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -390,18 +477,27 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
     uint32_t best_flat = 0;
     bool degenerate = false;
 
-    auto step = [&](int m) {
+    // atom records of a row: X[s + ka] (entering the window) and X[s + kb + 1] (leaving it)
+    float4 nlo0, nhi0, nlo1, nhi1;
+    auto load_row = [&](int m) {
+        nlo0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        nhi0 = nlo0; nlo1 = nlo0; nhi1 = nlo0;
+        if (m < 0) return;
         const uint32_t s = i00 + (uint32_t)m;
         const uint32_t j0 = s + ka, j1 = s + (uint32_t)(kb + 1);
-        float4 lo0 = make_float4(0.f, 0.f, 0.f, 0.f), hi0 = lo0, lo1 = lo0, hi1 = lo0;
         if (j0 < numAtoms) {
-            lo0 = __ldg(Xt + 2 * (size_t)j0);
-            hi0 = __ldg(Xt + 2 * (size_t)j0 + 1);
+            nlo0 = __ldg(Xt + 2 * (size_t)j0);
+            nhi0 = __ldg(Xt + 2 * (size_t)j0 + 1);
         }
         if (!empty_win && j1 < numAtoms) {
-            lo1 = __ldg(Xt + 2 * (size_t)j1);
-            hi1 = __ldg(Xt + 2 * (size_t)j1 + 1);
+            nlo1 = __ldg(Xt + 2 * (size_t)j1);
+            nhi1 = __ldg(Xt + 2 * (size_t)j1 + 1);
         }
+    };
+    // step(m): consumes the records fetched for row m and fetches those of row m - 1
+    auto step = [&](int m) {
+        const float4 lo0 = nlo0, hi0 = nhi0, lo1 = nlo1, hi1 = nhi1;
+        load_row(m - 1);
         // d = X[s + ka] - rho^(pL) X[s + kb + 1] in FP32 (one rounding), U = rho^p U + d in FP64
         U[0] = fma(rho2, U[0], (double)fmaf(-rL2, lo1.x, a0 * lo0.x));
         U[1] = fma(rho2, U[1], (double)fmaf(-rL2, lo1.y, a0 * lo0.y));
@@ -431,8 +527,10 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
 
     if (NSEG > 1) {
         // ---- pass 1: the segment from a zero state (nobody needs the lowest segment's end value) ----
-        if (seg > 0)
+        if (seg > 0) {
+            load_row(hi - 1);
             for (int m = hi - 1; m >= lo; m--) step(m);
+        }
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) E[wi][c][lane] = U[c];
         __syncthreads();
@@ -448,17 +546,20 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
 
     // ---- pass 2: the segment (again) from its true state, with output ----
     int m = hi - 1;
+    load_row(m);
     for (; m >= lo && m >= (int)w.N_t0; m--) step(m);
     if (HAS_C) {
         float(*ring)[TCW_NCH][32] =
             reinterpret_cast<float(*)[TCW_NCH][32]>(walk_smem + Cfg::kEBytes + (size_t)wi * TCX_WALK_DEPTH * TCW_NCH * 32 * 4);
-        const float *Ct = C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + nn;
         const size_t cstride = (size_t)w.N_t0 * cpitch;
+        // piece q = lane, lane + 32 of a row: channel q / 8, columns 4 (q % 8) .. + 3 of the warp's 32
+        const float *Cp0 = C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + (size_t)(n - lane) + (size_t)(lane >> 3) * cstride + 4 * (lane & 7);
+        const float *Cp1 = Cp0 + 4 * cstride;
         const int m_top = m;
         auto fetch = [&](int row, int slot) {
             if (row >= lo) {
-#pragma unroll
-                for (int c = 0; c < TCW_NCH; c++) cp_async4(&ring[slot][c][lane], Ct + c * cstride + (size_t)row * cpitch);
+                cp_async16(&ring[slot][lane >> 3][4 * (lane & 7)], Cp0 + (size_t)row * cpitch);
+                if (lane < 24) cp_async16(&ring[slot][4 + (lane >> 3)][4 * (lane & 7)], Cp1 + (size_t)row * cpitch);
             }
             cp_async_commit();  // one group per row, also when empty: the group count stays uniform
         };
@@ -467,9 +568,11 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
         int slot = 0;
 #pragma unroll 1
         for (; m >= lo; m--) {
-            cp_async_wait<TCX_WALK_DEPTH - 1>();  // the oldest row in flight has landed
+            cp_async_wait<TCX_WALK_DEPTH - 1>();  // the oldest row in flight has landed (this lane's pieces)
+            __syncwarp();                         // ... and every other lane's
             step(m);
             cell(m, &ring[slot][0][lane]);
+            __syncwarp();  // all lanes have read the slot before it is refilled
             fetch(m - TCX_WALK_DEPTH, slot);
             slot = slot + 1 == TCX_WALK_DEPTH ? 0 : slot + 1;
         }

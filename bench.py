@@ -106,6 +106,16 @@ def measured_peaks():
     return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
+def measured_tensor_peaks():
+    """Dense 16-bit tensor-core peaks (TFLOP/s): (burst, sustained, source)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), \
+            "MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 8192^3: burst / sustained; kind::f16 runs at the bf16 rate)"
+    return 2250.0, 2250.0, "nominal dense bf16 of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
 
@@ -186,6 +196,8 @@ def workload_config(spec):
         "cells_per_template": spec["cells"],
         "l2": "L2 flushed (256 MiB memset) between timed steps, outside the CUDA events",
         "exp_mode": "lal_lut",
+        "exp_path": ("FP64 recurrence down the rows + tcgen05 FP16 pass for the lookup table's deviation from the exact "
+                     "exponential (default on canonical grids; TCW_EXP_DIRECT = tiled direct sum)"),
     }
 
 
@@ -304,8 +316,28 @@ def timed_steps(h, w, flags, steps, warmup):
         t = h.timer_stop()
         if i >= warmup:
             ms.append(t)
-            stages.append(h.last_stage_ms())
+            st = h.last_stage_ms()
+            st.update({"map_" + k: v for k, v in h.last_exp_stage_ms().items()})
+            stages.append(st)
     return ms, stages
+
+
+def exp_split(stages):
+    return {k: statistics.mean(s["map_" + k] for s in stages) for k in ("operands", "tensor", "walk")}
+
+
+def exp_variants(h, L, spec, T, peaks, steps=2, warmup=1):
+    """The same resident batch through the other exponential-window paths: exact exponentials (the reference's
+    pycuda semantics: pure FP64 recurrence) and the tiled direct sum (TCW_EXP_DIRECT, round 1's FFMA2 kernel)."""
+    out = {}
+    for name, fl in (("exact_exp_recurrence", L.WANT_BTSG | L.EXP_EXACT), ("lut_direct_sum", L.WANT_BTSG | L.EXP_DIRECT)):
+        ms, stages = timed_steps(h, spec["w"], fl, steps, warmup)
+        map_ms = statistics.mean(s["map"] for s in stages)
+        out[name] = {"cells_per_s": T * spec["cells"] / (statistics.mean(ms) * 1e-3), "ms_per_step": statistics.mean(ms),
+                     "ms_per_template": statistics.mean(ms) / T, "steps": steps, "stage_ms": mean_stage(stages)}
+        if name == "lut_direct_sum":
+            out[name]["roofline"] = exp_roofline(spec, T, map_ms, peaks)
+    return out
 
 
 def pinned_batch(L, T, spec, seed):
@@ -328,10 +360,33 @@ def mean_stage(stages):
     return {k: statistics.mean(s[k] for s in stages) for k in stages[0]}
 
 
+def exp_rec_roofline(spec, T, xs, hbm_peak, hbm_src):
+    """Rooflines of the exponential window's default path (tcw_exp_rec.cuh): the tensor-core pass for the
+    lookup table's deviation from the exact exponential (dominant kernel) and the FP64 walk."""
+    burst, sustained, src = measured_tensor_peaks()
+    tc_flop = 14 * spec["visits"]  # 7 channel MACs per atom visit; the kernel issues 8/7 of that plus tile padding
+    achieved = T * tc_flop / (xs["tensor"] * 1e-3) / 1e12
+    walk_bytes = (28 + 4) * spec["cells"]  # correction sums in (7 x FP32), F_mn out (the lnBtSG pass re-reads it)
+    walk = T * walk_bytes / (xs["walk"] * 1e-3) / 1e9
+    return {
+        "bound": "tensor", "kernel": "tcw_exptc_map_kernel<FP16>", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+        "frac": achieved / burst, "frac_of_sustained_peak": achieved / sustained, "peak_sustained": sustained,
+        "traffic": measured_traffic(spec["name"], T), "peak_source": src,
+        "algorithmic_flop_per_template": tc_flop, "atom_visits_per_template": spec["visits"],
+        "launch_ms": xs["tensor"],
+        "note": ("algorithmic flop = 2 x 7 channels x atom visits of the map (the direct sum's MAC count); the kernel is "
+                 "bounded by shared-memory operand bandwidth (SS-mode M128 N128 MMAs read 128 B/clk), DESIGN.md section 5"),
+        "walk_kernel": {"bound": "hbm", "kernel": "tcw_exp_walk_kernel", "achieved": walk, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": walk / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_template": walk_bytes,
+                        "launch_ms": xs["walk"]},
+        "operand_prep_ms": xs["operands"],
+    }
+
+
 def exp_roofline(spec, T, map_ms, peaks):
     achieved = T * spec["alg_flop"] / (map_ms * 1e-3) / 1e12
     return {
-        "bound": "fp32", "kernel": "tcw_exp_map_kernel", "achieved": achieved,
+        "bound": "fp32", "kernel": "tcw_exp_map_canon_kernel (TCW_EXP_DIRECT)", "achieved": achieved,
         "peak": peaks["ffma_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["ffma_tflops"],
         "frac_of_nominal_74.4": achieved / 74.4,
         "traffic": measured_traffic(spec["name"], T),
@@ -469,7 +524,7 @@ def run_gpu(args):
     hbm_peak, hbm_src = measured_peaks()
     if rank == 0:
         if spec["window"] == "exp":
-            roofline = exp_roofline(spec, hi - lo, map_ms, peaks)
+            roofline = exp_rec_roofline(spec, hi - lo, exp_split(stages), hbm_peak, hbm_src)
         else:
             achieved = T * spec["alg_bytes"] / (map_ms * 1e-3) / 1e9
             roofline = {
@@ -490,7 +545,8 @@ def run_gpu(args):
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "f32 (f64 prefix sums / table indices, fixed-point lnBtSG marginals)",
+            "dtype": "f32 (f64 recurrences / prefix sums / table indices, f16 tensor-core correction pass with f32 "
+                     "accumulation, fixed-point lnBtSG marginals)",
             "data": "synthetic",
             "config": workload_config(spec),
             "clocks": dict(clocks, remeasured=remeasured),
@@ -511,6 +567,8 @@ def run_gpu(args):
         }
         if strong:
             line["strong"] = strong
+        if spec["window"] == "exp" and not args.no_secondary:
+            line["other_paths"] = exp_variants(h, L, spec, hi - lo, peaks)
         if not args.no_secondary and world == 1 and args.workload == "exp120":
             line["configs"] = secondary_configs(h, L, hbm_peak, hbm_src, peaks, local_rank)
         if not args.no_cpu and world == 1:
@@ -593,7 +651,8 @@ def sec_exp30(h, L, peaks, steps=10, warmup=3):
         "e2e": {"value": T * spec["cells"] / statistics.mean(times), "unit": "cells/s",
                 "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(T * L.RESULT_DTYPE.itemsize),
                 "api": "tcw_map_batch (C ABI), pinned host atoms in, records out"},
-        "roofline": exp_roofline(spec, T, map_ms, peaks), "stage_ms": mean_stage(stages), "config": workload_config(spec),
+        "roofline": exp_rec_roofline(spec, T, exp_split(stages), *measured_peaks()), "stage_ms": mean_stage(stages),
+        "other_paths": exp_variants(h, L, spec, T, peaks), "config": workload_config(spec),
     }
 
 

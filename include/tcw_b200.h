@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define TCW_ABI_VERSION 2
+#define TCW_ABI_VERSION 3
 
 /* lalpulsar transientWindowType_t values used by the reference
  * (tcw:691-697, 742-743, 793-807; pyfstat/core.py:828-840).  lalpulsar is not importable
@@ -240,6 +240,10 @@ int tcw_timer_stop(tcw_handle *h, float *milliseconds); /* synchronises the stop
  * stream: [0] prep (merge+scan), [1] weight table, [2] map kernel, [3] BtSG pass,
  * [4] finalize.  Synchronises. */
 int tcw_last_stage_ms(tcw_handle *h, float ms[5]);
+/* The map stage of the last call, split for the exponential window's recurrence path (tcw_exp_rec.cuh):
+ * [0] operand preparation (scales + chunked atoms), [1] tensor-core pass, [2] the walk (recurrence + F-stat
+ * epilogue).  All zero when the last map took another path.  Synchronises. */
+int tcw_last_exp_stage_ms(tcw_handle *h, float ms[3]);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 uint64_t tcw_launch_count(const tcw_handle *h);
 /* Writes a buffer larger than L2 (256 MiB) on the handle's stream. */

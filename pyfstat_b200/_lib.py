@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # $PYFSTAT_B200_LIB: another build of the same library (development: kernel variants side by side)
 LIB_PATH = os.environ.get("PYFSTAT_B200_LIB") or os.path.join(PKG, "libtcw_b200.so")
 
-TCW_ABI_VERSION = 2
+TCW_ABI_VERSION = 3
 
 # flags (include/tcw_b200.h)
 WANT_FMN = 0x1
@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = (
     "tcw_abi_version", "tcw_create", "tcw_destroy", "tcw_last_error", "tcw_device_name",
     "tcw_map_dims", "tcw_map_batch", "tcw_map_batch_windows", "tcw_submit", "tcw_wait", "tcw_upload_atoms", "tcw_map_resident", "tcw_fetch_results",
     "tcw_fetch_fmn", "tcw_fetch_merged", "tcw_synchronize", "tcw_timer_start", "tcw_timer_stop",
-    "tcw_last_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
+    "tcw_last_stage_ms", "tcw_last_exp_stage_ms", "tcw_launch_count", "tcw_flush_l2", "tcw_microbench", "tcw_microbench_ffma2",
     "tcw_host_alloc",
     "tcw_host_free", "tcw_cell_index_range", "tcw_set_exp_lut", "tcw_get_exp_lut",
     "tcw_device_count", "tcw_device_name_of", "tcw_results_device",
@@ -139,6 +139,7 @@ def load_library(build_if_missing: bool = True):
     L.tcw_timer_start.argtypes = [vp]
     L.tcw_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.tcw_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.tcw_last_exp_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.tcw_launch_count.argtypes = [vp]
     L.tcw_launch_count.restype = C.c_uint64
     L.tcw_flush_l2.argtypes = [vp]
@@ -425,6 +426,13 @@ class Handle:
         ms = (C.c_float * 5)()
         self._check(self.L.tcw_last_stage_ms(self._h, ms))
         return dict(zip(("prep", "table", "map", "btsg", "finalize"), (float(x) for x in ms)))
+
+    def last_exp_stage_ms(self):
+        """The map stage of the last call split for the exponential window's recurrence path: operand
+        preparation, tensor-core pass, walk (all zero when another path ran)."""
+        ms = (C.c_float * 3)()
+        self._check(self.L.tcw_last_exp_stage_ms(self._h, ms))
+        return dict(zip(("operands", "tensor", "walk"), (float(x) for x in ms)))
 
     @property
     def launch_count(self) -> int:

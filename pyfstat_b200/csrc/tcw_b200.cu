@@ -51,6 +51,8 @@ struct tcw_handle {
     cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};  // start, prep, table, loops end... finalize
     cudaEvent_t ev_fin = nullptr;
     std::vector<cudaEvent_t> ev_sub;  // 3 per sub-batch: map begin, map end, btsg end
+    std::vector<cudaEvent_t> ev_x;    // 2 per sub-batch (exp recurrence path): operands ready, tensor-core pass done
+    bool x_valid = false;
     int n_sub_last = 0;
     bool stage_valid = false;
     std::string err;
@@ -75,7 +77,7 @@ struct tcw_handle {
     // d_zero: everything a map needs zero-initialised -- max keys, lnBtSG marginals, flags, tile-queue
     // counters -- in ONE region, cleared by one memset per map
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
-        d_wins, d_tilemax, d_shift, d_G, d_C, d_scale;
+        d_wins, d_tilemax, d_shift, d_G, d_C, d_scale, d_Xd;
     int tc_f16 = 1;  // tensor-core pass of the exp window: FP16 operands (default) or TF32 ($TCW_TC_TF32=1)
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
@@ -368,7 +370,9 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     if (const char *v = getenv("TCW_TC_TF32")) h->tc_f16 = atoi(v) ? 0 : 1;
 #define WALK_ATTR(NS)                                                                                              \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           WalkCfg<NS>::kEBytes + WalkCfg<NS>::kRingBytes))
+                                           WalkCfg<NS>::smem(true)));                                                  \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<false, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           WalkCfg<NS>::smem(false)))
     WALK_ATTR(1);
     WALK_ATTR(2);
     WALK_ATTR(4);
@@ -387,7 +391,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->d_atoms, &h->d_natoms, &h->d_meta, &h->d_X, &h->d_X8, &h->d_P, &h->d_Fmn, &h->d_scratch,
                       &h->d_zero, &h->d_results, &h->d_W, &h->d_Kn, &h->d_lut, &h->d_flush, &h->d_wins,
-                      &h->d_tilemax, &h->d_shift, &h->d_G, &h->d_C, &h->d_scale})
+                      &h->d_tilemax, &h->d_shift, &h->d_G, &h->d_C, &h->d_scale, &h->d_Xd})
         release(*b);
     for (auto ev : h->ev_timer)
         if (ev) cudaEventDestroy(ev);
@@ -399,6 +403,7 @@ extern "C" int tcw_destroy(tcw_handle *h) {
     for (auto p : h->hp_small)
         if (p) cudaFreeHost(p);
     for (auto ev : h->ev_sub) cudaEventDestroy(ev);
+    for (auto ev : h->ev_x) cudaEventDestroy(ev);
     for (auto ev : h->ev_up) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -923,8 +928,13 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         if (const char *env = getenv("TCW_UPLOAD_CHUNKS")) chunks = std::max(1, atoi(env));
         S = std::min(S, std::max(8, (T + chunks - 1) / chunks));
     }
-    if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (28 B per cell): cap it at 4 GB
-        S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, (4ull << 30) / tc_c_per_tpl));
+    if (exp_rec) {  // FP64 copies of the atoms for the walk
+        if ((rc = ensure(h, h->d_Xd, (size_t)T * TCW_NCH * h->xpad * sizeof(double)))) return rc;
+    }
+    if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (28 B per cell): cap it at 8 GB
+        size_t cap = 8ull << 30;
+        if (const char *env = getenv("TCW_EXP_SCRATCH_MB")) cap = std::max<size_t>(64, (size_t)atoll(env)) << 20;
+        S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, cap / tc_c_per_tpl));
         if ((uint64_t)S * tc_n_nt * tc_n_mb * tc_rs >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
         if ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl))) return rc;
         if ((rc = ensure(h, h->d_G, (size_t)S * tc_rs * 4 * tc_U * 512))) return rc;
@@ -979,6 +989,12 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         CUDA_TRY(h, cudaEventCreate(&ev));
         h->ev_sub.push_back(ev);
     }
+    while (exp_rec && (int)h->ev_x.size() < 2 * n_sub) {
+        cudaEvent_t ev;
+        CUDA_TRY(h, cudaEventCreate(&ev));
+        h->ev_x.push_back(ev);
+    }
+    h->x_valid = false;
 
     // the zero-initialised region (one memset): 256-byte aligned sub-arrays
     size_t zero_bytes = 0;
@@ -1172,6 +1188,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
 #undef LAUNCH_RECT
         } else if (exp_rec) {
             const float *corr = nullptr;
+            tcw_exp_atoms_f64_kernel<<<dim3((h->xpad + 255) / 256, cnt), 256, 0, st>>>(
+                (const float *)h->d_X.p, h->xpad, t_base, (double *)h->d_Xd.p);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+            if (!exp_tc) {
+                CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb], st));
+                CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
+            }
             if (exp_tc) {
                 const uint32_t g_elems = tc_rs * 4 * tc_U * 2 * (2 * tc_kc);
                 const dim3 g_grid(std::min<uint32_t>((g_elems + 255u) / 256u, 1024u), cnt);
@@ -1184,38 +1208,43 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                     tcw_exptc_atoms_kernel<true><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
                                                                          (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
                                                                          tc_U, (const float *)h->d_scale.p, h->d_G.p);
-                    h->launches++;
-                    CUDA_TRY(h, cudaGetLastError());
-                    tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
-                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,
-                        (float *)h->d_C.p, tc_cpitch);
                 } else {
                     tcw_exptc_atoms_kernel<false><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
                                                                           (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
                                                                           tc_U, nullptr, h->d_G.p);
-                    h->launches++;
-                    CUDA_TRY(h, cudaGetLastError());
-                    tcw_exptc_map_kernel<false><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
-                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, nullptr, (float *)h->d_C.p, tc_cpitch);
                 }
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
+                CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb], st));
+                if (tc_f16)
+                    tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
+                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,
+                        (float *)h->d_C.p, tc_cpitch);
+                else
+                    tcw_exptc_map_kernel<false><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
+                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, nullptr, (float *)h->d_C.p, tc_cpitch);
+                h->launches++;
+                CUDA_TRY(h, cudaGetLastError());
+                CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
                 corr = (const float *)h->d_C.p;
             }
-            // row segments per column: enough threads to fill the GPU (pass 1 of the segmented walk costs
-            // about a third of a walk, so none when the batch alone fills it)
+            // row segments per column: measured (B200, 120-d maps): with 8 templates (46 000 columns) one
+            // segment is fastest (1.80 ms; 2: 1.89, 4: 2.01, 8: 2.15 -- pass 1 of the segmented walk costs more
+            // than the extra warps bring); with 4 templates 2-8 segments tie.  So: segments only until the
+            // launch has ~256 columns per SM.
             int nseg = 1;
-            while (nseg < 8 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 1280) nseg *= 2;
+            while (nseg < 8 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 256) nseg *= 2;
             if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(8, atoi(env)));
 #define LAUNCH_WALK(HASC, NS)                                                                                      \
     do {                                                                                                           \
         using WC = WalkCfg<NS>;                                                                                    \
-        const size_t smem = (NS > 1 || HASC ? WC::kEBytes : 0) + (HASC ? WC::kRingBytes : 0);                      \
+        const size_t smem = WC::smem(HASC);                                                                        \
         dim3 grid((w.N_tau + 32 * WC::kCG - 1) / (32 * WC::kCG), cnt);                                             \
         tcw_exp_walk_kernel<HASC, NS><<<grid, WC::kThreads, smem, st>>>(                                           \
-            (const float *)h->d_X8.p, h->xpad, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base, w, \
+            (const double *)h->d_Xd.p, h->xpad, (const int32_t *)h->d_Kn.p,                                        \
+            (const TplMeta *)h->d_meta.p, t_base, w,                                                               \
             ep.ec.i00[0], ep.delta[0], TAtom, corr, tc_cpitch, fmn, p_maxkey, p_flags);                            \
     } while (0)
             if (exp_tc) {
@@ -1293,6 +1322,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaEventRecord(h->ev_fin, st));
     h->n_sub_last = n_sub;
+    h->x_valid = exp_rec;
     h->stage_valid = true;
     h->have_fmn = want_fmn;
     h->last_N_t0 = w.N_t0;
@@ -1321,6 +1351,24 @@ static int map_impl(tcw_handle *h, const tcw_window_range *win, uint32_t flags, 
 
 extern "C" int tcw_map_resident(tcw_handle *h, const tcw_window_range *win, uint32_t flags) {
     return map_impl(h, win, flags, nullptr);
+}
+
+extern "C" int tcw_last_exp_stage_ms(tcw_handle *h, float ms[3]) {
+    if (!h || !ms) return TCW_E_INVALID;
+    ms[0] = ms[1] = ms[2] = 0.0f;
+    if (!h->stage_valid) return fail(h, TCW_E_STATE, "tcw_last_exp_stage_ms: no map has been run");
+    if (!h->x_valid) return TCW_OK;  // the last map did not take the recurrence path
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_fin));
+    for (int sb = 0; sb < h->n_sub_last; sb++) {
+        float a = 0, b = 0, c = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&a, h->ev_sub[3 * sb + 0], h->ev_x[2 * sb]));
+        CUDA_TRY(h, cudaEventElapsedTime(&b, h->ev_x[2 * sb], h->ev_x[2 * sb + 1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&c, h->ev_x[2 * sb + 1], h->ev_sub[3 * sb + 1]));
+        ms[0] += a;
+        ms[1] += b;
+        ms[2] += c;
+    }
+    return TCW_OK;
 }
 
 extern "C" int tcw_last_stage_ms(tcw_handle *h, float ms[5]) {

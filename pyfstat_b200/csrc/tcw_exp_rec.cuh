@@ -405,22 +405,45 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
 // pass 1 walks every segment from a zero state (no output) and leaves its end value E_s in shared memory;
 // the state entering segment s is then  sum_{s' > s} rho^(p SEG (s' - s - 1)) E_s'  (Horner, a few terms);
 // pass 2 walks the segment again from that state and emits the cells.
-// Correction sums (HAS_C) are prefetched TCX_WALK_DEPTH rows ahead into a per-warp shared-memory ring with
-// 16-byte cp.async.cg copies (a row of a warp = 7 channels x 128 B = 56 pieces, two per lane): no registers
-// held across the HBM latency of a serial walk, and the stream bypasses L1, which holds the atoms.  The
-// two atom records of the next row are fetched one row ahead.
-#define TCX_WALK_DEPTH 12
+//
+// Operands of a row step, per warp -- all of them from shared memory, none held in registers across rows.
+// A warp at 2-6 warps per scheduler issues nearly serially, so what counts is the number of instructions
+// per step and the latency of each; the versions measured on the way (8 x 120-d maps, exact mode):
+//   * atoms as 32-byte FP32 records from global memory (broadcast load of the ENTERING atom, 96-byte-stride
+//     gather of the LEAVING atoms), FP32 -> FP64 conversions: 2.4 ms whatever the segmentation -- 150
+//     instructions per step, 14 conversions per cell and pass on the XU pipe (ncu: XU 52 %), and the
+//     compiler reusing the dead padding register of a prefetching load as a temporary (35 % of all stall
+//     samples on one instruction that waits for that load);
+//   * the same with the leaving atoms in a shared-memory ring: 2.4 ms; FP64 copies of the atoms (no
+//     conversions) but 16 more registers for the prefetch: 2.6-3.0 ms (occupancy);
+//   * this version: 1.80 ms.  The 32 leaving atoms of a row lie in a window of <= 97 consecutive atoms that
+//     slides down by ONE atom per row: the warp keeps it in a ring (FP64, channel-major, 128 atoms; the
+//     stride-3 reads are bank-conflict-free) and fetches 16 new atoms every 16 rows; the entering atom comes
+//     from a second ring of 32 atoms (a broadcast read).  FP64 copies of the atoms
+//     (tcw_exp_atoms_f64_kernel) feed DFMAs directly; the only conversions left are the 7 sums going to FP32.
+// Correction sums (HAS_C) are prefetched TCX_WALK_DEPTH rows ahead into a third ring (a row of a warp =
+// 7 channels x 128 B = 56 16-byte pieces, two per lane).  Everything arrives by cp.async.cg -- one commit
+// group per row, so a fixed wait_group count covers all rings -- bypassing L1.
+#define TCX_WALK_DEPTH 4
+#define TCX_WALK_XRING 128  // atoms in the leaving-atom ring (8 blocks of 16)
 template <int NSEG>
 struct WalkCfg {
     static constexpr int kCG = NSEG >= 4 ? 1 : 4 / NSEG;  // column groups (of 32 window lengths) per CTA
     static constexpr int kWarps = NSEG * kCG;
     static constexpr int kThreads = 32 * kWarps;
-    static constexpr int kEBytes = kWarps * TCW_NCH * 32 * 8;
-    static constexpr int kRingBytes = kWarps * TCX_WALK_DEPTH * TCW_NCH * 32 * 4;
+    static constexpr int kWarpXBytes = TCW_NCH * (TCX_WALK_XRING + 32) * 8;  // leaving-atom ring + entering-atom ring
+    static constexpr int kXRingBytes = kWarps * kWarpXBytes;                 // (also holds E between the passes)
+    static constexpr int kCRingBytes = kWarps * TCX_WALK_DEPTH * TCW_NCH * 32 * 4;
+    static constexpr int smem(bool has_c) { return kXRingBytes + (has_c ? kCRingBytes : 0); }
 };
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+// src_bytes = 0: the 16 destination bytes are zero-filled and the source is not read
+__device__ __forceinline__ void cp_async16_zfill(void *dst_smem, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                 : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -428,23 +451,40 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// FP64 copy of the merged atoms for the walk: Xd[t][7][xpad], channel-major and zero padded like X.
+__global__ void tcw_exp_atoms_f64_kernel(const float *__restrict__ X, uint32_t xpad, int t_base, double *__restrict__ Xd) {
+    const int t = t_base + blockIdx.y;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < xpad; j += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++)
+            Xd[((size_t)t * TCW_NCH + c) * xpad + j] = (double)__ldg(X + ((size_t)t * TCW_NCH + c) * xpad + j);
+    }
+}
+
 template <bool HAS_C, int NSEG>
 __global__ void __launch_bounds__(WalkCfg<NSEG>::kThreads)
-tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *__restrict__ Kn,
-                    const TplMeta *__restrict__ meta, int t_base, MapWindow w, uint32_t i00, int32_t delta, uint32_t TAtom,
-                    const float *__restrict__ C, uint32_t cpitch, float *__restrict__ Fmn,
-                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
+                    const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, MapWindow w,
+                    uint32_t i00, int32_t delta, uint32_t TAtom, const float *__restrict__ C, uint32_t cpitch,
+                    float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     using Cfg = WalkCfg<NSEG>;
     extern __shared__ __align__(16) unsigned char walk_smem[];
     __shared__ unsigned long long red[Cfg::kWarps];
-    double(*E)[TCW_NCH][32] = reinterpret_cast<double(*)[TCW_NCH][32]>(walk_smem);  // [warp][channel][lane]
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int seg = wi % NSEG, cg = wi / NSEG;
+    double(*ringX)[TCX_WALK_XRING] = reinterpret_cast<double(*)[TCX_WALK_XRING]>(
+        walk_smem + (size_t)wi * Cfg::kWarpXBytes);  // [channel][atom & 127]: atoms leaving the windows
+    double(*ringX0)[32] = reinterpret_cast<double(*)[32]>(
+        walk_smem + (size_t)wi * Cfg::kWarpXBytes + TCW_NCH * TCX_WALK_XRING * 8);  // [channel][atom & 31]: atoms entering
+    // end values of pass 1, [channel][lane] at the start of each warp's (then idle) atom ring
+    auto E = [&](int wj) { return reinterpret_cast<double(*)[32]>(walk_smem + (size_t)wj * Cfg::kWarpXBytes); };
+    float(*ringC)[TCW_NCH][32] = reinterpret_cast<float(*)[TCW_NCH][32]>(
+        walk_smem + Cfg::kXRingBytes + (size_t)wi * TCX_WALK_DEPTH * TCW_NCH * 32 * 4);  // [slot][channel][lane]
     const uint32_t n = (blockIdx.x * Cfg::kCG + cg) * 32 + lane;
     const bool active = n < w.N_tau;
-    const float4 *Xt = reinterpret_cast<const float4 *>(X8 + (size_t)t * xpad * 8);
+    const double *Xs = X + (size_t)t * TCW_NCH * xpad;
 
     // the column's window: k in [ka, kb], weights w0 rho^(k - ka)
     const uint32_t nn = active ? n : w.N_tau - 1;
@@ -459,8 +499,21 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
     const double rho = exp(-(double)TAtom * inv_tau), rho2 = rho * rho;
     const double w0 = empty_win ? 0.0 : exp(-((double)ka * TAtom + (double)delta) * inv_tau), w02 = w0 * w0;
     const double rhoL = empty_win ? 0.0 : exp(-(double)L * (double)TAtom * inv_tau);
-    const float rL = (float)rhoL, rL2 = (float)(rhoL * rhoL);
-    const float a0 = empty_win ? 0.0f : 1.0f;
+    const double rhoL2 = rhoL * rhoL;
+    const float w0f = (float)w0, w02f = (float)w02;  // scale of the sums, applied in FP32 after the conversion
+
+    // leaving atom of row m: index m + off.  The warp's 32 offsets span <= 96 atoms whenever dtau <= TAtom
+    // (3 dtau / TAtom per column); wider spans take the plain gather.
+    const int off_own = (int)i00 + kb + 1;
+    int off_min = empty_win ? 0x7fffffff : off_own, off_max = empty_win ? -0x7fffffff : off_own;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        off_min = min(off_min, __shfl_xor_sync(0xffffffffu, off_min, o));
+        off_max = max(off_max, __shfl_xor_sync(0xffffffffu, off_max, o));
+    }
+    if (off_max < off_min) off_min = off_max = 0;  // no lane has a window
+    const bool use_ring = off_max - off_min <= TCX_WALK_XRING - 32;
+    const int off = empty_win ? off_min : off_own;
 
     // rows 0 .. R-1 (rows >= N_t0 lie beyond the map -- the canonical plan guarantees R >= N_t0 -- and
     // give no output); segment `seg` owns rows [lo, hi)
@@ -472,67 +525,107 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
 #pragma unroll
     for (int c = 0; c < TCW_NCH; c++) U[c] = 0.0;
 
-    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch : nullptr;
+    float *Ft = Fmn ? Fmn + (size_t)tz * w.N_t0 * w.pitch + n : nullptr;  // + m * pitch
     float best = -1.0f;
-    uint32_t best_flat = 0;
-    bool degenerate = false;
+    int best_m = 0;
 
-    // atom records of a row: X[s + ka] (entering the window) and X[s + kb + 1] (leaving it)
-    float4 nlo0, nhi0, nlo1, nhi1;
-    auto load_row = [&](int m) {
-        nlo0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        nhi0 = nlo0; nlo1 = nlo0; nhi1 = nlo0;
-        if (m < 0) return;
-        const uint32_t s = i00 + (uint32_t)m;
-        const uint32_t j0 = s + ka, j1 = s + (uint32_t)(kb + 1);
-        if (j0 < numAtoms) {
-            nlo0 = __ldg(Xt + 2 * (size_t)j0);
-            nhi0 = __ldg(Xt + 2 * (size_t)j0 + 1);
-        }
-        if (!empty_win && j1 < numAtoms) {
-            nlo1 = __ldg(Xt + 2 * (size_t)j1);
-            nhi1 = __ldg(Xt + 2 * (size_t)j1 + 1);
+    // atoms [16 b, 16 b + 16) of the 7 channels into the ring: 56 pieces of 16 bytes (2 atoms), two per lane
+    // (zeros outside the padded array; the array itself is zero beyond numAtoms)
+    auto fetch_block = [&](int b, bool entering) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int q = lane + 32 * h;
+            if (q < 8 * TCW_NCH) {
+                const int c = q >> 3;
+                const int j = 16 * b + 2 * (q & 7);
+                const bool ok = j >= 0 && (uint32_t)j + 2u <= xpad;
+                double *dst = entering ? &ringX0[c][j & 31] : &ringX[c][j & (TCX_WALK_XRING - 1)];
+                cp_async16_zfill(dst, Xs + (size_t)c * xpad + (ok ? j : 0), ok ? 16u : 0u);
+            }
         }
     };
-    // step(m): consumes the records fetched for row m and fetches those of row m - 1
+    const int off0 = (int)i00 + ka;  // entering atom of row m: index m + off0
+    // everything the pass starting at row m_first needs at once: blocks from one below the lowest
+    // leaving atom up to the highest
+    auto fill_ring = [&](int m_first) {
+        __syncwarp();
+        if (use_ring) {
+            const int jl = m_first + off_min;
+            for (int b = (jl >> 4) - 1; b <= (jl + (off_max - off_min)) >> 4; b++) fetch_block(b, false);
+        }
+        fetch_block((m_first + off0) >> 4, true);
+        fetch_block(((m_first + off0) >> 4) - 1, true);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+    };
+    // end of row m: the block needed 16 rows from now joins this row's commit group
+    auto row_end = [&](int m) {
+        const int jl = m + off_min, j0 = m + off0;
+        if (use_ring && (jl & 15) == 15) fetch_block((jl >> 4) - 1, false);
+        if ((j0 & 15) == 15) fetch_block((j0 >> 4) - 1, true);  // into the half the rows above have left
+        cp_async_commit();
+    };
+
+    // entering atom of a row, fetched one row ahead (one broadcast 32-byte record)
+    // (rows m < 0 and atoms beyond the data read the zero padding of the array: xpad >= numAtoms + 64)
     auto step = [&](int m) {
-        const float4 lo0 = nlo0, hi0 = nhi0, lo1 = nlo1, hi1 = nhi1;
-        load_row(m - 1);
-        // d = X[s + ka] - rho^(pL) X[s + kb + 1] in FP32 (one rounding), U = rho^p U + d in FP64
-        U[0] = fma(rho2, U[0], (double)fmaf(-rL2, lo1.x, a0 * lo0.x));
-        U[1] = fma(rho2, U[1], (double)fmaf(-rL2, lo1.y, a0 * lo0.y));
-        U[2] = fma(rho2, U[2], (double)fmaf(-rL2, lo1.z, a0 * lo0.z));
-        U[3] = fma(rho, U[3], (double)fmaf(-rL, lo1.w, a0 * lo0.w));
-        U[4] = fma(rho, U[4], (double)fmaf(-rL, hi1.x, a0 * hi0.x));
-        U[5] = fma(rho, U[5], (double)fmaf(-rL, hi1.y, a0 * hi0.y));
-        U[6] = fma(rho, U[6], (double)fmaf(-rL, hi1.z, a0 * hi0.z));
+        double x0[TCW_NCH], x1[TCW_NCH];
+        {
+            const int slot0 = (m + off0) & 31;  // the same address in every lane: a broadcast read
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) x0[c] = ringX0[c][slot0];
+        }
+        if (use_ring) {
+            const int slot = (m + off) & (TCX_WALK_XRING - 1);
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) x1[c] = ringX[c][slot];
+        } else {
+            const uint32_t j1 = min((uint32_t)(m + off), numAtoms);  // the record at numAtoms is zero padding
+#pragma unroll
+            for (int c = 0; c < TCW_NCH; c++) x1[c] = __ldg(Xs + (size_t)c * xpad + j1);
+        }
+        // U = rho^p U + (X[s + ka] - rho^(pL) X[s + kb + 1]), all in FP64.
+        // (Columns with an empty window keep accumulating the entering atoms; their cells are forced to the
+        // F = 2 fallback in cell().)
+#pragma unroll
+        for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rho2 : rho, U[c], fma(-(c < 3 ? rhoL2 : rhoL), x1[c], x0[c]));
     };
     auto cell = [&](int m, const float *cc) {
         float S[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) {
-            S[c] = (float)((c < 3 ? w02 : w0) * U[c]);
-            if (HAS_C) S[c] += cc[c * 32];
+            const float u = (float)U[c];
+            S[c] = HAS_C ? fmaf(u, c < 3 ? w02f : w0f, cc[c * 32]) : u * (c < 3 ? w02f : w0f);
         }
-        const float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+        float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
+        if (empty_win) F = 2.0f;  // no atom in the window: all sums zero in the reference -> its fallback value
         if (active) {
-            if (Ft) Ft[(size_t)m * w.pitch + n] = F;
+            if (Ft) Ft[(size_t)m * w.pitch] = F;
             if (F >= best) {  // rows are walked downwards: among equal F the smaller row wins (np.argmax order)
                 best = F;
-                best_flat = (uint32_t)m * w.N_tau + n;
+                best_m = m;
             }
-            if (K >= 0 && (K == 0 || i00 + (uint32_t)m == numAtoms - 1)) degenerate = true;
         }
     };
 
     if (NSEG > 1) {
         // ---- pass 1: the segment from a zero state (nobody needs the lowest segment's end value) ----
-        if (seg > 0) {
-            load_row(hi - 1);
-            for (int m = hi - 1; m >= lo; m--) step(m);
+        if (seg > 0 && hi > lo) {
+            fill_ring(hi - 1);
+#pragma unroll 1
+            for (int m = hi - 1; m >= lo; m--) {
+                cp_async_wait<TCX_WALK_DEPTH - 1>();
+                __syncwarp();
+                step(m);
+                __syncwarp();
+                row_end(m);
+            }
         }
+        cp_async_wait<0>();  // no copy into the ring is in flight any more
+        __syncwarp();
 #pragma unroll
-        for (int c = 0; c < TCW_NCH; c++) E[wi][c][lane] = U[c];
+        for (int c = 0; c < TCW_NCH; c++) E(wi)[c][lane] = U[c];
         __syncthreads();
         // ---- state entering the segment ----
         const double rS = exp(-(double)SEG * (double)TAtom * inv_tau), rS2 = rS * rS;
@@ -540,50 +633,73 @@ tcw_exp_walk_kernel(const float *__restrict__ X8, uint32_t xpad, const int32_t *
         for (int c = 0; c < TCW_NCH; c++) U[c] = 0.0;
         for (int sp = NSEG - 1; sp > seg; sp--) {
 #pragma unroll
-            for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rS2 : rS, U[c], E[cg * NSEG + sp][c][lane]);
+            for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rS2 : rS, U[c], E(cg * NSEG + sp)[c][lane]);
         }
+        __syncthreads();  // every warp has read the end values: the rings may be refilled
     }
 
     // ---- pass 2: the segment (again) from its true state, with output ----
     int m = hi - 1;
-    load_row(m);
-    for (; m >= lo && m >= (int)w.N_t0; m--) step(m);
+    if (hi > lo) {
+        fill_ring(m);
+    }
+#pragma unroll 1
+    for (; m >= lo && m >= (int)w.N_t0; m--) {  // rows beyond the map: no output
+        cp_async_wait<TCX_WALK_DEPTH - 1>();
+        __syncwarp();
+        step(m);
+        __syncwarp();
+        row_end(m);
+    }
     if (HAS_C) {
-        float(*ring)[TCW_NCH][32] =
-            reinterpret_cast<float(*)[TCW_NCH][32]>(walk_smem + Cfg::kEBytes + (size_t)wi * TCX_WALK_DEPTH * TCW_NCH * 32 * 4);
         const size_t cstride = (size_t)w.N_t0 * cpitch;
         // piece q = lane, lane + 32 of a row: channel q / 8, columns 4 (q % 8) .. + 3 of the warp's 32
         const float *Cp0 = C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + (size_t)(n - lane) + (size_t)(lane >> 3) * cstride + 4 * (lane & 7);
         const float *Cp1 = Cp0 + 4 * cstride;
         const int m_top = m;
-        auto fetch = [&](int row, int slot) {
+        auto fetch_c = [&](int row, int slot) {
             if (row >= lo) {
-                cp_async16(&ring[slot][lane >> 3][4 * (lane & 7)], Cp0 + (size_t)row * cpitch);
-                if (lane < 24) cp_async16(&ring[slot][4 + (lane >> 3)][4 * (lane & 7)], Cp1 + (size_t)row * cpitch);
+                cp_async16(&ringC[slot][lane >> 3][4 * (lane & 7)], Cp0 + (size_t)row * cpitch);
+                if (lane < 24) cp_async16(&ringC[slot][4 + (lane >> 3)][4 * (lane & 7)], Cp1 + (size_t)row * cpitch);
             }
-            cp_async_commit();  // one group per row, also when empty: the group count stays uniform
         };
 #pragma unroll 1
-        for (int r = 0; r < TCX_WALK_DEPTH; r++) fetch(m_top - r, r);
+        for (int r = 0; r < TCX_WALK_DEPTH; r++) {
+            fetch_c(m_top - r, r);
+            cp_async_commit();
+        }
         int slot = 0;
 #pragma unroll 1
         for (; m >= lo; m--) {
             cp_async_wait<TCX_WALK_DEPTH - 1>();  // the oldest row in flight has landed (this lane's pieces)
             __syncwarp();                         // ... and every other lane's
             step(m);
-            cell(m, &ring[slot][0][lane]);
-            __syncwarp();  // all lanes have read the slot before it is refilled
-            fetch(m - TCX_WALK_DEPTH, slot);
+            cell(m, &ringC[slot][0][lane]);
+            __syncwarp();  // all lanes have read the slots before they are refilled
+            fetch_c(m - TCX_WALK_DEPTH, slot);
+            row_end(m);
             slot = slot + 1 == TCX_WALK_DEPTH ? 0 : slot + 1;
         }
-        cp_async_wait<0>();
     } else {
+#pragma unroll 1
         for (; m >= lo; m--) {
+            cp_async_wait<TCX_WALK_DEPTH - 1>();
+            __syncwarp();
             step(m);
             cell(m, nullptr);
+            __syncwarp();
+            row_end(m);
         }
     }
-    if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
-    const unsigned long long key = (active && best > -1.0f) ? pack_key(best, best_flat) : 0ull;
+    cp_async_wait<0>();
+    // single-atom cells (Exp.cu's i_t1 == i_t0): a column whose window holds one atom, or the row that starts
+    // on the last atom
+    {
+        const int m_last = (int)numAtoms - 1 - (int)i00;
+        const int top = min(hi, (int)w.N_t0);
+        const bool degenerate = active && K >= 0 && top > lo && (K == 0 || (m_last >= lo && m_last < top));
+        if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
+    }
+    const unsigned long long key = (active && best > -1.0f) ? pack_key(best, (uint32_t)best_m * w.N_tau + n) : 0ull;
     block_atomic_max_key<Cfg::kWarps>(key, &maxkey[t], red);
 }

@@ -326,10 +326,12 @@ def exp_split(stages):
     return {k: statistics.mean(s["map_" + k] for s in stages) for k in ("operands", "tensor", "walk")}
 
 
-def exp_variants(h, L, spec, T, peaks, steps=2, warmup=1):
-    """The same resident batch through the other exponential-window paths: exact exponentials (the reference's
+def exp_variants(h, L, spec, batch, peaks, steps=2, warmup=1):
+    """The same batch through the other exponential-window paths: exact exponentials (the reference's
     pycuda semantics: pure FP64 recurrence) and the tiled direct sum (TCW_EXP_DIRECT, round 1's FFMA2 kernel)."""
     out = {}
+    T = batch.T
+    h.upload(batch)
     for name, fl in (("exact_exp_recurrence", L.WANT_BTSG | L.EXP_EXACT), ("lut_direct_sum", L.WANT_BTSG | L.EXP_DIRECT)):
         ms, stages = timed_steps(h, spec["w"], fl, steps, warmup)
         map_ms = statistics.mean(s["map"] for s in stages)
@@ -568,7 +570,7 @@ def run_gpu(args):
         if strong:
             line["strong"] = strong
         if spec["window"] == "exp" and not args.no_secondary:
-            line["other_paths"] = exp_variants(h, L, spec, hi - lo, peaks)
+            line["other_paths"] = exp_variants(h, L, spec, batch, peaks)
         if not args.no_secondary and world == 1 and args.workload == "exp120":
             line["configs"] = secondary_configs(h, L, hbm_peak, hbm_src, peaks, local_rank)
         if not args.no_cpu and world == 1:
@@ -652,7 +654,7 @@ def sec_exp30(h, L, peaks, steps=10, warmup=3):
                 "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(T * L.RESULT_DTYPE.itemsize),
                 "api": "tcw_map_batch (C ABI), pinned host atoms in, records out"},
         "roofline": exp_rec_roofline(spec, T, exp_split(stages), *measured_peaks()), "stage_ms": mean_stage(stages),
-        "other_paths": exp_variants(h, L, spec, T, peaks), "config": workload_config(spec),
+        "other_paths": exp_variants(h, L, spec, batch, peaks), "config": workload_config(spec),
     }
 
 

@@ -97,8 +97,12 @@ def default_flags() -> int:
     """Backend knobs the caller API has no slot for come from the environment:
     ``PYFSTAT_B200_EXP=exact`` selects exact exp() instead of lalpulsar's lookup table;
     ``PYFSTAT_B200_ALLOW_DEGENERATE=1`` gives pycuda semantics for single-atom windows;
-    ``PYFSTAT_B200_GENERIC=1`` forces the generic (bit-faithful) kernels."""
+    ``PYFSTAT_B200_GENERIC=1`` forces the generic (bit-faithful) kernels;
+    ``PYFSTAT_B200_EXP_DIRECT=1`` keeps the exponential window on the tiled direct sum (no recurrence /
+    tensor-core pass)."""
     flags = 0
+    if os.environ.get("PYFSTAT_B200_EXP_DIRECT", "0") not in ("0", ""):
+        flags |= _lib.EXP_DIRECT
     if os.environ.get("PYFSTAT_B200_EXP", "lal").lower() == "exact":
         flags |= _lib.EXP_EXACT
     if os.environ.get("PYFSTAT_B200_ALLOW_DEGENERATE", "0") not in ("0", ""):

@@ -25,21 +25,22 @@
 //     sum_k X w_lut = sum_k X w_exact  +  sum_k X (w_lut - w_exact)
 // The first term is the recurrence; the second is a Hankel contraction whose weights are <= 2e-3 of
 // the first term's, so it needs 3 significant digits, not 7: it runs on the 5th-gen tensor cores in
-// one TF32 pass (tcgen05.mma kind::tf32, FP32 accumulation in TMEM).  TF32 rounding of X and V
-// (2^-11 each) and the tensor core's truncating accumulation (measured 6e-6 of sum|terms| at
-// K = 5760, profiles/r02_tc_probe.txt) are multiplied by the 2e-3 and land below 1e-8 of the sums.
+// one pass with 11-bit operands (tcgen05.mma kind::f16 -- or kind::tf32 -- FP32 accumulation in
+// TMEM).  The operand roundings (2^-11 each) and the tensor core's truncating accumulation (measured
+// 6e-6 of sum|terms| at K = 5760, profiles/r02_tc_probe.txt) are multiplied by the 2e-3.
 //
-// Tensor-core kernel.  D_c[(i), n] = sum_k X_c[s0 + 4 i + k] V[k, n]: in the no-swizzle K-major
-// canonical layout a row is 16 bytes = 4 TF32 values and the 8 rows of a core matrix are 16 bytes
-// apart, so a descriptor laid over the plain atom array IS the Hankel operand for the rows
-// m = m0 + r + 4 i of row class r (tools/tc_probe/hankel_tf32.cu).  Channels are stacked in M: the
+// Tensor-core kernel.  D_c[(i), n] = sum_k X_c[s0 + R i + k] V[k, n], R = elements per 16 bytes: in
+// the no-swizzle K-major canonical layout a row is 16 bytes and the 8 rows of a core matrix are 16
+// bytes apart, so a descriptor laid over the plain atom array IS the Hankel operand for the rows
+// m = m0 + r + R i of row class r (tools/tc_probe/hankel_tf32.cu).  Channels are stacked in M: the
 // 128 lanes of an MMA are 2 channels x 64 rows, each 8-row group reading its own 256-byte chunk of
-// atoms (32 rows' span + 32 k), the chunks 256 bytes apart (SBO); a prep kernel lays the atoms out
-// in that chunked form -- per class r, channel pair p and 32-atom block u: [c'][64 floats] -- so a
-// stage's A operand is four contiguous 4-KB bulk copies.  N = 128 window lengths.  The four channel
-// pairs (a2,b2 | ab,- | Fa | Fb) own 4 x 128 TMEM columns = all 512; per 32-k stage 16 MMAs
-// (M128 N128 K8).  Warp roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C);
-// persistent CTAs, one per SM, static round-robin over tiles ordered by decreasing k range.
+// atoms (its rows' span + one stage of k), the chunks 256 bytes apart (SBO); a prep kernel lays the
+// atoms out in that chunked form -- per class r, channel pair p and block u: [c'][chunk] -- so a
+// stage's A operand of a pair is one contiguous 4-KB bulk copy.  N = 128 window lengths.  A tile is
+// processed as two units of two channel pairs (a2,b2 | ab,- with the w^2 table, Fa | Fb with the w
+// table), each unit in one half of TMEM, 8 MMAs (M128 N128, 32 bytes of K) per 24-KB stage.  Warp
+// roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C); persistent CTAs, one
+// per SM, static round-robin over tiles ordered by decreasing k range.
 #pragma once
 #include <cuda_fp16.h>
 

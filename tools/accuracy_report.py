@@ -47,33 +47,35 @@ for win, n, dets, label in CASES:
         O.set_exp_lut(*geom)
         b = synth_atoms(1, n, dets, seed=171)
         w = canonical_window(win, 10**9, n)
-        res, F = h.map_batch(b, w, L.WANT_FMN | L.WANT_BTSG)
         t0 = time.time()
         o = O.compute_map(b.template(0), b.TAtom, w)
         dt = time.time() - t0
         Fo = o["F_mn"]
-        rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
-        row = dict(
-            window=win, atoms=n, detectors="+".join(dets), baseline=label, exp_lut=f"{geom[0]:g}:{geom[1]}",
-            cells=int(rel.size), oracle_s=round(dt, 2),
-            rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)), rel_p9999=float(np.quantile(rel, 0.9999)),
-            rel_max=float(rel.max()), n_gt_1e4=int((rel > 1e-4).sum()), n_gt_1e5=int((rel > 1e-5).sum()),
-            argmax_equal=bool((int(res["m_ML"][0]), int(res["n_ML"][0])) == (o["m_ML"], o["n_ML"])),
-            maxF_rel=float(abs(float(res["maxF"][0]) - o["maxF"]) / o["maxF"]),
-            lnBtSG_abs=float(abs(float(res["lnBtSG"][0]) - o["lnBtSG"])),
-            MP_equal=bool((int(res["m_MP"][0]), int(res["n_MP"][0])) == (o["m_MP"], o["n_MP"])),
-        )
-        if win == "rect":
-            cond = cond_map(o["merged"], *Fo.shape)
-            fallback = (F[0] == 2.0) != (Fo == 2.0)
-            strata = []
-            for lo, hi in zip(COND_EDGES[:-1], COND_EDGES[1:]):
-                sel = (cond >= lo) & (cond < hi) & ~fallback
-                if sel.any():
-                    strata.append(dict(cond=f"[{lo:g}, {hi:g})", cells=int(sel.sum()), rel_median=float(np.median(rel[sel])),
-                                       rel_max=float(rel[sel].max()), n_gt_1e4=int((rel[sel] > 1e-4).sum()),
-                                       max_rel_over_cond=float((rel[sel] / cond[sel]).max())))
-            row["cond_strata"] = strata
-            row["cells_flipped_across_the_cut"] = int(fallback.sum())
-        print(json.dumps(row), flush=True)
+        # exponential window: the default path (FP64 recurrence + FP16 tensor-core pass) and the tiled direct sum
+        for path_name, path_flags in ((("recurrence+tensor", 0), ("direct_sum", L.EXP_DIRECT)) if win == "exp" else (("tiled", 0),)):
+            res, F = h.map_batch(b, w, L.WANT_FMN | L.WANT_BTSG | path_flags)
+            rel = np.abs(F[0] - Fo) / np.maximum(np.abs(Fo), 1e-30)
+            row = dict(
+                window=win, atoms=n, detectors="+".join(dets), baseline=label, exp_lut=f"{geom[0]:g}:{geom[1]}", kernels=path_name,
+                cells=int(rel.size), oracle_s=round(dt, 2),
+                rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)), rel_p9999=float(np.quantile(rel, 0.9999)),
+                rel_max=float(rel.max()), n_gt_1e4=int((rel > 1e-4).sum()), n_gt_1e5=int((rel > 1e-5).sum()),
+                argmax_equal=bool((int(res["m_ML"][0]), int(res["n_ML"][0])) == (o["m_ML"], o["n_ML"])),
+                maxF_rel=float(abs(float(res["maxF"][0]) - o["maxF"]) / o["maxF"]),
+                lnBtSG_abs=float(abs(float(res["lnBtSG"][0]) - o["lnBtSG"])),
+                MP_equal=bool((int(res["m_MP"][0]), int(res["n_MP"][0])) == (o["m_MP"], o["n_MP"])),
+            )
+            if win == "rect":
+                cond = cond_map(o["merged"], *Fo.shape)
+                fallback = (F[0] == 2.0) != (Fo == 2.0)
+                strata = []
+                for lo, hi in zip(COND_EDGES[:-1], COND_EDGES[1:]):
+                    sel = (cond >= lo) & (cond < hi) & ~fallback
+                    if sel.any():
+                        strata.append(dict(cond=f"[{lo:g}, {hi:g})", cells=int(sel.sum()), rel_median=float(np.median(rel[sel])),
+                                           rel_max=float(rel[sel].max()), n_gt_1e4=int((rel[sel] > 1e-4).sum()),
+                                           max_rel_over_cond=float((rel[sel] / cond[sel]).max())))
+                row["cond_strata"] = strata
+                row["cells_flipped_across_the_cut"] = int(fallback.sum())
+            print(json.dumps(row), flush=True)
 h.close()

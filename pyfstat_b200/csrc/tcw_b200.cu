@@ -79,6 +79,7 @@ struct tcw_handle {
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
         d_wins, d_tilemax, d_shift, d_G, d_C, d_scale, d_Xd;
     int tc_f16 = 1;  // tensor-core pass of the exp window: FP16 operands (default) or TF32 ($TCW_TC_TF32=1)
+    int tc_pair = 0;  // ... on CTA pairs (cta_group::2), FP16 only ($TCW_TC_2CTA=1)
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -368,6 +369,8 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     if (const char *v = getenv("TCW_TC_TF32")) h->tc_f16 = atoi(v) ? 0 : 1;
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX2_SMEM));
+    if (const char *v = getenv("TCW_TC_2CTA")) h->tc_pair = (atoi(v) && h->tc_f16) ? 1 : 0;
 #define WALK_ATTR(NS)                                                                                              \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            WalkCfg<NS>::smem(true)));                                                  \
@@ -1025,16 +1028,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     uint32_t exp_TM = 0, exp_TN = 0;
     exp_tile_dims(h->exp_variant, &exp_TM, &exp_TN);
     if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
-        const int kind = exp_tc ? (tc_f16 ? 3 : 1) : exp_rec ? 2 : 0;
+        const int kind = exp_tc ? (tc_f16 ? (h->tc_pair ? 4 : 3) : 1) : exp_rec ? 2 : 0;
         const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
                          h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom && h->w_kind == kind &&
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
             size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
-            if (kind == 1 || kind == 3) total = (size_t)tc_n_nt * tc_chunks * (TCX_TAUS * tc_kc);
+            if (kind == 1 || kind >= 3) total = (size_t)tc_n_nt * tc_chunks * (TCX_TAUS * tc_kc);
             if (kind == 0 && (rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
-            if ((kind == 1 || kind == 3) && (rc = ensure(h, h->d_W, (size_t)tc_n_nt * tc_chunks * 32768))) return rc;
+            if ((kind == 1 || kind >= 3) && (rc = ensure(h, h->d_W, (size_t)tc_n_nt * tc_chunks * 32768))) return rc;
             if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
             h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -1060,6 +1063,9 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             else if (kind == 3)
                 tcw_exptc_table_kernel<true><<<blocks, 256, 0, st>>>(h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
                                                                      tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
+            else if (kind == 4)
+                tcw_exptc_table2_kernel<<<blocks, 256, 0, st>>>((__half *)h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
+                                                                tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
             if (kind != 2) h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
@@ -1216,7 +1222,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb], st));
-                if (tc_f16)
+                if (tc_f16 && h->tc_pair) {
+                    const uint32_t n_pair_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * 4u;
+                    const uint32_t ctas2 = 2u * std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount / 2u, n_pair_tiles);
+                    tcw_exptc_map2_kernel<<<ctas2, TCX_THREADS, TCX2_SMEM, st>>>(
+                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_pair_tiles, (const float *)h->d_scale.p,
+                        (float *)h->d_C.p, tc_cpitch);
+                } else if (tc_f16)
                     tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
                         (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,

@@ -452,6 +452,297 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- the same pass on CTA PAIRS (tcgen05 cta_group::2), FP16 only ---------------------------------------
+// The single-CTA kernel is bounded by shared memory: an M128 N128 MMA reads 8 KB of operands in 64 cycles -- all
+// of the SM's 128 B/clk -- while TMA writes the next stages into the same memory (tensor pipe 70 % active).
+// A CTA pair runs ONE M256 N128 MMA across two SMs: each SM holds its own 128 rows of A (its row class) and
+// HALF of B (64 window lengths), the halves are exchanged between the two tensor cores, so an SM reads
+// 4 + 2 KB per MMA and TMA writes 16 instead of 24 KB per stage.  The pair works on row classes 2 r' and
+// 2 r' + 1 of one (template, row block, tau tile): same weights, k ranges that differ by at most one atom.
+// Protocol: both CTAs run a TMA producer (own shared memory, own `full` barriers) and 4 epilogue warps (own
+// TMEM); the leader's MMA thread waits for its own `full` barrier and for `peer_full`, on which the peer's
+// otherwise idle warp 1 forwards the peer's `full` completions (remote mbarrier arrive); tcgen05.commit
+// multicasts `empty` / `tmem_full` to both CTAs; the peer's epilogue threads arrive remotely on the leader's
+// `tmem_empty`.
+// MEASURED (8 x 120-d maps): correct (same maps as the single-CTA kernel), but NOT faster -- 10.5 ms against
+// 9.2-9.6 ms; 15.1 ms with a single forwarding thread; more stages change nothing.  A pair MMA (M256 N128 K16)
+// takes ~133 cycles where the single-CTA one (M128 N128 K16) takes ~114 and the tensor-pipe floor is 64: with
+// shared memory relieved the limit moves elsewhere -- presumably the exchange of the B halves between the two
+// SMs (2 KB per MMA in 16-byte core-matrix rows of the no-swizzle layout), which ncu does not expose.  Kept as
+// an opt-in experiment ($TCW_TC_2CTA=1, tests/test_gpu_parity.py::test_exp_tensor_pass_cta_pair).
+#define TCX2_STAGES 10
+#define TCX2_A_BYTES 8192
+#define TCX2_B_BYTES 8192
+#define TCX2_STAGE_BYTES (TCX2_A_BYTES + TCX2_B_BYTES)
+#define TCX2_SMEM (TCX2_STAGES * TCX2_STAGE_BYTES + 128)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\tbra WAITC_LOOP;\n\tWAITC_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+    __syncwarp();
+}
+__device__ __forceinline__ void tcx2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tcx2_commit(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
+// Weight tables for the pair kernel: Vt2[nt][chunk][table][half][kq 8][ng 8][nr 8][kk 8] -- the 64 window lengths
+// of a CTA are one contiguous 8-KB block per table and stage.
+__global__ void tcw_exptc_table2_kernel(__half *__restrict__ Vt, const int32_t *__restrict__ Kn, uint32_t N_tau,
+                                        uint32_t n_nt, uint32_t n_chunks, uint32_t tau, uint32_t dtau, uint32_t TAtom,
+                                        int32_t delta, const ExpLut lut) {
+    using Cfg = TcxCfg<true>;
+    constexpr uint32_t TE = (uint32_t)Cfg::kTableElems;  // 8192
+    const size_t total = (size_t)n_nt * n_chunks * TE;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t off = (uint32_t)(idx % TE);
+        const uint32_t kk = off & 7u, nr = (off >> 3) & 7u, ng = (off >> 6) & 7u, kq = (off >> 9) & 7u, half_ = off >> 12;
+        const size_t rest = idx / TE;
+        const uint32_t chunk = (uint32_t)(rest % n_chunks), nt = (uint32_t)(rest / n_chunks);
+        const uint32_t k = chunk * Cfg::kKC + kq * 8 + kk, n = nt * TCX_TAUS + half_ * 64 + ng * 8 + nr;
+        double v1 = 0.0, v2 = 0.0;
+        if (n < N_tau && (int32_t)k <= Kn[n]) {
+            const uint32_t tau_n = tau + n * dtau;
+            const long long t_rel = (long long)k * TAtom + delta;
+            if (t_rel >= 0 && t_rel <= (long long)TCW_EXP_EFOLDING * tau_n) {
+                const double x = __ddiv_rn((double)t_rel, (double)tau_n);
+                const double wl = fast_neg_exp_lut(x, lut), we = exp(-x);
+                v1 = wl - we;
+                v2 = (wl - we) * (wl + we);
+            }
+        }
+        __half *base = Vt + rest * 2 * TE;
+        base[off] = __float2half_rn((float)ldexp(v1, TCX_VSCALE_LOG2));
+        base[TE + off] = __float2half_rn((float)ldexp(v2, TCX_VSCALE_LOG2));
+    }
+}
+
+struct Tcx2Tile {
+    uint32_t tz, rp, mb, nt;
+    int nchunks;
+};
+__device__ __forceinline__ Tcx2Tile tcx2_tile(uint32_t j, uint32_t cnt, uint32_t n_mb, uint32_t n_nt, const MapWindow &w,
+                                              uint32_t i00, const TplMeta *__restrict__ meta, int t_base,
+                                              const int32_t *__restrict__ Kn) {
+    using Cfg = TcxCfg<true>;
+    Tcx2Tile tl;
+    tl.tz = j % cnt;
+    uint32_t rest = j / cnt;
+    tl.rp = rest & 3u;  // row classes 2 rp and 2 rp + 1
+    rest >>= 2;
+    tl.mb = rest % n_mb;
+    tl.nt = n_nt - 1u - rest / n_mb;
+    const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
+    const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
+    const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan + 2 * tl.rp;  // the earlier class: longer k range
+    const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
+    const bool rows = tl.mb * Cfg::kSpan + 2 * tl.rp < w.N_t0;
+    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
+    return tl;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCX_THREADS, 1)
+tcw_exptc_map2_kernel(const void *__restrict__ Gv, uint32_t U, const void *__restrict__ Vtv, uint32_t n_chunks_tab,
+                      const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
+                      MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles,
+                      const float *__restrict__ scale, float *__restrict__ C, uint32_t cpitch) {
+    using Cfg = TcxCfg<true>;
+    extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
+    __shared__ __align__(8) uint64_t full[TCX2_STAGES], empty[TCX2_STAGES], peer_full[TCX2_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const unsigned char *G = reinterpret_cast<const unsigned char *>(Gv);
+    const unsigned char *Vt = reinterpret_cast<const unsigned char *>(Vtv);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TCX2_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&peer_full[s], 1);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 256);  // the epilogue threads of BOTH CTAs (used in the leader only)
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcx_fence_before();
+    cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+    tcx_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer (both CTAs, own shared memory) ----
+            uint32_t it = 0;
+            for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
+                const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                const uint32_t r = 2 * tl.rp + rank;
+                const unsigned char *gA = G + (((size_t)tl.tz * Cfg::kRowStep + r) * 4 * U + 8ull * tl.mb) * 512;  // + (p U + c) * 512
+                const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768 + (size_t)rank * 8192;       // + c * 32 KB (+ 16 KB: w^2)
+                for (int hh = 0; hh < 2; hh++)
+                    for (int c = 0; c < tl.nchunks; c++, it++) {
+                        const uint32_t s = it % TCX2_STAGES;
+                        mbar_wait(&empty[s], ((it / TCX2_STAGES) & 1u) ^ 1u);
+                        unsigned char *st = smem + (size_t)s * TCX2_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[s], TCX2_STAGE_BYTES);
+#pragma unroll
+                        for (int pl = 0; pl < 2; pl++)
+                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 512, 4096, &full[s]);
+                        bulk_g2s(st + TCX2_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX2_B_BYTES, &full[s]);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 1) {  // ---- peer: forward `full` completions to the leader, one lane per stage ----
+            if (lane < TCX2_STAGES) {
+                uint32_t total = 0;
+                for (uint32_t j = pair; j < n_tiles; j += n_pairs)
+                    total += 2u * (uint32_t)tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn).nchunks;
+                const uint32_t remote = mapa_shared(smem_u32(&peer_full[lane]), 0);
+                uint32_t use = 0;
+                for (uint32_t it = (uint32_t)lane; it < total; it += TCX2_STAGES, use++) {
+                    mbar_wait(&full[lane], use & 1u);
+                    mbar_arrive_remote(remote);
+                }
+            }
+        } else if (lane == 0) {  // ---- leader: MMA issuer for the pair ----
+            constexpr uint32_t idesc = tcx_idesc(256, TCX_TAUS, true);
+            const uint64_t da = tcx_desc(0, 16, 256);    // A: this CTA's 128 rows
+            const uint64_t db = tcx_desc(0, 1024, 128);  // B: this CTA's 64 columns, [kq][ng 8][8][16 B]
+            uint32_t it = 0, unit = 0;
+            for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
+                const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+                for (int hh = 0; hh < 2; hh++, unit++) {
+                    const uint32_t buf = unit & 1u;
+                    mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
+                    tcx_fence_after();
+                    const uint32_t d0 = tmem + buf * 256u;
+                    for (int c = 0; c < tl.nchunks; c++, it++) {
+                        const uint32_t s = it % TCX2_STAGES;
+                        mbar_wait(&full[s], (it / TCX2_STAGES) & 1u);
+                        mbar_wait(&peer_full[s], (it / TCX2_STAGES) & 1u);
+                        tcx_fence_after();
+                        const uint32_t a0 = smem_u32(smem + (size_t)s * TCX2_STAGE_BYTES), b0 = a0 + TCX2_A_BYTES;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint64_t bd = db | (uint64_t)(((b0 + q * 2048) >> 4) & 0x3FFF);
+#pragma unroll
+                            for (int pl = 0; pl < 2; pl++) {
+                                const uint64_t ad = da | (uint64_t)(((a0 + pl * 4096 + q * 32) >> 4) & 0x3FFF);
+                                tcx2_mma(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
+                            }
+                        }
+                        tcx2_commit(&empty[s]);
+                    }
+                    if (tl.nchunks > 0) tcx2_commit(&tmem_full[buf]);
+                    else {
+                        mbar_arrive_plain(&tmem_full[buf]);
+                        mbar_arrive_remote(mapa_shared(smem_u32(&tmem_full[buf]), 1));
+                    }
+                }
+            }
+        }
+    } else {  // ---- epilogue warps (both CTAs): own TMEM -> C ----
+        const uint32_t q = warp & 3u;
+        const uint32_t L = q * 32 + lane;
+        const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
+        const uint32_t leader_empty[2] = {mapa_shared(smem_u32(&tmem_empty[0]), 0), mapa_shared(smem_u32(&tmem_empty[1]), 0)};
+        uint32_t unit = 0;
+        for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
+            const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+            const uint32_t m = tl.mb * Cfg::kSpan + 2 * tl.rp + rank + Cfg::kRowStep * i;
+            for (int hh = 0; hh < 2; hh++, unit++) {
+                const uint32_t buf = unit & 1u;
+                const float undo = scale[4 * tl.tz + 2 + hh];
+                mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
+                tcx_fence_after();
+#pragma unroll 1
+                for (int pl = 0; pl < 2; pl++) {
+                    const int ch = tcx_channel(2 * hh + pl, (int)cp);
+                    float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
+                    const bool store = ch >= 0 && m < w.N_t0;
+#pragma unroll 1
+                    for (int cb = 0; cb < 4; cb++) {
+                        uint32_t v[32];
+                        if (tl.nchunks > 0) {
+                            const uint32_t taddr = tmem + ((q * 32u) << 16) + buf * 256u + (uint32_t)(pl * 128 + cb * 32);
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                : "r"(taddr));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int x = 0; x < 32; x++) v[x] = __float_as_uint(__uint_as_float(v[x]) * undo);
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < 32; x++) v[x] = 0u;
+                        }
+                        if (store) {
+                            uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
+#pragma unroll
+                            for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+                        }
+                    }
+                }
+                tcx_fence_before();
+                mbar_arrive_remote(leader_empty[buf]);  // (the leader's own threads also go through the cluster address)
+            }
+        }
+    }
+    tcx_fence_before();
+    cluster_sync_all();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
 // FP64 copy of the merged atoms for the walk: Xd[t][7][xpad], channel-major and zero padded like X.
 __global__ void tcw_exp_atoms_f64_kernel(const float *__restrict__ X, uint32_t xpad, int t_base, double *__restrict__ Xd) {
     const int t = t_base + blockIdx.y;

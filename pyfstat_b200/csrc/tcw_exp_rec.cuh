@@ -49,7 +49,9 @@
 
 #define TCX_TAUS 128     // window lengths per tile (MMA N)
 #define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + rowstep i)
+#ifndef TCX_STAGES
 #define TCX_STAGES 8
+#endif
 #define TCX_A_BYTES 8192   // 2 pairs x 16 chunks x 256 B
 #define TCX_B_BYTES 16384  // 128 taus x 32 k x 4 B (one table)
 #define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)

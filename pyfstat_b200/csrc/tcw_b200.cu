@@ -380,6 +380,7 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     WALK_ATTR(2);
     WALK_ATTR(4);
     WALK_ATTR(8);
+    WALK_ATTR(16);
 #undef WALK_ATTR
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECTP_SMEM));
@@ -1248,8 +1249,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             // than the extra warps bring); with 4 templates 2-8 segments tie.  So: segments only until the
             // launch has ~256 columns per SM.
             int nseg = 1;
-            while (nseg < 8 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 256) nseg *= 2;
-            if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(8, atoi(env)));
+            while (nseg < 16 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 256) nseg *= 2;
+            if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(16, atoi(env)));
 #define LAUNCH_WALK(HASC, NS)                                                                                      \
     do {                                                                                                           \
         using WC = WalkCfg<NS>;                                                                                    \
@@ -1264,12 +1265,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 if (nseg == 1) LAUNCH_WALK(true, 1);
                 else if (nseg == 2) LAUNCH_WALK(true, 2);
                 else if (nseg == 4) LAUNCH_WALK(true, 4);
-                else LAUNCH_WALK(true, 8);
+                else if (nseg == 8) LAUNCH_WALK(true, 8);
+                else LAUNCH_WALK(true, 16);
             } else {
                 if (nseg == 1) LAUNCH_WALK(false, 1);
                 else if (nseg == 2) LAUNCH_WALK(false, 2);
                 else if (nseg == 4) LAUNCH_WALK(false, 4);
-                else LAUNCH_WALK(false, 8);
+                else if (nseg == 8) LAUNCH_WALK(false, 8);
+                else LAUNCH_WALK(false, 16);
             }
 #undef LAUNCH_WALK
         } else {

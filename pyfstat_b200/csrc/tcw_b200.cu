@@ -940,7 +940,9 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         if (const char *env = getenv("TCW_EXP_SCRATCH_MB")) cap = std::max<size_t>(64, (size_t)atoll(env)) << 20;
         S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, cap / tc_c_per_tpl));
         if ((uint64_t)S * tc_n_nt * tc_n_mb * tc_rs >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
-        if ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl))) return rc;
+        // a device short of memory gets smaller sub-batches instead of an error
+        while ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl)) == TCW_E_NOMEM && S > 1) S = (S + 1) / 2;
+        if (rc) return rc;
         if ((rc = ensure(h, h->d_G, (size_t)S * tc_rs * 4 * tc_U * 512))) return rc;
         if ((rc = ensure(h, h->d_scale, (size_t)S * 4 * sizeof(float)))) return rc;
     }

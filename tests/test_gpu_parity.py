@@ -760,6 +760,26 @@ def test_exp_tensor_pass_variants(gpu, oracle, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_exp_recurrence_sub_batches_and_segment_counts(gpu, monkeypatch):
+    """The correction-sum scratch caps the templates per launch ($TCW_EXP_SCRATCH_MB) and the host picks the
+    number of row segments of the walk from the launch size ($TCW_WALK_NSEG overrides): however a batch is cut,
+    the maps agree to FP64 rounding of the recurrence (1e-6 on F_mn) and the records are the same."""
+    n = 1440
+    b = synth_atoms(3, n, ("H1", "L1"), seed=616)
+    w = canonical_window("exp", 10**9, n)
+    ref, Fref = run_gpu(gpu, b, w, 0)
+    assert np.all(ref["path"] == 2)
+    for env, val in (("TCW_EXP_SCRATCH_MB", "64"), ("TCW_WALK_NSEG", "1"), ("TCW_WALK_NSEG", "16")):
+        monkeypatch.setenv(env, val)
+        res, F = run_gpu(gpu, b, w, 0)
+        monkeypatch.delenv(env)
+        assert (np.abs(F - Fref) / np.abs(Fref)).max() <= 1e-6, (env, val)
+        for k in ("m_ML", "n_ML", "m_MP", "n_MP", "status"):
+            assert np.array_equal(res[k], ref[k]), (env, val, k)
+        assert np.allclose(res["lnBtSG"], ref["lnBtSG"], atol=1e-6) and np.allclose(res["maxF"], ref["maxF"], rtol=1e-6)
+
+
+@pytest.mark.gpu
 def test_exp_recurrence_ragged_templates_and_segments(gpu, oracle):
     """Templates of different lengths (same first atom) in one launch, maps whose row count is not a
     multiple of anything (row segments of the walk, 256-row tensor-core tiles, 128-column tiles with a

@@ -300,6 +300,12 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                         const uint32_t s = it % TCX_STAGES;
                         mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
                         unsigned char *st = smem + (size_t)s * TCX_STAGE_BYTES;
+#ifdef TCX_PROBE_NO_TMA  // timing probe: no operand traffic (the MMAs run on whatever the stage holds)
+                        if (it >= TCX_STAGES) {
+                            mbar_arrive_plain(&full[s]);
+                            continue;
+                        }
+#endif
                         mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
 #pragma unroll
                         for (int pl = 0; pl < 2; pl++)

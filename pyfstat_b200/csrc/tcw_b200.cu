@@ -79,7 +79,6 @@ struct tcw_handle {
     DevBuf d_atoms, d_natoms, d_meta, d_X, d_X8, d_P, d_Fmn, d_scratch, d_zero, d_results, d_W, d_Kn, d_lut, d_flush,
         d_wins, d_tilemax, d_shift, d_G, d_C, d_scale, d_Xd;
     int tc_f16 = 1;  // tensor-core pass of the exp window: FP16 operands (default) or TF32 ($TCW_TC_TF32=1)
-    int tc_pair = 0;  // ... on CTA pairs (cta_group::2), FP16 only ($TCW_TC_2CTA=1)
     // rect launches through the persistent warp-specialised kernel: $TCW_RECT_PERSIST = 0 never,
     // 1 (default) when the launch has enough tiles to fill the GPU, 2 whenever the plan allows (tests)
     int rect_persist = 1;
@@ -369,8 +368,6 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     if (const char *v = getenv("TCW_TC_TF32")) h->tc_f16 = atoi(v) ? 0 : 1;
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX2_SMEM));
-    if (const char *v = getenv("TCW_TC_2CTA")) h->tc_pair = (atoi(v) && h->tc_f16) ? 1 : 0;
 #define WALK_ATTR(NS)                                                                                              \
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            WalkCfg<NS>::smem(true)));                                                  \
@@ -904,7 +901,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT);
     const bool exp_tc = exp_rec && !exact;
     const bool tc_f16 = h->tc_f16 != 0;
-    const uint32_t tc_rs = tc_f16 ? TcxCfg<true>::kRowStep : TcxCfg<false>::kRowStep, tc_kc = 8 * tc_rs, tc_span = 64 * tc_rs;
+    const uint32_t tc_rs = tc_f16 ? TcxCfg<true>::kRowStep : TcxCfg<false>::kRowStep, tc_kc = 8 * tc_rs, tc_span = TCX_IROWS;
     const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + tc_span - 1) / tc_span;
     const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + tc_kc - 1) / tc_kc + 10;
     const uint32_t tc_chunks = path == PATH_FAST && w.type == TCW_WINDOW_EXP ? (ep.KW + tc_kc - 1) / tc_kc : 0;
@@ -939,11 +936,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         size_t cap = 8ull << 30;
         if (const char *env = getenv("TCW_EXP_SCRATCH_MB")) cap = std::max<size_t>(64, (size_t)atoll(env)) << 20;
         S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, cap / tc_c_per_tpl));
-        if ((uint64_t)S * tc_n_nt * tc_n_mb * tc_rs >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
+        if ((uint64_t)S * tc_n_nt * tc_n_mb >= 0xFFFFFFFFull) return fail(h, TCW_E_INVALID, "too many exp tiles in one launch");
         // a device short of memory gets smaller sub-batches instead of an error
         while ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl)) == TCW_E_NOMEM && S > 1) S = (S + 1) / 2;
         if (rc) return rc;
-        if ((rc = ensure(h, h->d_G, (size_t)S * tc_rs * 4 * tc_U * 512))) return rc;
+        if ((rc = ensure(h, h->d_G, (size_t)S * 4 * tc_U * 4096))) return rc;
         if ((rc = ensure(h, h->d_scale, (size_t)S * 4 * sizeof(float)))) return rc;
     }
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
@@ -1031,16 +1028,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     uint32_t exp_TM = 0, exp_TN = 0;
     exp_tile_dims(h->exp_variant, &exp_TM, &exp_TN);
     if (path == PATH_FAST && w.type == TCW_WINDOW_EXP) {
-        const int kind = exp_tc ? (tc_f16 ? (h->tc_pair ? 4 : 3) : 1) : exp_rec ? 2 : 0;
+        const int kind = exp_tc ? (tc_f16 ? 3 : 1) : exp_rec ? 2 : 0;
         const bool hit = h->w_valid && memcmp(&h->w_key, win, sizeof(*win)) == 0 &&
                          h->w_t0_data == h->meta[0].t0_data && h->w_TAtom == TAtom && h->w_kind == kind &&
                          h->w_exact == (int)exact && h->w_KW == ep.KW && h->w_Kn == ep.Kn && h->w_TN == exp_TN;
         if (!hit) {
             const uint32_t n_tiles = (w.N_tau + exp_TN - 1) / exp_TN;
             size_t total = (size_t)ep.ec.P * n_tiles * ep.KW * exp_TN;  // table cells (threads of the builder)
-            if (kind == 1 || kind >= 3) total = (size_t)tc_n_nt * tc_chunks * (TCX_TAUS * tc_kc);
+            if (kind == 1 || kind == 3) total = (size_t)tc_n_nt * tc_chunks * (TCX_TAUS * tc_kc);
             if (kind == 0 && (rc = ensure(h, h->d_W, total * TCW_EXP_WP * sizeof(float)))) return rc;
-            if ((kind == 1 || kind >= 3) && (rc = ensure(h, h->d_W, (size_t)tc_n_nt * tc_chunks * 32768))) return rc;
+            if ((kind == 1 || kind == 3) && (rc = ensure(h, h->d_W, (size_t)tc_n_nt * tc_chunks * 32768))) return rc;
             if ((rc = ensure(h, h->d_Kn, ep.Kn.size() * sizeof(int32_t)))) return rc;
             h->w_valid = false;
             h->w_Kn = ep.Kn;  // keep the host copy alive for the async upload
@@ -1066,9 +1063,6 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             else if (kind == 3)
                 tcw_exptc_table_kernel<true><<<blocks, 256, 0, st>>>(h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
                                                                      tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
-            else if (kind == 4)
-                tcw_exptc_table2_kernel<<<blocks, 256, 0, st>>>((__half *)h->d_W.p, (const int32_t *)h->d_Kn.p, w.N_tau, tc_n_nt,
-                                                                tc_chunks, w.tau, w.dtau, TAtom, ep.delta[0], lut);
             if (kind != 2) h->launches++;
             CUDA_TRY(h, cudaGetLastError());
             CUDA_TRY(h, cudaStreamSynchronize(st));  // w_Kn host buffer consumed
@@ -1206,9 +1200,9 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
             }
             if (exp_tc) {
-                const uint32_t g_elems = tc_rs * 4 * tc_U * 2 * (2 * tc_kc);
+                const uint32_t g_elems = 4 * tc_U * 16 * (2 * tc_kc);
                 const dim3 g_grid(std::min<uint32_t>((g_elems + 255u) / 256u, 1024u), cnt);
-                const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * tc_rs;
+                const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb;
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
                 if (tc_f16) {
                     tcw_exptc_scale_kernel<<<cnt, 256, 0, st>>>((const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p,
@@ -1225,14 +1219,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb], st));
-                if (tc_f16 && h->tc_pair) {
-                    const uint32_t n_pair_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb * 4u;
-                    const uint32_t ctas2 = 2u * std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount / 2u, n_pair_tiles);
-                    tcw_exptc_map2_kernel<<<ctas2, TCX_THREADS, TCX2_SMEM, st>>>(
-                        h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_pair_tiles, (const float *)h->d_scale.p,
-                        (float *)h->d_C.p, tc_cpitch);
-                } else if (tc_f16)
+                if (tc_f16)
                     tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
                         (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,

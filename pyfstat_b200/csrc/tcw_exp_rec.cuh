@@ -31,12 +31,18 @@
 //
 // Tensor-core kernel.  D_c[(i), n] = sum_k X_c[s0 + R i + k] V[k, n], R = elements per 16 bytes: in
 // the no-swizzle K-major canonical layout a row is 16 bytes and the 8 rows of a core matrix are 16
-// bytes apart, so a descriptor laid over the plain atom array IS the Hankel operand for the rows
-// m = m0 + r + R i of row class r (tools/tc_probe/hankel_tf32.cu).  Channels are stacked in M: the
-// 128 lanes of an MMA are 2 channels x 64 rows, each 8-row group reading its own 256-byte chunk of
-// atoms (its rows' span + one stage of k), the chunks 256 bytes apart (SBO); a prep kernel lays the
-// atoms out in that chunked form -- per class r, channel pair p and block u: [c'][chunk] -- so a
-// stage's A operand of a pair is one contiguous 4-KB bulk copy.  N = 128 window lengths.  A tile is
+// bytes apart, so a descriptor laid over the plain atom array IS a Hankel operand: the 8 rows of a
+// core matrix are the map rows m, m + R, ..., m + 7 R (tools/tc_probe/hankel_tf32.cu).  The 8-row
+// groups of an MMA are free to start anywhere (SBO), so group g takes the rows of CLASS g (m = m0 + g
+// + R i'): the 64 rows of a channel are 64 CONSECUTIVE map rows, whose k ranges differ by less than
+// one stage.  (The first version laid one descriptor over 64 rows of ONE class -- a band of 64 R = 512
+// map rows per tile, executing 8 % more MMAs than needed at 120 d and 33 % more at 30 d because the k
+// range of a tile is that of its longest row.)  Channels are stacked in M: the 128 lanes of an MMA are
+// 2 channels x 64 rows, each 8-row group reading its own 256-byte chunk of atoms (its rows' span + one
+// stage of k; a start shifted by the class needs its own 16-byte aligned copy), the chunks 256 bytes
+// apart (SBO); a prep kernel lays the atoms out in that chunked form -- per channel pair p and atom
+// block u: [group][c'][chunk] -- so a stage's A operand of a pair is one contiguous 4-KB bulk copy.
+// N = 128 window lengths.  A tile is
 // processed as two units of two channel pairs (a2,b2 | ab,- with the w^2 table, Fa | Fb with the w
 // table), each unit in one half of TMEM, 8 MMAs (M128 N128, 32 bytes of K) per 24-KB stage.  Warp
 // roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C); persistent CTAs, one
@@ -48,7 +54,7 @@
 #include "tcw_generic.cuh"
 
 #define TCX_TAUS 128     // window lengths per tile (MMA N)
-#define TCX_IROWS 64     // rows per channel per tile (m = m0 + r + rowstep i)
+#define TCX_IROWS 64     // rows per channel per tile: 64 consecutive map rows
 #ifndef TCX_STAGES
 #define TCX_STAGES 8
 #endif
@@ -66,19 +72,24 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 // Operand precision of the tensor-core pass.  Both have an 11-bit significand; what differs is how many
 // elements a 16-byte core-matrix row holds, i.e. the atom stride between consecutive MMA rows:
-//   TF32: 4 -> row classes r = 0..3, tile rows m = m0 + r + 4 i, 32 k per 24-KB stage
-//   FP16: 8 -> row classes r = 0..7, tile rows m = m0 + r + 8 i, 64 k per 24-KB stage: twice the MACs per
+//   TF32: 4 -> 4 row classes, a core matrix spans 32 rows: groups 0-3 = classes 0-3 of rows m0 .. m0 + 31,
+//              groups 4-7 the same for m0 + 32 .. m0 + 63; 32 k per 24-KB stage
+//   FP16: 8 -> 8 row classes, group g = class g of rows m0 .. m0 + 63; 64 k per 24-KB stage: twice the MACs per
 //         shared-memory byte, and shared-memory bandwidth is what bounds this kernel.
 // FP16's range is handled by exact power-of-two scaling: atoms per template and channel group to
 // [2^13, 2^14), weights by 2^12; the scale is undone on the FP32 accumulators in the epilogue.
 template <bool F16>
 struct TcxCfg {
     static constexpr int kRowStep = F16 ? 8 : 4;    // elements per 16 bytes = atoms between MMA rows = row classes
-    static constexpr int kKC = 8 * kRowStep;        // k per stage (= atoms per 8-row group)
-    static constexpr int kSpan = 64 * kRowStep;     // map rows spanned by a tile
+    static constexpr int kKC = 8 * kRowStep;        // k per stage (= atoms spanned by the rows of an 8-row group)
+    static constexpr int kSpan = TCX_IROWS;         // map rows of a tile
+    static constexpr int kUStep = TCX_IROWS / kKC;  // atom blocks (of kKC) per tile row block
     static constexpr int kChunk = 2 * kKC;          // elements per 256-byte chunk (8 rows' span + one stage of k)
     static constexpr int kElem = F16 ? 2 : 4;
     static constexpr size_t kTableElems = (size_t)TCX_TAUS * kKC;  // one table of one (nt, chunk): 16 KB
+    // group gg (0..7) of a channel, row i' (0..7) of the group -> row of the tile, and the group's atom offset
+    __host__ __device__ static constexpr int row_of(int gg, int ip) { return gg % kRowStep + kRowStep * ip + kKC * (gg / kRowStep); }
+    __host__ __device__ static constexpr int atom_of(int gg) { return gg % kRowStep + kKC * (gg / kRowStep); }
 };
 #define TCX_VSCALE_LOG2 12
 
@@ -119,7 +130,7 @@ __global__ void tcw_exptc_scale_kernel(const float *__restrict__ X, uint32_t xpa
     }
 }
 
-// ---- atoms in chunked form: G[tz][r][p][u][c'][kChunk],  value = X_ch[i00 + r + kKC u + e] ----
+// ---- atoms in chunked form: G[tz][p][u][gg 8][c' 2][kChunk],  value = X_ch[i00 + atom_of(gg) + kKC u + e] ----
 template <bool F16>
 __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
                                        int t_base, uint32_t i00, uint32_t U, const float *__restrict__ scale,
@@ -127,18 +138,16 @@ __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpa
     using Cfg = TcxCfg<F16>;
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
-    const size_t per_tpl = (size_t)Cfg::kRowStep * 4 * U * 2 * Cfg::kChunk;
+    const size_t per_tpl = (size_t)4 * U * 16 * Cfg::kChunk;
     const float s2 = F16 ? scale[4 * tz] : 1.0f, s1 = F16 ? scale[4 * tz + 1] : 1.0f;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_tpl; idx += (size_t)gridDim.x * blockDim.x) {
         const uint32_t e = (uint32_t)(idx % Cfg::kChunk);
         size_t rest = idx / Cfg::kChunk;
-        const uint32_t cp = (uint32_t)rest & 1u;
-        rest >>= 1;
-        const uint32_t u = (uint32_t)(rest % U);
-        rest /= U;
-        const uint32_t p = (uint32_t)rest & 3u, r = (uint32_t)rest >> 2;
+        const uint32_t cp = (uint32_t)rest & 1u, gg = ((uint32_t)rest >> 1) & 7u;
+        rest >>= 4;
+        const uint32_t u = (uint32_t)(rest % U), p = (uint32_t)(rest / U);
         const int ch = tcx_channel((int)p, (int)cp);
-        const uint64_t j = (uint64_t)i00 + r + (uint64_t)Cfg::kKC * u + e;
+        const uint64_t j = (uint64_t)i00 + (uint32_t)Cfg::atom_of((int)gg) + (uint64_t)Cfg::kKC * u + e;
         float v = 0.0f;
         if (ch >= 0 && j < numAtoms) v = __ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j);
         if (F16) reinterpret_cast<__half *>(Gv)[(size_t)tz * per_tpl + idx] = __float2half_rn(v * (ch < 3 ? s2 : s1));
@@ -221,7 +230,7 @@ __device__ __forceinline__ void tcx_fence_before() { asm volatile("tcgen05.fence
 __device__ __forceinline__ void tcx_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 struct TcxTile {
-    uint32_t tz, r, mb, nt;
+    uint32_t tz, mb, nt;
     int nchunks;
 };
 template <bool F16>
@@ -231,17 +240,14 @@ __device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n
     using Cfg = TcxCfg<F16>;
     TcxTile tl;
     tl.tz = j % cnt;
-    uint32_t rest = j / cnt;
-    tl.r = rest % Cfg::kRowStep;
-    rest /= Cfg::kRowStep;
+    const uint32_t rest = j / cnt;
     tl.mb = rest % n_mb;
     tl.nt = n_nt - 1u - rest / n_mb;  // widest windows first
     const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
     const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
-    const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan + tl.r;
+    const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan;  // the tile's first row has the longest k range
     const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
-    const bool rows = tl.mb * Cfg::kSpan + tl.r < w.N_t0;
-    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
+    tl.nchunks = k_end > 0 ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
     return tl;
 }
 
@@ -292,8 +298,8 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
             uint32_t it = 0;
             for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
                 const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-                // chunks are 256 B; a stage's A operand of pair p: 16 chunks (8 u x 2 c') = 4 KB at u = 8 mb + c
-                const unsigned char *gA = G + (((size_t)tl.tz * Cfg::kRowStep + tl.r) * 4 * U + 8ull * tl.mb) * 512;  // + (p U + c) * 512
+                // chunks are 256 B; a stage's A operand of pair p: 16 chunks (8 groups x 2 c') = 4 KB at u = kUStep mb + c
+                const unsigned char *gA = G + ((size_t)tl.tz * 4 * U + (size_t)Cfg::kUStep * tl.mb) * 4096;  // + (p U + c) * 4096
                 const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768;  // + c * 32 KB (+ 16 KB: w^2)
                 for (int hh = 0; hh < 2; hh++)
                     for (int c = 0; c < tl.nchunks; c++, it++) {
@@ -309,7 +315,7 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                         mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
 #pragma unroll
                         for (int pl = 0; pl < 2; pl++)
-                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 512, 4096, &full[s]);
+                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 4096, 4096, &full[s]);
                         bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX_B_BYTES, &full[s]);
                     }
             }
@@ -351,11 +357,12 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
     } else {  // ---- epilogue warps: TMEM -> C ----
         const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
         const uint32_t L = q * 32 + lane;
-        const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
+        const uint32_t grp = L >> 3, gg = grp >> 1, cp = grp & 1u;  // 8-row group of the MMA: [gg][c']
+        const uint32_t row = (uint32_t)Cfg::row_of((int)gg, (int)(L & 7u));
         uint32_t unit = 0;
         for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
             const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-            const uint32_t m = tl.mb * Cfg::kSpan + tl.r + Cfg::kRowStep * i;
+            const uint32_t m = tl.mb * Cfg::kSpan + row;
             for (int hh = 0; hh < 2; hh++, unit++) {
                 const uint32_t buf = unit & 1u;
                 const float undo = F16 ? scale[4 * tl.tz + 2 + hh] : 1.0f;
@@ -458,297 +465,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// ---- the same pass on CTA PAIRS (tcgen05 cta_group::2), FP16 only ---------------------------------------
-// The single-CTA kernel is bounded by shared memory: an M128 N128 MMA reads 8 KB of operands in 64 cycles -- all
-// of the SM's 128 B/clk -- while TMA writes the next stages into the same memory (tensor pipe 70 % active).
-// A CTA pair runs ONE M256 N128 MMA across two SMs: each SM holds its own 128 rows of A (its row class) and
-// HALF of B (64 window lengths), the halves are exchanged between the two tensor cores, so an SM reads
-// 4 + 2 KB per MMA and TMA writes 16 instead of 24 KB per stage.  The pair works on row classes 2 r' and
-// 2 r' + 1 of one (template, row block, tau tile): same weights, k ranges that differ by at most one atom.
-// Protocol: both CTAs run a TMA producer (own shared memory, own `full` barriers) and 4 epilogue warps (own
-// TMEM); the leader's MMA thread waits for its own `full` barrier and for `peer_full`, on which the peer's
-// otherwise idle warp 1 forwards the peer's `full` completions (remote mbarrier arrive); tcgen05.commit
-// multicasts `empty` / `tmem_full` to both CTAs; the peer's epilogue threads arrive remotely on the leader's
-// `tmem_empty`.
-// MEASURED (8 x 120-d maps): correct (same maps as the single-CTA kernel), but NOT faster -- 10.5 ms against
-// 9.2-9.6 ms; 15.1 ms with a single forwarding thread; more stages change nothing.  A pair MMA (M256 N128 K16)
-// takes ~133 cycles where the single-CTA one (M128 N128 K16) takes ~114 and the tensor-pipe floor is 64: with
-// shared memory relieved the limit moves elsewhere -- presumably the exchange of the B halves between the two
-// SMs (2 KB per MMA in 16-byte core-matrix rows of the no-swizzle layout), which ncu does not expose.  Kept as
-// an opt-in experiment ($TCW_TC_2CTA=1, tests/test_gpu_parity.py::test_exp_tensor_pass_cta_pair).
-#define TCX2_STAGES 10
-#define TCX2_A_BYTES 8192
-#define TCX2_B_BYTES 8192
-#define TCX2_STAGE_BYTES (TCX2_A_BYTES + TCX2_B_BYTES)
-#define TCX2_SMEM (TCX2_STAGES * TCX2_STAGE_BYTES + 128)
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tWAITC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAITC_DONE;\n\tbra WAITC_LOOP;\n\tWAITC_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    __syncwarp();
-    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-    __syncwarp();
-}
-__device__ __forceinline__ void tcx2_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void tcx2_commit(uint64_t *bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-            smem_u32(bar)),
-        "h"((uint16_t)3)
-        : "memory");
-}
-
-// Weight tables for the pair kernel: Vt2[nt][chunk][table][half][kq 8][ng 8][nr 8][kk 8] -- the 64 window lengths
-// of a CTA are one contiguous 8-KB block per table and stage.
-__global__ void tcw_exptc_table2_kernel(__half *__restrict__ Vt, const int32_t *__restrict__ Kn, uint32_t N_tau,
-                                        uint32_t n_nt, uint32_t n_chunks, uint32_t tau, uint32_t dtau, uint32_t TAtom,
-                                        int32_t delta, const ExpLut lut) {
-    using Cfg = TcxCfg<true>;
-    constexpr uint32_t TE = (uint32_t)Cfg::kTableElems;  // 8192
-    const size_t total = (size_t)n_nt * n_chunks * TE;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t off = (uint32_t)(idx % TE);
-        const uint32_t kk = off & 7u, nr = (off >> 3) & 7u, ng = (off >> 6) & 7u, kq = (off >> 9) & 7u, half_ = off >> 12;
-        const size_t rest = idx / TE;
-        const uint32_t chunk = (uint32_t)(rest % n_chunks), nt = (uint32_t)(rest / n_chunks);
-        const uint32_t k = chunk * Cfg::kKC + kq * 8 + kk, n = nt * TCX_TAUS + half_ * 64 + ng * 8 + nr;
-        double v1 = 0.0, v2 = 0.0;
-        if (n < N_tau && (int32_t)k <= Kn[n]) {
-            const uint32_t tau_n = tau + n * dtau;
-            const long long t_rel = (long long)k * TAtom + delta;
-            if (t_rel >= 0 && t_rel <= (long long)TCW_EXP_EFOLDING * tau_n) {
-                const double x = __ddiv_rn((double)t_rel, (double)tau_n);
-                const double wl = fast_neg_exp_lut(x, lut), we = exp(-x);
-                v1 = wl - we;
-                v2 = (wl - we) * (wl + we);
-            }
-        }
-        __half *base = Vt + rest * 2 * TE;
-        base[off] = __float2half_rn((float)ldexp(v1, TCX_VSCALE_LOG2));
-        base[TE + off] = __float2half_rn((float)ldexp(v2, TCX_VSCALE_LOG2));
-    }
-}
-
-struct Tcx2Tile {
-    uint32_t tz, rp, mb, nt;
-    int nchunks;
-};
-__device__ __forceinline__ Tcx2Tile tcx2_tile(uint32_t j, uint32_t cnt, uint32_t n_mb, uint32_t n_nt, const MapWindow &w,
-                                              uint32_t i00, const TplMeta *__restrict__ meta, int t_base,
-                                              const int32_t *__restrict__ Kn) {
-    using Cfg = TcxCfg<true>;
-    Tcx2Tile tl;
-    tl.tz = j % cnt;
-    uint32_t rest = j / cnt;
-    tl.rp = rest & 3u;  // row classes 2 rp and 2 rp + 1
-    rest >>= 2;
-    tl.mb = rest % n_mb;
-    tl.nt = n_nt - 1u - rest / n_mb;
-    const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
-    const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
-    const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan + 2 * tl.rp;  // the earlier class: longer k range
-    const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
-    const bool rows = tl.mb * Cfg::kSpan + 2 * tl.rp < w.N_t0;
-    tl.nchunks = (rows && k_end > 0) ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
-    return tl;
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCX_THREADS, 1)
-tcw_exptc_map2_kernel(const void *__restrict__ Gv, uint32_t U, const void *__restrict__ Vtv, uint32_t n_chunks_tab,
-                      const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
-                      MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles,
-                      const float *__restrict__ scale, float *__restrict__ C, uint32_t cpitch) {
-    using Cfg = TcxCfg<true>;
-    extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
-    __shared__ __align__(8) uint64_t full[TCX2_STAGES], empty[TCX2_STAGES], peer_full[TCX2_STAGES], tmem_full[2], tmem_empty[2];
-    __shared__ uint32_t tmem_base_s;
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const unsigned char *G = reinterpret_cast<const unsigned char *>(Gv);
-    const unsigned char *Vt = reinterpret_cast<const unsigned char *>(Vtv);
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < TCX2_STAGES; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-            mbar_init(&peer_full[s], 1);
-        }
-#pragma unroll
-        for (int b = 0; b < 2; b++) {
-            mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], 256);  // the epilogue threads of BOTH CTAs (used in the leader only)
-        }
-        mbar_fence_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tcx_fence_before();
-    cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
-    tcx_fence_after();
-    const uint32_t tmem = tmem_base_s;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer (both CTAs, own shared memory) ----
-            uint32_t it = 0;
-            for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
-                const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-                const uint32_t r = 2 * tl.rp + rank;
-                const unsigned char *gA = G + (((size_t)tl.tz * Cfg::kRowStep + r) * 4 * U + 8ull * tl.mb) * 512;  // + (p U + c) * 512
-                const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768 + (size_t)rank * 8192;       // + c * 32 KB (+ 16 KB: w^2)
-                for (int hh = 0; hh < 2; hh++)
-                    for (int c = 0; c < tl.nchunks; c++, it++) {
-                        const uint32_t s = it % TCX2_STAGES;
-                        mbar_wait(&empty[s], ((it / TCX2_STAGES) & 1u) ^ 1u);
-                        unsigned char *st = smem + (size_t)s * TCX2_STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full[s], TCX2_STAGE_BYTES);
-#pragma unroll
-                        for (int pl = 0; pl < 2; pl++)
-                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 512, 4096, &full[s]);
-                        bulk_g2s(st + TCX2_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX2_B_BYTES, &full[s]);
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        if (rank == 1) {  // ---- peer: forward `full` completions to the leader, one lane per stage ----
-            if (lane < TCX2_STAGES) {
-                uint32_t total = 0;
-                for (uint32_t j = pair; j < n_tiles; j += n_pairs)
-                    total += 2u * (uint32_t)tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn).nchunks;
-                const uint32_t remote = mapa_shared(smem_u32(&peer_full[lane]), 0);
-                uint32_t use = 0;
-                for (uint32_t it = (uint32_t)lane; it < total; it += TCX2_STAGES, use++) {
-                    mbar_wait(&full[lane], use & 1u);
-                    mbar_arrive_remote(remote);
-                }
-            }
-        } else if (lane == 0) {  // ---- leader: MMA issuer for the pair ----
-            constexpr uint32_t idesc = tcx_idesc(256, TCX_TAUS, true);
-            const uint64_t da = tcx_desc(0, 16, 256);    // A: this CTA's 128 rows
-            const uint64_t db = tcx_desc(0, 1024, 128);  // B: this CTA's 64 columns, [kq][ng 8][8][16 B]
-            uint32_t it = 0, unit = 0;
-            for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
-                const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-                for (int hh = 0; hh < 2; hh++, unit++) {
-                    const uint32_t buf = unit & 1u;
-                    mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
-                    tcx_fence_after();
-                    const uint32_t d0 = tmem + buf * 256u;
-                    for (int c = 0; c < tl.nchunks; c++, it++) {
-                        const uint32_t s = it % TCX2_STAGES;
-                        mbar_wait(&full[s], (it / TCX2_STAGES) & 1u);
-                        mbar_wait(&peer_full[s], (it / TCX2_STAGES) & 1u);
-                        tcx_fence_after();
-                        const uint32_t a0 = smem_u32(smem + (size_t)s * TCX2_STAGE_BYTES), b0 = a0 + TCX2_A_BYTES;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const uint64_t bd = db | (uint64_t)(((b0 + q * 2048) >> 4) & 0x3FFF);
-#pragma unroll
-                            for (int pl = 0; pl < 2; pl++) {
-                                const uint64_t ad = da | (uint64_t)(((a0 + pl * 4096 + q * 32) >> 4) & 0x3FFF);
-                                tcx2_mma(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
-                            }
-                        }
-                        tcx2_commit(&empty[s]);
-                    }
-                    if (tl.nchunks > 0) tcx2_commit(&tmem_full[buf]);
-                    else {
-                        mbar_arrive_plain(&tmem_full[buf]);
-                        mbar_arrive_remote(mapa_shared(smem_u32(&tmem_full[buf]), 1));
-                    }
-                }
-            }
-        }
-    } else {  // ---- epilogue warps (both CTAs): own TMEM -> C ----
-        const uint32_t q = warp & 3u;
-        const uint32_t L = q * 32 + lane;
-        const uint32_t grp = L >> 3, ib = grp >> 1, cp = grp & 1u, i = ib * 8 + (L & 7u);
-        const uint32_t leader_empty[2] = {mapa_shared(smem_u32(&tmem_empty[0]), 0), mapa_shared(smem_u32(&tmem_empty[1]), 0)};
-        uint32_t unit = 0;
-        for (uint32_t j = pair; j < n_tiles; j += n_pairs) {
-            const Tcx2Tile tl = tcx2_tile(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-            const uint32_t m = tl.mb * Cfg::kSpan + 2 * tl.rp + rank + Cfg::kRowStep * i;
-            for (int hh = 0; hh < 2; hh++, unit++) {
-                const uint32_t buf = unit & 1u;
-                const float undo = scale[4 * tl.tz + 2 + hh];
-                mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
-                tcx_fence_after();
-#pragma unroll 1
-                for (int pl = 0; pl < 2; pl++) {
-                    const int ch = tcx_channel(2 * hh + pl, (int)cp);
-                    float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
-                    const bool store = ch >= 0 && m < w.N_t0;
-#pragma unroll 1
-                    for (int cb = 0; cb < 4; cb++) {
-                        uint32_t v[32];
-                        if (tl.nchunks > 0) {
-                            const uint32_t taddr = tmem + ((q * 32u) << 16) + buf * 256u + (uint32_t)(pl * 128 + cb * 32);
-                            asm volatile(
-                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                : "r"(taddr));
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int x = 0; x < 32; x++) v[x] = __float_as_uint(__uint_as_float(v[x]) * undo);
-                        } else {
-#pragma unroll
-                            for (int x = 0; x < 32; x++) v[x] = 0u;
-                        }
-                        if (store) {
-                            uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
-#pragma unroll
-                            for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
-                        }
-                    }
-                }
-                tcx_fence_before();
-                mbar_arrive_remote(leader_empty[buf]);  // (the leader's own threads also go through the cluster address)
-            }
-        }
-    }
-    tcx_fence_before();
-    cluster_sync_all();
-    if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
 // FP64 copy of the merged atoms for the walk: Xd[t][7][xpad], channel-major and zero padded like X.

@@ -898,14 +898,17 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     }
     // exponential window on a canonical grid: FP64 recurrence down the rows (+ the tensor-core correction
     // in lookup-table mode), tcw_exp_rec.cuh; TCW_EXP_DIRECT keeps the tiled direct sum
-    const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT);
+    // (an uploaded table that is not e^{-i dx} takes the direct sum: the tensor-core pass relies on the table's
+    // deviation from the exact exponential being small)
+    const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT) &&
+                         (exact || h->lut_canonical);
     const bool exp_tc = exp_rec && !exact;
     const bool tc_f16 = h->tc_f16 != 0;
     const uint32_t tc_rs = tc_f16 ? TcxCfg<true>::kRowStep : TcxCfg<false>::kRowStep, tc_kc = 8 * tc_rs, tc_span = TCX_IROWS;
     const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + tc_span - 1) / tc_span;
     const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + tc_kc - 1) / tc_kc + 10;
     const uint32_t tc_chunks = path == PATH_FAST && w.type == TCW_WINDOW_EXP ? (ep.KW + tc_kc - 1) / tc_kc : 0;
-    const size_t tc_c_per_tpl = (size_t)TCW_NCH * w.N_t0 * tc_cpitch * sizeof(float);
+    const size_t tc_c_per_tpl = (size_t)w.N_t0 * tc_cpitch * TcxC::kBytesPerCell;
 
     // ---- buffers ----
     int rc;
@@ -932,7 +935,17 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     if (exp_rec) {  // FP64 copies of the atoms for the walk
         if ((rc = ensure(h, h->d_Xd, (size_t)T * TCW_NCH * h->xpad * sizeof(double)))) return rc;
     }
-    if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (28 B per cell): cap it at 8 GB
+    // FP16 correction sums: |accumulator| <= max|atom| sum_k |V| <= 2^14 2^12 (e^{dx/2} - 1) 2.01 (terms of the window),
+    // stored times 2^-tc_shift so that the bound stays below 2^15
+    int tc_shift = 0;
+    if (exp_tc) {
+        const double dx = h->lut_xmax / (double)h->lut_len;
+        const double tau_max = (double)w.tau + (double)(w.N_tau - 1) * (double)w.dtau;
+        const double terms = std::min((double)ep.KW, tau_max / (double)TAtom + 1.0) + 1.0;
+        const double bound = ldexp(2.01 * expm1(0.5 * dx) * terms, 14 + TCX_VSCALE_LOG2);
+        while (tc_shift < 60 && ldexp(bound, -tc_shift) > 32768.0) tc_shift++;
+    }
+    if (exp_tc) {  // the correction sums of a sub-batch live in an HBM scratch (20 B per cell): cap it at 8 GB
         size_t cap = 8ull << 30;
         if (const char *env = getenv("TCW_EXP_SCRATCH_MB")) cap = std::max<size_t>(64, (size_t)atoll(env)) << 20;
         S = (int)std::max<size_t>(1, std::min<size_t>((size_t)S, cap / tc_c_per_tpl));
@@ -1190,7 +1203,10 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             else LAUNCH_RECT(1, false);
 #undef LAUNCH_RECT
         } else if (exp_rec) {
-            const float *corr = nullptr;
+            // correction sums of the sub-batch: group A (a2, b2, ab) then group F (Fa, Fb), TcxC
+            unsigned char *c_a = (unsigned char *)h->d_C.p;
+            unsigned char *c_f = c_a + (size_t)cnt * 3 * w.N_t0 * tc_cpitch * TcxC::kElemA;
+            const unsigned char *corr = nullptr;
             tcw_exp_atoms_f64_kernel<<<dim3((h->xpad + 255) / 256, cnt), 256, 0, st>>>(
                 (const float *)h->d_X.p, h->xpad, t_base, (double *)h->d_Xd.p);
             h->launches++;
@@ -1204,17 +1220,17 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 const dim3 g_grid(std::min<uint32_t>((g_elems + 255u) / 256u, 1024u), cnt);
                 const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb;
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);
+                tcw_exptc_scale_kernel<<<cnt, 256, 0, st>>>((const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p,
+                                                            t_base, (float *)h->d_scale.p);
+                h->launches++;
                 if (tc_f16) {
-                    tcw_exptc_scale_kernel<<<cnt, 256, 0, st>>>((const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p,
-                                                                t_base, (float *)h->d_scale.p);
-                    h->launches++;
                     tcw_exptc_atoms_kernel<true><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
                                                                          (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
                                                                          tc_U, (const float *)h->d_scale.p, h->d_G.p);
                 } else {
                     tcw_exptc_atoms_kernel<false><<<g_grid, 256, 0, st>>>((const float *)h->d_X.p, h->xpad,
                                                                           (const TplMeta *)h->d_meta.p, t_base, ep.ec.i00[0],
-                                                                          tc_U, nullptr, h->d_G.p);
+                                                                          tc_U, (const float *)h->d_scale.p, h->d_G.p);
                 }
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
@@ -1222,16 +1238,16 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 if (tc_f16)
                     tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, (const float *)h->d_scale.p,
-                        (float *)h->d_C.p, tc_cpitch);
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, -tc_shift), c_a, c_f, tc_cpitch);
                 else
                     tcw_exptc_map_kernel<false><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, nullptr, (float *)h->d_C.p, tc_cpitch);
+                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, TCX_VSCALE_LOG2 - tc_shift), c_a, c_f,
+                        tc_cpitch);
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
-                corr = (const float *)h->d_C.p;
+                corr = c_a;
             }
             // row segments per column: measured (B200, 120-d maps): with 8 templates (46 000 columns) one
             // segment is fastest (1.80 ms; 2: 1.89, 4: 2.01, 8: 2.15 -- pass 1 of the segmented walk costs more
@@ -1248,7 +1264,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         tcw_exp_walk_kernel<HASC, NS><<<grid, WC::kThreads, smem, st>>>(                                           \
             (const double *)h->d_Xd.p, h->xpad, (const int32_t *)h->d_Kn.p,                                        \
             (const TplMeta *)h->d_meta.p, t_base, w,                                                               \
-            ep.ec.i00[0], ep.delta[0], TAtom, corr, tc_cpitch, fmn, p_maxkey, p_flags);                            \
+            ep.ec.i00[0], ep.delta[0], TAtom, corr, c_f, tc_cpitch, (const float *)h->d_scale.p,                   \
+            ldexpf(1.0f, tc_shift), fmn, p_maxkey, p_flags);                                                       \
     } while (0)
             if (exp_tc) {
                 if (nseg == 1) LAUNCH_WALK(true, 1);
@@ -1619,3 +1636,15 @@ extern "C" int tcw_microbench(tcw_handle *h, double *ffma_tflops, double *dadd_t
     h->launches += 4;
     return TCW_OK;
 }
+
+#ifdef TCX_TIMING
+// development build only (-DTCX_TIMING): role wait cycles of the tensor-core pass, see tcw_exp_rec.cuh
+extern "C" int tcw_debug_tcx_timing(unsigned long long *out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, tcx_timing, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(tcx_timing, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

@@ -50,6 +50,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "tcw_common.cuh"
 #include "tcw_generic.cuh"
 
@@ -63,6 +65,7 @@
 #define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)
 #define TCX_THREADS 192
 #define TCX_SMEM (TCX_STAGES * TCX_STAGE_BYTES + 128)
+#define TCX_EPI_PITCH 36  // floats per row of an epilogue warp's 32 x 32 transposition tile (144 B)
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
@@ -92,6 +95,28 @@ struct TcxCfg {
     __host__ __device__ static constexpr int atom_of(int gg) { return gg % kRowStep + kKC * (gg / kRowStep); }
 };
 #define TCX_VSCALE_LOG2 12
+
+// Storage of the correction sums C between the tensor-core pass and the walk, per channel GROUP:
+//   group A = a2, b2, ab (the antenna-pattern matrix M), group F = Fa, Fb (the data vector v), F = v^T M^-1 v.
+// A relative error eps in M moves F by ~eps cond(M), the same error in v by ~eps sqrt(cond(M)) (v ~ N(0, M/2)),
+// and cond reaches 1e4 on single-detector data.  FP16 (2^-11 of a sum that is <= 2e-3 of the window sum: 1e-6)
+// is therefore safe for group F and not for group A: measured on H1-only 15-d maps, all-FP16 raises the largest
+// F_mn error from 8.9e-5 to 1.2e-4 of the oracle's value (bar 1e-4); two-detector maps 2.6e-5 -> 3.1e-5.
+// Default: A in FP32, F in FP16 -- 20 bytes per cell instead of 28.
+#ifndef TCX_CA_F16
+#define TCX_CA_F16 0
+#endif
+#ifndef TCX_CF_F16
+#define TCX_CF_F16 1
+#endif
+struct TcxC {
+    static constexpr bool kA16 = TCX_CA_F16 != 0, kF16 = TCX_CF_F16 != 0;
+    static constexpr int kElemA = kA16 ? 2 : 4, kElemF = kF16 ? 2 : 4;
+    static constexpr int kBytesPerCell = 3 * kElemA + 4 * kElemF;
+    // a warp's row in the walk's ring: [a2 | b2 | ab | Fa_re | Fa_im | Fb_re | Fb_im] x 32 window lengths
+    static constexpr int kRowA = 32 * kElemA, kRowF = 32 * kElemF, kRowBytes = 3 * kRowA + 4 * kRowF;
+    static constexpr int kPiecesA = 3 * kRowA / 16, kPiecesF = 4 * kRowF / 16;
+};
 
 // channel of (pair p, slot c'): a2,b2 | ab,- | Fa_re,Fa_im | Fb_re,Fb_im ; -1 = unused slot
 __device__ __forceinline__ int tcx_channel(int p, int cp) {
@@ -139,7 +164,7 @@ __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpa
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
     const size_t per_tpl = (size_t)4 * U * 16 * Cfg::kChunk;
-    const float s2 = F16 ? scale[4 * tz] : 1.0f, s1 = F16 ? scale[4 * tz + 1] : 1.0f;
+    const float s2 = scale[4 * tz], s1 = scale[4 * tz + 1];
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_tpl; idx += (size_t)gridDim.x * blockDim.x) {
         const uint32_t e = (uint32_t)(idx % Cfg::kChunk);
         size_t rest = idx / Cfg::kChunk;
@@ -151,7 +176,7 @@ __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpa
         float v = 0.0f;
         if (ch >= 0 && j < numAtoms) v = __ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j);
         if (F16) reinterpret_cast<__half *>(Gv)[(size_t)tz * per_tpl + idx] = __float2half_rn(v * (ch < 3 ? s2 : s1));
-        else reinterpret_cast<float *>(Gv)[(size_t)tz * per_tpl + idx] = tf32_rna(v);
+        else reinterpret_cast<float *>(Gv)[(size_t)tz * per_tpl + idx] = tf32_rna(v * (ch < 3 ? s2 : s1));
     }
 }
 
@@ -229,29 +254,66 @@ __device__ __forceinline__ void tcx_commit(uint64_t *bar) {
 __device__ __forceinline__ void tcx_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcx_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// -DTCX_TIMING (development): cycles each role spends waiting, summed over the CTAs of every launch
+// (tools/tcx_timing.py reads them through tcw_debug_tcx_timing)
+#ifdef TCX_TIMING
+__device__ unsigned long long tcx_timing[16];
+#define TCX_T0() const long long _t0 = clock64()
+#define TCX_T1(acc) acc += clock64() - _t0
+#else
+#define TCX_T0()
+#define TCX_T1(acc)
+#endif
+
 struct TcxTile {
     uint32_t tz, mb, nt;
     int nchunks;
 };
+// Tile j -> (template, row block, tau tile) and its number of k stages.  The two global loads a tile needs
+// (the template's atom count, the longest window of the tau tile) are issued one tile ahead (tcx_tile_load)
+// and consumed when the tile starts (tcx_tile_finish): an L2 round trip per tile in the single thread that
+// issues the MMAs otherwise shows as 3-6 % of the pass.
+struct TcxRaw {
+    uint32_t numAtoms;
+    int32_t kn;
+};
+__device__ __forceinline__ TcxRaw tcx_tile_load(uint32_t j, uint32_t n_tiles, uint32_t cnt, uint32_t n_mb, uint32_t n_nt,
+                                                const MapWindow &w, const TplMeta *__restrict__ meta, int t_base,
+                                                const int32_t *__restrict__ Kn) {
+    TcxRaw r;
+    r.numAtoms = 0;
+    r.kn = -1;
+    if (j < n_tiles) {
+        const uint32_t tz = j % cnt, nt = n_nt - 1u - (j / cnt) / n_mb;
+        const uint32_t n_last = min(nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
+        r.numAtoms = __ldg(&meta[t_base + tz].numAtoms);
+        r.kn = __ldg(Kn + n_last);
+    }
+    return r;
+}
 template <bool F16>
-__device__ __forceinline__ TcxTile tcx_tile(uint32_t j, uint32_t cnt, uint32_t n_mb, uint32_t n_nt, const MapWindow &w,
-                                            uint32_t i00, const TplMeta *__restrict__ meta, int t_base,
-                                            const int32_t *__restrict__ Kn) {
+__device__ __forceinline__ TcxTile tcx_tile_finish(uint32_t j, const TcxRaw &raw, uint32_t cnt, uint32_t n_mb, uint32_t n_nt,
+                                                   uint32_t i00) {
     using Cfg = TcxCfg<F16>;
     TcxTile tl;
     tl.tz = j % cnt;
     const uint32_t rest = j / cnt;
     tl.mb = rest % n_mb;
     tl.nt = n_nt - 1u - rest / n_mb;  // widest windows first
-    const uint32_t numAtoms = meta[t_base + tl.tz].numAtoms;
-    const uint32_t n_last = min(tl.nt * TCX_TAUS + TCX_TAUS, w.N_tau) - 1u;
     const long long s_first = (long long)i00 + (long long)tl.mb * Cfg::kSpan;  // the tile's first row has the longest k range
-    const long long k_end = min((long long)Kn[n_last] + 1, (long long)numAtoms - s_first);
+    const long long k_end = min((long long)raw.kn + 1, (long long)raw.numAtoms - s_first);
     tl.nchunks = k_end > 0 ? (int)((k_end + Cfg::kKC - 1) / Cfg::kKC) : 0;
     return tl;
 }
+#define TCX_TILE_LOOP_BEGIN                                                                        \
+    TcxRaw raw_next = tcx_tile_load(blockIdx.x, n_tiles, cnt, n_mb, n_nt, w, meta, t_base, Kn);    \
+    for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {                                   \
+        const TcxTile tl = tcx_tile_finish<F16>(j, raw_next, cnt, n_mb, n_nt, i00);                \
+        raw_next = tcx_tile_load(j + gridDim.x, n_tiles, cnt, n_mb, n_nt, w, meta, t_base, Kn);
 
-// C[tz][ch][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128).
+// CA[tz][3][m][cpitch], CF[tz][4][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128)
+// in the accumulators' own (scaled) units times the power of two `cs`, which the host derives from a bound on
+// sum_k |X V| so that no FP16 value can overflow; the walk undoes the scaling.  Precision per group: TcxC.
 // A tile is processed as two UNITS -- channel pairs (a2,b2 | ab,-) with the w^2 table, then (Fa | Fb) with
 // the w table; no operand is shared between them, so the split costs no traffic -- each accumulating into
 // one half of TMEM (2 x 128 columns): the epilogue warps drain unit u while the MMAs of unit u + 1 run.
@@ -260,11 +322,12 @@ __global__ void __launch_bounds__(TCX_THREADS, 1)
 tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__restrict__ Vtv, uint32_t n_chunks_tab,
                      const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, uint32_t cnt,
                      MapWindow w, uint32_t i00, uint32_t n_nt, uint32_t n_mb, uint32_t n_tiles,
-                     const float *__restrict__ scale, float *__restrict__ C, uint32_t cpitch) {
+                     float cs, unsigned char *__restrict__ CA, unsigned char *__restrict__ CF, uint32_t cpitch) {
     using Cfg = TcxCfg<F16>;
     extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
     __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float stage_s[4][32 * TCX_EPI_PITCH];  // the epilogue warps' transposition tiles
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned char *G = reinterpret_cast<const unsigned char *>(Gv);
@@ -296,15 +359,24 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA producer ----
             uint32_t it = 0;
-            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-                const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+            long long tp_wait = 0, tp_total = 0;
+            (void)tp_wait;
+            (void)tp_total;
+#ifdef TCX_TIMING
+            const long long tp_begin = clock64();
+#endif
+            TCX_TILE_LOOP_BEGIN
                 // chunks are 256 B; a stage's A operand of pair p: 16 chunks (8 groups x 2 c') = 4 KB at u = kUStep mb + c
                 const unsigned char *gA = G + ((size_t)tl.tz * 4 * U + (size_t)Cfg::kUStep * tl.mb) * 4096;  // + (p U + c) * 4096
                 const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768;  // + c * 32 KB (+ 16 KB: w^2)
                 for (int hh = 0; hh < 2; hh++)
                     for (int c = 0; c < tl.nchunks; c++, it++) {
                         const uint32_t s = it % TCX_STAGES;
-                        mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
+                        {
+                            TCX_T0();
+                            mbar_wait(&empty[s], ((it / TCX_STAGES) & 1u) ^ 1u);
+                            TCX_T1(tp_wait);
+                        }
                         unsigned char *st = smem + (size_t)s * TCX_STAGE_BYTES;
 #ifdef TCX_PROBE_NO_TMA  // timing probe: no operand traffic (the MMAs run on whatever the stage holds)
                         if (it >= TCX_STAGES) {
@@ -319,6 +391,10 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                         bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX_B_BYTES, &full[s]);
                     }
             }
+#ifdef TCX_TIMING
+            atomicAdd(&tcx_timing[0], (unsigned long long)(clock64() - tp_begin));
+            atomicAdd(&tcx_timing[1], (unsigned long long)tp_wait);
+#endif
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
@@ -326,16 +402,35 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
             const uint64_t da = tcx_desc(0, 16, 256);      // A: K halves 16 B apart, 8-row groups = chunks 256 B apart
             const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][16 B]: K steps 2 KB apart, 8-column groups 128 B
             uint32_t it = 0, unit = 0;
-            for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-                const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
+            long long tm_dec = 0, tm_tmem = 0, tm_full = 0, tm_n = 0;
+            (void)tm_dec, (void)tm_tmem, (void)tm_full, (void)tm_n;
+#ifdef TCX_TIMING
+            const long long tm_begin = clock64();
+#endif
+#ifdef TCX_TIMING
+            long long _td = clock64();
+#endif
+            TCX_TILE_LOOP_BEGIN
+#ifdef TCX_TIMING
+                tm_dec += (tl.nchunks >= 0 ? clock64() : 0) - _td;
+                tm_n += 16 * tl.nchunks;
+#endif
                 for (int hh = 0; hh < 2; hh++, unit++) {
                     const uint32_t buf = unit & 1u;
-                    mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
+                    {
+                        TCX_T0();
+                        mbar_wait(&tmem_empty[buf], ((unit >> 1) & 1u) ^ 1u);
+                        TCX_T1(tm_tmem);
+                    }
                     tcx_fence_after();
                     const uint32_t d0 = tmem + buf * 256u;
                     for (int c = 0; c < tl.nchunks; c++, it++) {
                         const uint32_t s = it % TCX_STAGES;
-                        mbar_wait(&full[s], (it / TCX_STAGES) & 1u);
+                        {
+                            TCX_T0();
+                            mbar_wait(&full[s], (it / TCX_STAGES) & 1u);
+                            TCX_T1(tm_full);
+                        }
                         tcx_fence_after();
                         const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
 #pragma unroll
@@ -352,62 +447,132 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                     if (tl.nchunks > 0) tcx_commit(&tmem_full[buf]);
                     else mbar_arrive_plain(&tmem_full[buf]);
                 }
+#ifdef TCX_TIMING
+                _td = clock64();
+#endif
             }
+#ifdef TCX_TIMING
+            atomicAdd(&tcx_timing[2], (unsigned long long)(clock64() - tm_begin));
+            atomicAdd(&tcx_timing[3], (unsigned long long)tm_dec);
+            atomicAdd(&tcx_timing[4], (unsigned long long)tm_tmem);
+            atomicAdd(&tcx_timing[5], (unsigned long long)tm_full);
+            atomicAdd(&tcx_timing[6], (unsigned long long)tm_n);
+#endif
         }
     } else {  // ---- epilogue warps: TMEM -> C ----
+        // A thread of tcgen05.ld holds ONE row (TMEM lane) and consecutive window lengths; stored as they
+        // come, a warp's store instruction touches 32 different 128-byte lines (measured: ~15 000 cycles per
+        // unit, which bounds every unit with fewer than ~10 k stages -- most of a 30-d map).  So each warp
+        // passes blocks of 32 rows x 64 window lengths (FP16: 128 B per row) through a padded shared-memory
+        // tile (pitch 144 B: both directions conflict-free) and writes 4 full lines per instruction; the TMEM
+        // load of the next block is in flight meanwhile.
         const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
-        const uint32_t L = q * 32 + lane;
-        const uint32_t grp = L >> 3, gg = grp >> 1, cp = grp & 1u;  // 8-row group of the MMA: [gg][c']
-        const uint32_t row = (uint32_t)Cfg::row_of((int)gg, (int)(L & 7u));
+        unsigned char *stg = reinterpret_cast<unsigned char *>(&stage_s[q][0]);
+        unsigned char *stg_own = stg + lane * (TCX_EPI_PITCH * 4);                    // this lane's row (TMEM lane 32 q + lane)
+        const uint32_t sx = lane & 7u, srr = lane >> 3;                               // store role: 16-byte piece sx of row 4 k + srr
+        const unsigned char *stg_rd = stg + srr * (TCX_EPI_PITCH * 4) + 16 * sx;      // + 4 k * pitch
+        // row 4 k + srr of the quadrant is TMEM lane Lr = 32 q + 4 k + srr: group [gg][c'] = Lr >> 3, row i' = Lr & 7
         uint32_t unit = 0;
-        for (uint32_t j = blockIdx.x; j < n_tiles; j += gridDim.x) {
-            const TcxTile tl = tcx_tile<F16>(j, cnt, n_mb, n_nt, w, i00, meta, t_base, Kn);
-            const uint32_t m = tl.mb * Cfg::kSpan + row;
+        long long te_wait = 0;
+        (void)te_wait;
+#ifdef TCX_TIMING
+        const long long te_begin = clock64();
+#endif
+#define TCX_LD32(V, OFF, TADDR)                                                                                              \
+    asm volatile(                                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                            \
+        : "=r"(V[OFF + 0]), "=r"(V[OFF + 1]), "=r"(V[OFF + 2]), "=r"(V[OFF + 3]), "=r"(V[OFF + 4]), "=r"(V[OFF + 5]),        \
+          "=r"(V[OFF + 6]), "=r"(V[OFF + 7]), "=r"(V[OFF + 8]), "=r"(V[OFF + 9]), "=r"(V[OFF + 10]), "=r"(V[OFF + 11]),      \
+          "=r"(V[OFF + 12]), "=r"(V[OFF + 13]), "=r"(V[OFF + 14]), "=r"(V[OFF + 15]), "=r"(V[OFF + 16]), "=r"(V[OFF + 17]),  \
+          "=r"(V[OFF + 18]), "=r"(V[OFF + 19]), "=r"(V[OFF + 20]), "=r"(V[OFF + 21]), "=r"(V[OFF + 22]), "=r"(V[OFF + 23]),  \
+          "=r"(V[OFF + 24]), "=r"(V[OFF + 25]), "=r"(V[OFF + 26]), "=r"(V[OFF + 27]), "=r"(V[OFF + 28]), "=r"(V[OFF + 29]),  \
+          "=r"(V[OFF + 30]), "=r"(V[OFF + 31])                                                                               \
+        : "r"(TADDR))
+        // one unit: `c16` = its group is stored as FP16 (blocks of 64 window lengths) or FP32 (blocks of 32):
+        // either way a block is 128 bytes per row
+        auto drain_unit = [&](auto c16, const TcxTile &tl, int hh, uint32_t buf) {
+            constexpr bool C16 = decltype(c16)::value;
+            constexpr int BW = C16 ? 64 : 32, NB = 256 / BW, ES = C16 ? 2 : 4;
+            const bool has = tl.nchunks > 0;
+            const uint32_t tbase = tmem + ((q * 32u) << 16) + buf * 256u;  // + BW b: block b = (pair b / (NB/2), columns BW (b % (NB/2)) ..)
+            const int nch = hh == 0 ? 3 : 4;
+            unsigned char *dstb = (hh == 0 ? CA : CF) +
+                                  ((((size_t)tl.tz * nch * w.N_t0 + (size_t)tl.mb * Cfg::kSpan) * cpitch + (size_t)tl.nt * TCX_TAUS) * ES + 16 * sx);
+            // TMEM is read 32 columns at a time, the load of the next 32 in flight while these are converted
+            // and staged; a block (128 bytes per row) is 1 (FP32) or 2 (FP16) such loads
+            constexpr int LPB = BW / 32;
+            uint32_t va[32], vb[32];
+            if (has) TCX_LD32(va, 0, tbase);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t(&cur)[32] = (j & 1) ? vb : va;
+                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                if (has) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (j + 1 < 8) TCX_LD32(nxt, 0, tbase + (uint32_t)(32 * (j + 1)));
+                }
+                const int b = j / LPB, part = j % LPB;
+                if (part == 0) __syncwarp();  // the previous block has been read out of the tile
+                if (C16) {
+                    uint32_t hv[16];
+#pragma unroll
+                    for (int x = 0; x < 16; x++) {
+                        const __half2 h2 = has ? __floats2half2_rn(__uint_as_float(cur[2 * x]) * cs, __uint_as_float(cur[2 * x + 1]) * cs)
+                                               : __floats2half2_rn(0.0f, 0.0f);
+                        hv[x] = *reinterpret_cast<const uint32_t *>(&h2);
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+                        *reinterpret_cast<uint4 *>(stg_own + 64 * part + 16 * x) = make_uint4(hv[4 * x], hv[4 * x + 1], hv[4 * x + 2], hv[4 * x + 3]);
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 8; x++)
+                        *reinterpret_cast<uint4 *>(stg_own + 16 * x) =
+                            has ? make_uint4(__float_as_uint(__uint_as_float(cur[4 * x]) * cs), __float_as_uint(__uint_as_float(cur[4 * x + 1]) * cs),
+                                             __float_as_uint(__uint_as_float(cur[4 * x + 2]) * cs), __float_as_uint(__uint_as_float(cur[4 * x + 3]) * cs))
+                                : make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (part != LPB - 1) continue;
+                __syncwarp();
+                const int pl = b / (NB / 2), cbo = (b % (NB / 2)) * 128;  // pair of the unit, byte offset of the block in the row
+                // slot c' of (unit hh, pair pl) -> channel index WITHIN the group (-1: the unused slot)
+                const int ci0 = 2 * pl, ci1 = hh == 0 ? (pl == 0 ? 1 : -1) : 2 * pl + 1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t Lr = 32u * q + 4u * k + srr, grp = Lr >> 3;
+                    const int ci = (grp & 1u) ? ci1 : ci0;
+                    const uint32_t row = (uint32_t)Cfg::row_of((int)(grp >> 1), (int)(Lr & 7u));
+                    const uint4 val = *reinterpret_cast<const uint4 *>(stg_rd + 4 * k * (TCX_EPI_PITCH * 4));
+                    if (ci >= 0 && tl.mb * Cfg::kSpan + row < w.N_t0)
+                        *reinterpret_cast<uint4 *>(dstb + ((size_t)ci * w.N_t0 + row) * cpitch * ES + cbo) = val;
+                }
+            }
+        };
+        TCX_TILE_LOOP_BEGIN
             for (int hh = 0; hh < 2; hh++, unit++) {
                 const uint32_t buf = unit & 1u;
-                const float undo = F16 ? scale[4 * tl.tz + 2 + hh] : 1.0f;
-                mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
-                tcx_fence_after();
-#pragma unroll 1
-                for (int pl = 0; pl < 2; pl++) {
-                    const int ch = tcx_channel(2 * hh + pl, (int)cp);
-                    float *dst = C + (((size_t)tl.tz * TCW_NCH + (ch < 0 ? 0 : ch)) * w.N_t0 + m) * cpitch + (size_t)tl.nt * TCX_TAUS;
-                    const bool store = ch >= 0 && m < w.N_t0;
-#pragma unroll 1
-                    for (int cb = 0; cb < 4; cb++) {
-                        uint32_t v[32];
-                        if (tl.nchunks > 0) {
-                            const uint32_t taddr = tmem + ((q * 32u) << 16) + buf * 256u + (uint32_t)(pl * 128 + cb * 32);
-                            asm volatile(
-                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                : "r"(taddr));
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                            if (F16) {
-#pragma unroll
-                                for (int x = 0; x < 32; x++) v[x] = __float_as_uint(__uint_as_float(v[x]) * undo);
-                            }
-                        } else {
-#pragma unroll
-                            for (int x = 0; x < 32; x++) v[x] = 0u;
-                        }
-                        if (store) {
-                            uint4 *d4 = reinterpret_cast<uint4 *>(dst + cb * 32);
-#pragma unroll
-                            for (int x = 0; x < 8; x++) d4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
-                        }
-                    }
+                {
+                    TCX_T0();
+                    mbar_wait(&tmem_full[buf], (unit >> 1) & 1u);
+                    TCX_T1(te_wait);
                 }
+                tcx_fence_after();
+                if (hh == 0) drain_unit(std::integral_constant<bool, TcxC::kA16>{}, tl, 0, buf);
+                else drain_unit(std::integral_constant<bool, TcxC::kF16>{}, tl, 1, buf);
                 tcx_fence_before();
                 mbar_arrive_plain(&tmem_empty[buf]);
             }
         }
+#undef TCX_LD32
+#ifdef TCX_TIMING
+        if (tid == 64) {
+            atomicAdd(&tcx_timing[7], (unsigned long long)(clock64() - te_begin));
+            atomicAdd(&tcx_timing[8], (unsigned long long)te_wait);
+            atomicAdd(&tcx_timing[9], 1ull);
+        }
+#endif
     }
     tcx_fence_before();
     __syncthreads();
@@ -437,19 +602,25 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
 //     stride-3 reads are bank-conflict-free) and fetches 16 new atoms every 16 rows; the entering atom comes
 //     from a second ring of 32 atoms (a broadcast read).  FP64 copies of the atoms
 //     (tcw_exp_atoms_f64_kernel) feed DFMAs directly; the only conversions left are the 7 sums going to FP32.
-// Correction sums (HAS_C) are prefetched TCX_WALK_DEPTH rows ahead into a third ring (a row of a warp =
-// 7 channels x 128 B = 56 16-byte pieces, two per lane).  Everything arrives by cp.async.cg -- one commit
+// Correction sums (HAS_C; FP32 for a2, b2, ab and FP16 for Fa, Fb: TcxC) are prefetched TCX_WALK_DEPTH rows ahead
+// into a third ring (a row of a warp = 3 x 128 B + 4 x 64 B = 40 16-byte pieces, one or two per lane).  Everything arrives by cp.async.cg -- one commit
 // group per row, so a fixed wait_group count covers all rings -- bypassing L1.
+#ifndef TCX_WALK_DEPTH
 #define TCX_WALK_DEPTH 4
+#endif
 #define TCX_WALK_XRING 128  // atoms in the leaving-atom ring (8 blocks of 16)
 template <int NSEG>
 struct WalkCfg {
-    static constexpr int kCG = NSEG >= 4 ? 1 : 4 / NSEG;  // column groups (of 32 window lengths) per CTA
+#ifndef TCX_WALK_CGW
+#define TCX_WALK_CGW 2  // warps per CTA when the rows are not segmented
+#endif
+    static constexpr int kCG = NSEG >= TCX_WALK_CGW ? 1 : TCX_WALK_CGW / NSEG;  // column groups (of 32 window lengths) per CTA
     static constexpr int kWarps = NSEG * kCG;
     static constexpr int kThreads = 32 * kWarps;
     static constexpr int kWarpXBytes = TCW_NCH * (TCX_WALK_XRING + 32) * 8;  // leaving-atom ring + entering-atom ring
     static constexpr int kXRingBytes = kWarps * kWarpXBytes;                 // (also holds E between the passes)
-    static constexpr int kCRingBytes = kWarps * TCX_WALK_DEPTH * TCW_NCH * 32 * 4;
+    static constexpr int kDepth = kWarps > 4 ? 4 : TCX_WALK_DEPTH;  // rows of correction sums in flight per warp
+    static constexpr int kCRingBytes = kWarps * kDepth * TcxC::kRowBytes;
     static constexpr int smem(bool has_c) { return kXRingBytes + (has_c ? kCRingBytes : 0); }
 };
 
@@ -481,8 +652,8 @@ template <bool HAS_C, int NSEG>
 __global__ void __launch_bounds__(WalkCfg<NSEG>::kThreads)
 tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
                     const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, MapWindow w,
-                    uint32_t i00, int32_t delta, uint32_t TAtom, const float *__restrict__ C, uint32_t cpitch,
-                    float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+                    uint32_t i00, int32_t delta, uint32_t TAtom, const unsigned char *__restrict__ CA,
+                    const unsigned char *__restrict__ CF, uint32_t cpitch, const float *__restrict__ cscale, float cunshift, float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     using Cfg = WalkCfg<NSEG>;
     extern __shared__ __align__(16) unsigned char walk_smem[];
     __shared__ unsigned long long red[Cfg::kWarps];
@@ -496,8 +667,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         walk_smem + (size_t)wi * Cfg::kWarpXBytes + TCW_NCH * TCX_WALK_XRING * 8);  // [channel][atom & 31]: atoms entering
     // end values of pass 1, [channel][lane] at the start of each warp's (then idle) atom ring
     auto E = [&](int wj) { return reinterpret_cast<double(*)[32]>(walk_smem + (size_t)wj * Cfg::kWarpXBytes); };
-    float(*ringC)[TCW_NCH][32] = reinterpret_cast<float(*)[TCW_NCH][32]>(
-        walk_smem + Cfg::kXRingBytes + (size_t)wi * TCX_WALK_DEPTH * TCW_NCH * 32 * 4);  // [slot][channel][lane]
+    unsigned char *ringC = walk_smem + Cfg::kXRingBytes + (size_t)wi * Cfg::kDepth * TcxC::kRowBytes;  // [slot][channel][lane]
+    // the correction sums come in the tensor-core pass's scaled units (tcw_exptc_scale_kernel, times 2^-shift)
+    const float cf2 = HAS_C ? cscale[4 * tz + 2] * cunshift : 0.0f, cf1 = HAS_C ? cscale[4 * tz + 3] * cunshift : 0.0f;
     const uint32_t n = (blockIdx.x * Cfg::kCG + cg) * 32 + lane;
     const bool active = n < w.N_tau;
     const double *Xs = X + (size_t)t * TCW_NCH * xpad;
@@ -607,12 +779,19 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rho2 : rho, U[c], fma(-(c < 3 ? rhoL2 : rhoL), x1[c], x0[c]));
     };
-    auto cell = [&](int m, const float *cc) {
+    // cc: the slot of the correction-sum ring holding row m
+    auto cell = [&](int m, const unsigned char *cc) {
         float S[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) {
             const float u = (float)U[c];
-            S[c] = HAS_C ? fmaf(u, c < 3 ? w02f : w0f, cc[c * 32]) : u * (c < 3 ? w02f : w0f);
+            float corr = 0.0f;
+            if (HAS_C) {
+                const unsigned char *pc = cc + (c < 3 ? c * TcxC::kRowA : 3 * TcxC::kRowA + (c - 3) * TcxC::kRowF);
+                if (c < 3 ? TcxC::kA16 : TcxC::kF16) corr = __half2float(reinterpret_cast<const __half *>(pc)[lane]);
+                else corr = reinterpret_cast<const float *>(pc)[lane];
+            }
+            S[c] = HAS_C ? fmaf(corr, c < 3 ? cf2 : cf1, u * (c < 3 ? w02f : w0f)) : u * (c < 3 ? w02f : w0f);
         }
         float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
         if (empty_win) F = 2.0f;  // no atom in the window: all sums zero in the reference -> its fallback value
@@ -631,7 +810,7 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             fill_ring(hi - 1);
 #pragma unroll 1
             for (int m = hi - 1; m >= lo; m--) {
-                cp_async_wait<TCX_WALK_DEPTH - 1>();
+                cp_async_wait<Cfg::kDepth - 1>();
                 __syncwarp();
                 step(m);
                 __syncwarp();
@@ -661,45 +840,58 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     }
 #pragma unroll 1
     for (; m >= lo && m >= (int)w.N_t0; m--) {  // rows beyond the map: no output
-        cp_async_wait<TCX_WALK_DEPTH - 1>();
+        cp_async_wait<Cfg::kDepth - 1>();
         __syncwarp();
         step(m);
         __syncwarp();
         row_end(m);
     }
     if (HAS_C) {
-        const size_t cstride = (size_t)w.N_t0 * cpitch;
-        // piece q = lane, lane + 32 of a row: channel q / 8, columns 4 (q % 8) .. + 3 of the warp's 32
-        const float *Cp0 = C + (size_t)tz * TCW_NCH * w.N_t0 * cpitch + (size_t)(n - lane) + (size_t)(lane >> 3) * cstride + 4 * (lane & 7);
-        const float *Cp1 = Cp0 + 4 * cstride;
+        // a row of the warp: 16-byte pieces, group A first; piece q is fetched by lane q % 32
+        const unsigned char *src[2];
+        uint32_t dsto[2];
+        size_t rowb[2];
+#pragma unroll
+        for (int hq = 0; hq < 2; hq++) {
+            const int qq = lane + 32 * hq;
+            const bool isA = qq < TcxC::kPiecesA;
+            const int qf = qq - TcxC::kPiecesA;
+            const int ppc = (isA ? TcxC::kRowA : TcxC::kRowF) / 16;  // pieces per channel
+            const int ci = isA ? qq / ppc : qf / ppc, pi = isA ? qq % ppc : qf % ppc;
+            const int es = isA ? TcxC::kElemA : TcxC::kElemF, nch = isA ? 3 : 4;
+            src[hq] = (isA ? CA : CF) + (((size_t)tz * nch + ci) * w.N_t0 * cpitch + (size_t)(n - lane)) * es + 16 * pi;
+            rowb[hq] = (size_t)cpitch * es;
+            dsto[hq] = (uint32_t)(isA ? ci * TcxC::kRowA : 3 * TcxC::kRowA + ci * TcxC::kRowF) + 16u * pi;
+        }
         const int m_top = m;
         auto fetch_c = [&](int row, int slot) {
             if (row >= lo) {
-                cp_async16(&ringC[slot][lane >> 3][4 * (lane & 7)], Cp0 + (size_t)row * cpitch);
-                if (lane < 24) cp_async16(&ringC[slot][4 + (lane >> 3)][4 * (lane & 7)], Cp1 + (size_t)row * cpitch);
+                cp_async16(ringC + slot * TcxC::kRowBytes + dsto[0], src[0] + (size_t)row * rowb[0]);
+                if (lane + 32 < TcxC::kPiecesA + TcxC::kPiecesF)
+                    cp_async16(ringC + slot * TcxC::kRowBytes + dsto[1], src[1] + (size_t)row * rowb[1]);
             }
         };
 #pragma unroll 1
-        for (int r = 0; r < TCX_WALK_DEPTH; r++) {
+        for (int r = 0; r < Cfg::kDepth; r++) {
             fetch_c(m_top - r, r);
             cp_async_commit();
         }
         int slot = 0;
 #pragma unroll 1
         for (; m >= lo; m--) {
-            cp_async_wait<TCX_WALK_DEPTH - 1>();  // the oldest row in flight has landed (this lane's pieces)
+            cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
             __syncwarp();                         // ... and every other lane's
             step(m);
-            cell(m, &ringC[slot][0][lane]);
+            cell(m, ringC + slot * TcxC::kRowBytes);
             __syncwarp();  // all lanes have read the slots before they are refilled
-            fetch_c(m - TCX_WALK_DEPTH, slot);
+            fetch_c(m - Cfg::kDepth, slot);
             row_end(m);
-            slot = slot + 1 == TCX_WALK_DEPTH ? 0 : slot + 1;
+            slot = slot + 1 == Cfg::kDepth ? 0 : slot + 1;
         }
     } else {
 #pragma unroll 1
         for (; m >= lo; m--) {
-            cp_async_wait<TCX_WALK_DEPTH - 1>();
+            cp_async_wait<Cfg::kDepth - 1>();
             __syncwarp();
             step(m);
             cell(m, nullptr);

@@ -17,5 +17,5 @@ h.upload(b)
 for _ in range(2):
     h.map_resident(w, fl)
 h.synchronize()
-print(h.last_stage_ms())
+print(h.last_stage_ms(), h.last_exp_stage_ms())
 h.close()

@@ -368,7 +368,7 @@ def exp_rec_roofline(spec, T, xs, hbm_peak, hbm_src):
     burst, sustained, src = measured_tensor_peaks()
     tc_flop = 14 * spec["visits"]  # 7 channel MACs per atom visit; the kernel issues 8/7 of that plus tile padding
     achieved = T * tc_flop / (xs["tensor"] * 1e-3) / 1e12
-    walk_bytes = (28 + 4) * spec["cells"]  # correction sums in (7 x FP32), F_mn out (the lnBtSG pass re-reads it)
+    walk_bytes = (20 + 4) * spec["cells"]  # correction sums in (3 x FP32 + 4 x FP16), F_mn out (the lnBtSG pass re-reads it)
     walk = T * walk_bytes / (xs["walk"] * 1e-3) / 1e9
     return {
         "bound": "tensor", "kernel": "tcw_exptc_map_kernel<FP16>", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",

@@ -65,7 +65,6 @@
 #define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)
 #define TCX_THREADS 192
 #define TCX_SMEM (TCX_STAGES * TCX_STAGE_BYTES + 128)
-#define TCX_EPI_PITCH 36  // floats per row of an epilogue warp's 32 x 32 transposition tile (144 B)
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
@@ -232,20 +231,28 @@ __device__ __forceinline__ uint64_t tcx_desc(uint32_t saddr, uint32_t lbo, uint3
 __host__ __device__ constexpr uint32_t tcx_idesc(uint32_t M, uint32_t N, bool f16) {
     return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-template <bool F16>
+// COLL: collector usage of the A operand: 0 none (discard), 1 fill (read A, keep it in the collector buffer),
+// 2 lastuse (take A from the collector buffer: the same descriptor as the preceding `fill`)
+#ifndef TCX_COLLECTOR
+#define TCX_COLLECTOR 0
+#endif
+template <bool F16, int COLL>
 __device__ __forceinline__ void tcx_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    if (F16)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-            : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-            : "memory");
+#define TCX_MMA_ASM(KIND, CU)                                                                          \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                     \
+                 "tcgen05.mma.cta_group::1.kind::" KIND CU " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)                                          \
+                 : "memory")
+    if (F16) {
+        if (COLL == 1) TCX_MMA_ASM("f16", ".collector::a::fill");
+        else if (COLL == 2) TCX_MMA_ASM("f16", ".collector::a::lastuse");
+        else TCX_MMA_ASM("f16", "");
+    } else {
+        if (COLL == 1) TCX_MMA_ASM("tf32", ".collector::a::fill");
+        else if (COLL == 2) TCX_MMA_ASM("tf32", ".collector::a::lastuse");
+        else TCX_MMA_ASM("tf32", "");
+    }
+#undef TCX_MMA_ASM
 }
 __device__ __forceinline__ void tcx_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -327,7 +334,6 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
     extern __shared__ __align__(128) unsigned char tcx_smem_raw[];
     __shared__ __align__(8) uint64_t full[TCX_STAGES], empty[TCX_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float stage_s[4][32 * TCX_EPI_PITCH];  // the epilogue warps' transposition tiles
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tcx_smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned char *G = reinterpret_cast<const unsigned char *>(Gv);
@@ -399,8 +405,12 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
             constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS, F16);
-            const uint64_t da = tcx_desc(0, 16, 256);      // A: K halves 16 B apart, 8-row groups = chunks 256 B apart
-            const uint64_t db = tcx_desc(0, 2048, 128);    // B: [kq][ng][8][16 B]: K steps 2 KB apart, 8-column groups 128 B
+            // The MMA computes the TRANSPOSED tile: its A operand (M = 128) are the window lengths -- the weights
+            // V[k, n], shared by the two channel pairs of a unit -- its B operand (N = 128) the Hankel atoms
+            // (2 channels x 64 rows).  TMEM lane = window length: the epilogue's stores are coalesced as they
+            // come (32 lanes = 32 consecutive window lengths of one row).
+            const uint64_t dx = tcx_desc(0, 16, 256);      // atoms: K halves 16 B apart, 8-row groups = chunks 256 B apart
+            const uint64_t dv = tcx_desc(0, 2048, 128);    // weights: [kq][ng][8][16 B]: K steps 2 KB apart, 8-column groups 128 B
             uint32_t it = 0, unit = 0;
             long long tm_dec = 0, tm_tmem = 0, tm_full = 0, tm_n = 0;
             (void)tm_dec, (void)tm_tmem, (void)tm_full, (void)tm_n;
@@ -435,12 +445,12 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                         const uint32_t a0 = smem_u32(smem + (size_t)s * TCX_STAGE_BYTES), b0 = a0 + TCX_A_BYTES;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {  // 32 bytes of K per MMA: 8 TF32 / 16 FP16 values
-                            const uint64_t bd = db | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
-#pragma unroll
-                            for (int pl = 0; pl < 2; pl++) {
-                                const uint64_t ad = da | (uint64_t)(((a0 + pl * 4096 + q * 32) >> 4) & 0x3FFF);
-                                tcx_mma<F16>(d0 + pl * 128, ad, bd, idesc, (c > 0 || q > 0) ? 1u : 0u);
-                            }
+                            const uint64_t vd = dv | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
+                            const uint64_t xd0 = dx | (uint64_t)(((a0 + q * 32) >> 4) & 0x3FFF);
+                            const uint64_t xd1 = dx | (uint64_t)(((a0 + 4096 + q * 32) >> 4) & 0x3FFF);
+                            const uint32_t acc = (c > 0 || q > 0) ? 1u : 0u;
+                            tcx_mma<F16, TCX_COLLECTOR ? 1 : 0>(d0, vd, xd0, idesc, acc);
+                            tcx_mma<F16, TCX_COLLECTOR ? 2 : 0>(d0 + 128, vd, xd1, idesc, acc);
                         }
                         tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
                     }
@@ -460,97 +470,80 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
 #endif
         }
     } else {  // ---- epilogue warps: TMEM -> C ----
-        // A thread of tcgen05.ld holds ONE row (TMEM lane) and consecutive window lengths; stored as they
-        // come, a warp's store instruction touches 32 different 128-byte lines (measured: ~15 000 cycles per
-        // unit, which bounds every unit with fewer than ~10 k stages -- most of a 30-d map).  So each warp
-        // passes blocks of 32 rows x 64 window lengths (FP16: 128 B per row) through a padded shared-memory
-        // tile (pitch 144 B: both directions conflict-free) and writes 4 full lines per instruction; the TMEM
-        // load of the next block is in flight meanwhile.
+        // TMEM lane = window length n, column = (channel slot c', row): a thread holds ONE window length and, per
+        // tcgen05.ld, 32 (slot, row) values; the 32 lanes of a warp store 32 consecutive window lengths of one
+        // row -- a full 128-byte line (FP32) or 64 bytes (FP16) per instruction, no transposition needed.  The
+        // load of the next 32 columns is in flight while these are stored.
         const uint32_t q = warp & 3u;  // TMEM lane quadrant this warp may read
-        unsigned char *stg = reinterpret_cast<unsigned char *>(&stage_s[q][0]);
-        unsigned char *stg_own = stg + lane * (TCX_EPI_PITCH * 4);                    // this lane's row (TMEM lane 32 q + lane)
-        const uint32_t sx = lane & 7u, srr = lane >> 3;                               // store role: 16-byte piece sx of row 4 k + srr
-        const unsigned char *stg_rd = stg + srr * (TCX_EPI_PITCH * 4) + 16 * sx;      // + 4 k * pitch
-        // row 4 k + srr of the quadrant is TMEM lane Lr = 32 q + 4 k + srr: group [gg][c'] = Lr >> 3, row i' = Lr & 7
         uint32_t unit = 0;
         long long te_wait = 0;
         (void)te_wait;
 #ifdef TCX_TIMING
         const long long te_begin = clock64();
 #endif
-#define TCX_LD32(V, OFF, TADDR)                                                                                              \
+#define TCX_LD32(V, TADDR)                                                                                                   \
     asm volatile(                                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                            \
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                            \
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                            \
-        : "=r"(V[OFF + 0]), "=r"(V[OFF + 1]), "=r"(V[OFF + 2]), "=r"(V[OFF + 3]), "=r"(V[OFF + 4]), "=r"(V[OFF + 5]),        \
-          "=r"(V[OFF + 6]), "=r"(V[OFF + 7]), "=r"(V[OFF + 8]), "=r"(V[OFF + 9]), "=r"(V[OFF + 10]), "=r"(V[OFF + 11]),      \
-          "=r"(V[OFF + 12]), "=r"(V[OFF + 13]), "=r"(V[OFF + 14]), "=r"(V[OFF + 15]), "=r"(V[OFF + 16]), "=r"(V[OFF + 17]),  \
-          "=r"(V[OFF + 18]), "=r"(V[OFF + 19]), "=r"(V[OFF + 20]), "=r"(V[OFF + 21]), "=r"(V[OFF + 22]), "=r"(V[OFF + 23]),  \
-          "=r"(V[OFF + 24]), "=r"(V[OFF + 25]), "=r"(V[OFF + 26]), "=r"(V[OFF + 27]), "=r"(V[OFF + 28]), "=r"(V[OFF + 29]),  \
-          "=r"(V[OFF + 30]), "=r"(V[OFF + 31])                                                                               \
+        : "=r"(V[0]), "=r"(V[1]), "=r"(V[2]), "=r"(V[3]), "=r"(V[4]), "=r"(V[5]), "=r"(V[6]), "=r"(V[7]), "=r"(V[8]),        \
+          "=r"(V[9]), "=r"(V[10]), "=r"(V[11]), "=r"(V[12]), "=r"(V[13]), "=r"(V[14]), "=r"(V[15]), "=r"(V[16]),             \
+          "=r"(V[17]), "=r"(V[18]), "=r"(V[19]), "=r"(V[20]), "=r"(V[21]), "=r"(V[22]), "=r"(V[23]), "=r"(V[24]),            \
+          "=r"(V[25]), "=r"(V[26]), "=r"(V[27]), "=r"(V[28]), "=r"(V[29]), "=r"(V[30]), "=r"(V[31])                          \
         : "r"(TADDR))
-        // one unit: `c16` = its group is stored as FP16 (blocks of 64 window lengths) or FP32 (blocks of 32):
-        // either way a block is 128 bytes per row
-        auto drain_unit = [&](auto c16, const TcxTile &tl, int hh, uint32_t buf) {
-            constexpr bool C16 = decltype(c16)::value;
-            constexpr int BW = C16 ? 64 : 32, NB = 256 / BW, ES = C16 ? 2 : 4;
+        // one unit; `c16`: its group is stored as FP16, `edge`: the tile reaches beyond the last map row
+        auto drain_unit = [&](auto c16, auto edge, const TcxTile &tl, int hh, uint32_t buf) __attribute__((always_inline)) {
+            constexpr bool C16 = decltype(c16)::value, EDGE = decltype(edge)::value;
+            constexpr int ES = C16 ? 2 : 4;
             const bool has = tl.nchunks > 0;
-            const uint32_t tbase = tmem + ((q * 32u) << 16) + buf * 256u;  // + BW b: block b = (pair b / (NB/2), columns BW (b % (NB/2)) ..)
+            const uint32_t tbase = tmem + ((q * 32u) << 16) + buf * 256u;  // + column: 128 pl + 8 (2 gg + c') + i'
             const int nch = hh == 0 ? 3 : 4;
-            unsigned char *dstb = (hh == 0 ? CA : CF) +
-                                  ((((size_t)tl.tz * nch * w.N_t0 + (size_t)tl.mb * Cfg::kSpan) * cpitch + (size_t)tl.nt * TCX_TAUS) * ES + 16 * sx);
-            // TMEM is read 32 columns at a time, the load of the next 32 in flight while these are converted
-            // and staged; a block (128 bytes per row) is 1 (FP32) or 2 (FP16) such loads
-            constexpr int LPB = BW / 32;
+            const uint32_t m0 = tl.mb * Cfg::kSpan;
+            const size_t rowb = (size_t)cpitch * ES, chb = (size_t)w.N_t0 * rowb;
+            unsigned char *dstb = (hh == 0 ? CA : CF) + ((size_t)tl.tz * nch * w.N_t0 + m0) * rowb +
+                                  ((size_t)tl.nt * TCX_TAUS + 32u * q + lane) * ES;
+            const size_t rowstep = (size_t)Cfg::kRowStep * rowb;  // rows of a group are kRowStep apart
             uint32_t va[32], vb[32];
-            if (has) TCX_LD32(va, 0, tbase);
+            // columns 32 j ..: pair j / 4, groups 4 (j % 4) .. + 3 = [gg = 2 (j % 4) + h][c'], 8 rows each
+            auto store32 = [&](const uint32_t(&cur)[32], int j) __attribute__((always_inline)) {
+                const int pl = j >> 2;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
-                if (has) {
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (j + 1 < 8) TCX_LD32(nxt, 0, tbase + (uint32_t)(32 * (j + 1)));
-                }
-                const int b = j / LPB, part = j % LPB;
-                if (part == 0) __syncwarp();  // the previous block has been read out of the tile
-                if (C16) {
-                    uint32_t hv[16];
+                for (int h = 0; h < 2; h++) {
+                    const int gg = 2 * (j & 3) + h;
+                    const int r0 = gg % Cfg::kRowStep + Cfg::kKC * (gg / Cfg::kRowStep);  // row_of(gg, 0)
 #pragma unroll
-                    for (int x = 0; x < 16; x++) {
-                        const __half2 h2 = has ? __floats2half2_rn(__uint_as_float(cur[2 * x]) * cs, __uint_as_float(cur[2 * x + 1]) * cs)
-                                               : __floats2half2_rn(0.0f, 0.0f);
-                        hv[x] = *reinterpret_cast<const uint32_t *>(&h2);
+                    for (int cp = 0; cp < 2; cp++) {
+                        // slot c' of (unit hh, pair pl) -> channel index WITHIN the group (-1: the unused slot)
+                        const int ci = hh == 0 ? (pl == 0 ? cp : (cp == 0 ? 2 : -1)) : 2 * pl + cp;
+                        if (ci < 0) continue;
+                        unsigned char *d = dstb + (size_t)ci * chb + (size_t)r0 * rowb;
+#pragma unroll
+                        for (int ip = 0; ip < 8; ip++) {
+                            const float val = has ? __uint_as_float(cur[16 * h + 8 * cp + ip]) * cs : 0.0f;
+                            if (!EDGE || m0 + (uint32_t)(r0 + Cfg::kRowStep * ip) < w.N_t0) {
+                                if (C16) *reinterpret_cast<__half *>(d) = __float2half_rn(val);
+                                else *reinterpret_cast<float *>(d) = val;
+                            }
+                            d += rowstep;
+                            asm volatile("" : "+l"(d));  // one running pointer: keeps nvcc from materialising 64 row addresses
+                        }
                     }
-#pragma unroll
-                    for (int x = 0; x < 4; x++)
-                        *reinterpret_cast<uint4 *>(stg_own + 64 * part + 16 * x) = make_uint4(hv[4 * x], hv[4 * x + 1], hv[4 * x + 2], hv[4 * x + 3]);
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 8; x++)
-                        *reinterpret_cast<uint4 *>(stg_own + 16 * x) =
-                            has ? make_uint4(__float_as_uint(__uint_as_float(cur[4 * x]) * cs), __float_as_uint(__uint_as_float(cur[4 * x + 1]) * cs),
-                                             __float_as_uint(__uint_as_float(cur[4 * x + 2]) * cs), __float_as_uint(__uint_as_float(cur[4 * x + 3]) * cs))
-                                : make_uint4(0u, 0u, 0u, 0u);
                 }
-                if (part != LPB - 1) continue;
-                __syncwarp();
-                const int pl = b / (NB / 2), cbo = (b % (NB / 2)) * 128;  // pair of the unit, byte offset of the block in the row
-                // slot c' of (unit hh, pair pl) -> channel index WITHIN the group (-1: the unused slot)
-                const int ci0 = 2 * pl, ci1 = hh == 0 ? (pl == 0 ? 1 : -1) : 2 * pl + 1;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t Lr = 32u * q + 4u * k + srr, grp = Lr >> 3;
-                    const int ci = (grp & 1u) ? ci1 : ci0;
-                    const uint32_t row = (uint32_t)Cfg::row_of((int)(grp >> 1), (int)(Lr & 7u));
-                    const uint4 val = *reinterpret_cast<const uint4 *>(stg_rd + 4 * k * (TCX_EPI_PITCH * 4));
-                    if (ci >= 0 && tl.mb * Cfg::kSpan + row < w.N_t0)
-                        *reinterpret_cast<uint4 *>(dstb + ((size_t)ci * w.N_t0 + row) * cpitch * ES + cbo) = val;
-                }
+            };
+            // (a unit without MMAs -- no atom in any of its windows -- reads whatever TMEM holds and stores zeros)
+            TCX_LD32(va, tbase);
+#pragma unroll 1
+            for (int jj = 0; jj < 4; jj++) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                TCX_LD32(vb, tbase + (uint32_t)(32 * (2 * jj + 1)));
+                store32(va, 2 * jj);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (jj < 3) TCX_LD32(va, tbase + (uint32_t)(32 * (2 * jj + 2)));
+                store32(vb, 2 * jj + 1);
             }
         };
         TCX_TILE_LOOP_BEGIN
+            const bool edge = tl.mb * Cfg::kSpan + Cfg::kSpan > w.N_t0;
             for (int hh = 0; hh < 2; hh++, unit++) {
                 const uint32_t buf = unit & 1u;
                 {
@@ -559,8 +552,15 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                     TCX_T1(te_wait);
                 }
                 tcx_fence_after();
-                if (hh == 0) drain_unit(std::integral_constant<bool, TcxC::kA16>{}, tl, 0, buf);
-                else drain_unit(std::integral_constant<bool, TcxC::kF16>{}, tl, 1, buf);
+                using A16 = std::integral_constant<bool, TcxC::kA16>;
+                using F16c = std::integral_constant<bool, TcxC::kF16>;
+                if (hh == 0) {
+                    if (edge) drain_unit(A16{}, std::true_type{}, tl, 0, buf);
+                    else drain_unit(A16{}, std::false_type{}, tl, 0, buf);
+                } else {
+                    if (edge) drain_unit(F16c{}, std::true_type{}, tl, 1, buf);
+                    else drain_unit(F16c{}, std::false_type{}, tl, 1, buf);
+                }
                 tcx_fence_before();
                 mbar_arrive_plain(&tmem_empty[buf]);
             }

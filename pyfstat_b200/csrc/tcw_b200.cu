@@ -953,7 +953,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         // a device short of memory gets smaller sub-batches instead of an error
         while ((rc = ensure(h, h->d_C, (size_t)S * tc_c_per_tpl)) == TCW_E_NOMEM && S > 1) S = (S + 1) / 2;
         if (rc) return rc;
-        if ((rc = ensure(h, h->d_G, (size_t)S * 4 * tc_U * 4096))) return rc;
+        if ((rc = ensure(h, h->d_G, (size_t)S * tc_U * TCX_G_BYTES_PER_U))) return rc;
         if ((rc = ensure(h, h->d_scale, (size_t)S * 4 * sizeof(float)))) return rc;
     }
     float *fmn_full = nullptr, *fmn_scratch = nullptr;
@@ -1216,7 +1216,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
             }
             if (exp_tc) {
-                const uint32_t g_elems = 4 * tc_U * 16 * (2 * tc_kc);
+                const uint32_t g_elems = tc_U * 56 * (2 * tc_kc);
                 const dim3 g_grid(std::min<uint32_t>((g_elems + 255u) / 256u, 1024u), cnt);
                 const uint32_t n_tiles = (uint32_t)cnt * tc_n_nt * tc_n_mb;
                 const uint32_t ctas = std::min<uint32_t>((uint32_t)h->prop.multiProcessorCount, n_tiles);

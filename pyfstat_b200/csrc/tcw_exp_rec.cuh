@@ -42,9 +42,10 @@
 // stage of k; a start shifted by the class needs its own 16-byte aligned copy), the chunks 256 bytes
 // apart (SBO); a prep kernel lays the atoms out in that chunked form -- per channel pair p and atom
 // block u: [group][c'][chunk] -- so a stage's A operand of a pair is one contiguous 4-KB bulk copy.
-// N = 128 window lengths.  A tile is
-// processed as two units of two channel pairs (a2,b2 | ab,- with the w^2 table, Fa | Fb with the w
-// table), each unit in one half of TMEM, 8 MMAs (M128 N128, 32 bytes of K) per 24-KB stage.  Warp
+// 128 window lengths per tile.  A tile is processed as two units -- the channels a2, b2, ab with the w^2
+// table (one MMA of 3 x 64 rows per 32 bytes of K), then Fa | Fb with the w table (two MMAs of 2 x 64
+// rows) -- each unit in one half of TMEM.  The MMAs compute the TRANSPOSED tile (M = window lengths,
+// N = channel x row), see the kernel.  Warp
 // roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C); persistent CTAs, one
 // per SM, static round-robin over tiles ordered by decreasing k range.
 #pragma once
@@ -117,12 +118,6 @@ struct TcxC {
     static constexpr int kPiecesA = 3 * kRowA / 16, kPiecesF = 4 * kRowF / 16;
 };
 
-// channel of (pair p, slot c'): a2,b2 | ab,- | Fa_re,Fa_im | Fb_re,Fb_im ; -1 = unused slot
-__device__ __forceinline__ int tcx_channel(int p, int cp) {
-    const int ch = 2 * p + cp - (p >= 2 ? 1 : 0);
-    return (p == 1 && cp == 1) ? -1 : ch;
-}
-
 // per template: power-of-two scales of the two channel groups (a2,b2,ab | Fa,Fb).  scale[tz][0..1] multiplies the
 // atoms into [2^13, 2^14); scale[tz][2..3] undoes it (and the weights' 2^12) on the accumulators.
 __global__ void tcw_exptc_scale_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
@@ -154,7 +149,13 @@ __global__ void tcw_exptc_scale_kernel(const float *__restrict__ X, uint32_t xpa
     }
 }
 
-// ---- atoms in chunked form: G[tz][p][u][gg 8][c' 2][kChunk],  value = X_ch[i00 + atom_of(gg) + kKC u + e] ----
+// ---- atoms in chunked form, per template:
+//        unit 0 (a2, b2, ab):  G0[u][gg 8][c 3][kChunk]          -- 6 KB per atom block u
+//        unit 1 (Fa | Fb):     G1[p 2][u][gg 8][c' 2][kChunk]    -- 4 KB per pair and atom block
+//      value = X_ch[i00 + atom_of(gg) + kKC u + e]
+#define TCX_G0_BYTES 6144
+#define TCX_G1_BYTES 4096
+#define TCX_G_BYTES_PER_U (TCX_G0_BYTES + 2 * TCX_G1_BYTES)
 template <bool F16>
 __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta *__restrict__ meta,
                                        int t_base, uint32_t i00, uint32_t U, const float *__restrict__ scale,
@@ -162,20 +163,33 @@ __global__ void tcw_exptc_atoms_kernel(const float *__restrict__ X, uint32_t xpa
     using Cfg = TcxCfg<F16>;
     const int tz = blockIdx.y, t = t_base + tz;
     const uint32_t numAtoms = meta[t].numAtoms;
-    const size_t per_tpl = (size_t)4 * U * 16 * Cfg::kChunk;
+    const size_t n0 = (size_t)U * 24 * Cfg::kChunk, per_tpl = (size_t)U * 56 * Cfg::kChunk;
     const float s2 = scale[4 * tz], s1 = scale[4 * tz + 1];
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per_tpl; idx += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t e = (uint32_t)(idx % Cfg::kChunk);
-        size_t rest = idx / Cfg::kChunk;
-        const uint32_t cp = (uint32_t)rest & 1u, gg = ((uint32_t)rest >> 1) & 7u;
-        rest >>= 4;
-        const uint32_t u = (uint32_t)(rest % U), p = (uint32_t)(rest / U);
-        const int ch = tcx_channel((int)p, (int)cp);
+        uint32_t e, gg, u, ch;
+        if (idx < n0) {
+            e = (uint32_t)(idx % Cfg::kChunk);
+            size_t rest = idx / Cfg::kChunk;
+            ch = (uint32_t)(rest % 3);
+            rest /= 3;
+            gg = (uint32_t)rest & 7u;
+            u = (uint32_t)(rest >> 3);
+        } else {
+            const size_t i1 = idx - n0;
+            e = (uint32_t)(i1 % Cfg::kChunk);
+            size_t rest = i1 / Cfg::kChunk;
+            const uint32_t cp = (uint32_t)rest & 1u;
+            gg = ((uint32_t)rest >> 1) & 7u;
+            rest >>= 4;
+            u = (uint32_t)(rest % U);
+            ch = 3u + 2u * (uint32_t)(rest / U) + cp;
+        }
         const uint64_t j = (uint64_t)i00 + (uint32_t)Cfg::atom_of((int)gg) + (uint64_t)Cfg::kKC * u + e;
         float v = 0.0f;
-        if (ch >= 0 && j < numAtoms) v = __ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j);
-        if (F16) reinterpret_cast<__half *>(Gv)[(size_t)tz * per_tpl + idx] = __float2half_rn(v * (ch < 3 ? s2 : s1));
-        else reinterpret_cast<float *>(Gv)[(size_t)tz * per_tpl + idx] = tf32_rna(v * (ch < 3 ? s2 : s1));
+        if (j < numAtoms) v = __ldg(X + ((size_t)t * TCW_NCH + ch) * xpad + j);
+        v *= ch < 3 ? s2 : s1;
+        if (F16) reinterpret_cast<__half *>(Gv)[(size_t)tz * per_tpl + idx] = __float2half_rn(v);
+        else reinterpret_cast<float *>(Gv)[(size_t)tz * per_tpl + idx] = tf32_rna(v);
     }
 }
 
@@ -231,28 +245,20 @@ __device__ __forceinline__ uint64_t tcx_desc(uint32_t saddr, uint32_t lbo, uint3
 __host__ __device__ constexpr uint32_t tcx_idesc(uint32_t M, uint32_t N, bool f16) {
     return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
-// COLL: collector usage of the A operand: 0 none (discard), 1 fill (read A, keep it in the collector buffer),
-// 2 lastuse (take A from the collector buffer: the same descriptor as the preceding `fill`)
-#ifndef TCX_COLLECTOR
-#define TCX_COLLECTOR 0
-#endif
-template <bool F16, int COLL>
+template <bool F16>
 __device__ __forceinline__ void tcx_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-#define TCX_MMA_ASM(KIND, CU)                                                                          \
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                     \
-                 "tcgen05.mma.cta_group::1.kind::" KIND CU " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
-                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)                                          \
-                 : "memory")
-    if (F16) {
-        if (COLL == 1) TCX_MMA_ASM("f16", ".collector::a::fill");
-        else if (COLL == 2) TCX_MMA_ASM("f16", ".collector::a::lastuse");
-        else TCX_MMA_ASM("f16", "");
-    } else {
-        if (COLL == 1) TCX_MMA_ASM("tf32", ".collector::a::fill");
-        else if (COLL == 2) TCX_MMA_ASM("tf32", ".collector::a::lastuse");
-        else TCX_MMA_ASM("tf32", "");
-    }
-#undef TCX_MMA_ASM
+    if (F16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+            : "memory");
 }
 __device__ __forceinline__ void tcx_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -372,8 +378,10 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
             const long long tp_begin = clock64();
 #endif
             TCX_TILE_LOOP_BEGIN
-                // chunks are 256 B; a stage's A operand of pair p: 16 chunks (8 groups x 2 c') = 4 KB at u = kUStep mb + c
-                const unsigned char *gA = G + ((size_t)tl.tz * 4 * U + (size_t)Cfg::kUStep * tl.mb) * 4096;  // + (p U + c) * 4096
+                // atoms of a stage (atom block u = kUStep mb + c): unit 0 one 6-KB copy, unit 1 a 4-KB copy per pair
+                const unsigned char *gT = G + (size_t)tl.tz * U * TCX_G_BYTES_PER_U;
+                const unsigned char *gA0 = gT + (size_t)Cfg::kUStep * tl.mb * TCX_G0_BYTES;                                // + c * 6 KB
+                const unsigned char *gA1 = gT + (size_t)U * TCX_G0_BYTES + (size_t)Cfg::kUStep * tl.mb * TCX_G1_BYTES;  // + (p U + c) * 4 KB
                 const unsigned char *gB = Vt + (size_t)tl.nt * n_chunks_tab * 32768;  // + c * 32 KB (+ 16 KB: w^2)
                 for (int hh = 0; hh < 2; hh++)
                     for (int c = 0; c < tl.nchunks; c++, it++) {
@@ -390,10 +398,15 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                             continue;
                         }
 #endif
-                        mbar_arrive_expect_tx(&full[s], TCX_STAGE_BYTES);
+                        if (hh == 0) {
+                            mbar_arrive_expect_tx(&full[s], TCX_G0_BYTES + TCX_B_BYTES);
+                            bulk_g2s(st, gA0 + (size_t)c * TCX_G0_BYTES, TCX_G0_BYTES, &full[s]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], 2 * TCX_G1_BYTES + TCX_B_BYTES);
 #pragma unroll
-                        for (int pl = 0; pl < 2; pl++)
-                            bulk_g2s(st + pl * 4096, gA + ((size_t)(2 * hh + pl) * U + c) * 4096, 4096, &full[s]);
+                            for (int pl = 0; pl < 2; pl++)
+                                bulk_g2s(st + pl * TCX_G1_BYTES, gA1 + ((size_t)pl * U + c) * TCX_G1_BYTES, TCX_G1_BYTES, &full[s]);
+                        }
                         bulk_g2s(st + TCX_A_BYTES, gB + (size_t)c * 32768 + (hh == 0 ? 16384 : 0), TCX_B_BYTES, &full[s]);
                     }
             }
@@ -404,11 +417,13 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
-            constexpr uint32_t idesc = tcx_idesc(128, TCX_TAUS, F16);
+            constexpr uint32_t idesc = tcx_idesc(128, 128, F16), idesc3 = tcx_idesc(128, 192, F16);
             // The MMA computes the TRANSPOSED tile: its A operand (M = 128) are the window lengths -- the weights
-            // V[k, n], shared by the two channel pairs of a unit -- its B operand (N = 128) the Hankel atoms
-            // (2 channels x 64 rows).  TMEM lane = window length: the epilogue's stores are coalesced as they
-            // come (32 lanes = 32 consecutive window lengths of one row).
+            // V[k, n] -- its B operand the Hankel atoms: N = 3 x 64 (a2, b2, ab: unit 0) or 2 x 64 rows (a pair of
+            // unit 1).  TMEM lane = window length: the epilogue's stores are coalesced as they come (32 lanes = 32
+            // consecutive window lengths of one row).  (The first versions stacked the channels in M, two per MMA:
+            // unit 0 then needs two M128 MMAs with a quarter of their lanes idle; as N = 192 it is one MMA of 3/4 the
+            // duration -- 1/8 fewer tensor-pipe cycles per tile, and this pass runs at the board's power cap.)
             const uint64_t dx = tcx_desc(0, 16, 256);      // atoms: K halves 16 B apart, 8-row groups = chunks 256 B apart
             const uint64_t dv = tcx_desc(0, 2048, 128);    // weights: [kq][ng][8][16 B]: K steps 2 KB apart, 8-column groups 128 B
             uint32_t it = 0, unit = 0;
@@ -423,7 +438,7 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
             TCX_TILE_LOOP_BEGIN
 #ifdef TCX_TIMING
                 tm_dec += (tl.nchunks >= 0 ? clock64() : 0) - _td;
-                tm_n += 16 * tl.nchunks;
+                tm_n += 12 * tl.nchunks;
 #endif
                 for (int hh = 0; hh < 2; hh++, unit++) {
                     const uint32_t buf = unit & 1u;
@@ -447,10 +462,14 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                         for (int q = 0; q < 4; q++) {  // 32 bytes of K per MMA: 8 TF32 / 16 FP16 values
                             const uint64_t vd = dv | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
                             const uint64_t xd0 = dx | (uint64_t)(((a0 + q * 32) >> 4) & 0x3FFF);
-                            const uint64_t xd1 = dx | (uint64_t)(((a0 + 4096 + q * 32) >> 4) & 0x3FFF);
                             const uint32_t acc = (c > 0 || q > 0) ? 1u : 0u;
-                            tcx_mma<F16, TCX_COLLECTOR ? 1 : 0>(d0, vd, xd0, idesc, acc);
-                            tcx_mma<F16, TCX_COLLECTOR ? 2 : 0>(d0 + 128, vd, xd1, idesc, acc);
+                            if (hh == 0) {
+                                tcx_mma<F16>(d0, vd, xd0, idesc3, acc);
+                            } else {
+                                const uint64_t xd1 = dx | (uint64_t)(((a0 + TCX_G1_BYTES + q * 32) >> 4) & 0x3FFF);
+                                tcx_mma<F16>(d0, vd, xd0, idesc, acc);
+                                tcx_mma<F16>(d0 + 128, vd, xd1, idesc, acc);
+                            }
                         }
                         tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
                     }
@@ -491,54 +510,51 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
           "=r"(V[17]), "=r"(V[18]), "=r"(V[19]), "=r"(V[20]), "=r"(V[21]), "=r"(V[22]), "=r"(V[23]), "=r"(V[24]),            \
           "=r"(V[25]), "=r"(V[26]), "=r"(V[27]), "=r"(V[28]), "=r"(V[29]), "=r"(V[30]), "=r"(V[31])                          \
         : "r"(TADDR))
-        // one unit; `c16`: its group is stored as FP16, `edge`: the tile reaches beyond the last map row
-        auto drain_unit = [&](auto c16, auto edge, const TcxTile &tl, int hh, uint32_t buf) __attribute__((always_inline)) {
-            constexpr bool C16 = decltype(c16)::value, EDGE = decltype(edge)::value;
-            constexpr int ES = C16 ? 2 : 4;
+        // one unit (`u0`: unit 0 = a2, b2, ab in 192 columns [gg][c 3][i']; else Fa | Fb in 2 x 128 columns
+        // [pair][gg][c' 2][i']); `c16`: its group is stored as FP16; `edge`: the tile reaches beyond the last map row
+        auto drain_unit = [&](auto u0, auto c16, auto edge, const TcxTile &tl, uint32_t buf) __attribute__((always_inline)) {
+            constexpr bool U0 = decltype(u0)::value, C16 = decltype(c16)::value, EDGE = decltype(edge)::value;
+            constexpr int ES = C16 ? 2 : 4, NPAIR = U0 ? 3 : 4;  // pairs of 32-column loads
             const bool has = tl.nchunks > 0;
-            const uint32_t tbase = tmem + ((q * 32u) << 16) + buf * 256u;  // + column: 128 pl + 8 (2 gg + c') + i'
-            const int nch = hh == 0 ? 3 : 4;
+            const uint32_t tbase = tmem + ((q * 32u) << 16) + buf * 256u;
+            const int nch = U0 ? 3 : 4;
             const uint32_t m0 = tl.mb * Cfg::kSpan;
             const size_t rowb = (size_t)cpitch * ES, chb = (size_t)w.N_t0 * rowb;
-            unsigned char *dstb = (hh == 0 ? CA : CF) + ((size_t)tl.tz * nch * w.N_t0 + m0) * rowb +
+            unsigned char *dstb = (U0 ? CA : CF) + ((size_t)tl.tz * nch * w.N_t0 + m0) * rowb +
                                   ((size_t)tl.nt * TCX_TAUS + 32u * q + lane) * ES;
             const size_t rowstep = (size_t)Cfg::kRowStep * rowb;  // rows of a group are kRowStep apart
             uint32_t va[32], vb[32];
-            // columns 32 j ..: pair j / 4, groups 4 (j % 4) .. + 3 = [gg = 2 (j % 4) + h][c'], 8 rows each
+            // columns 32 j ..: the four 8-row groups 4 j .. 4 j + 3
             auto store32 = [&](const uint32_t(&cur)[32], int j) __attribute__((always_inline)) {
-                const int pl = j >> 2;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int gg = 2 * (j & 3) + h;
+                for (int h = 0; h < 4; h++) {
+                    const int grp = 4 * j + h;
+                    // group -> (gg, channel index within the stored group)
+                    const int gg = U0 ? grp / 3 : (grp & 15) >> 1;
+                    const int ci = U0 ? grp % 3 : 2 * (grp >> 4) + (grp & 1);
                     const int r0 = gg % Cfg::kRowStep + Cfg::kKC * (gg / Cfg::kRowStep);  // row_of(gg, 0)
+                    unsigned char *d = dstb + (size_t)ci * chb + (size_t)r0 * rowb;
 #pragma unroll
-                    for (int cp = 0; cp < 2; cp++) {
-                        // slot c' of (unit hh, pair pl) -> channel index WITHIN the group (-1: the unused slot)
-                        const int ci = hh == 0 ? (pl == 0 ? cp : (cp == 0 ? 2 : -1)) : 2 * pl + cp;
-                        if (ci < 0) continue;
-                        unsigned char *d = dstb + (size_t)ci * chb + (size_t)r0 * rowb;
-#pragma unroll
-                        for (int ip = 0; ip < 8; ip++) {
-                            const float val = has ? __uint_as_float(cur[16 * h + 8 * cp + ip]) * cs : 0.0f;
-                            if (!EDGE || m0 + (uint32_t)(r0 + Cfg::kRowStep * ip) < w.N_t0) {
-                                if (C16) *reinterpret_cast<__half *>(d) = __float2half_rn(val);
-                                else *reinterpret_cast<float *>(d) = val;
-                            }
-                            d += rowstep;
-                            asm volatile("" : "+l"(d));  // one running pointer: keeps nvcc from materialising 64 row addresses
+                    for (int ip = 0; ip < 8; ip++) {
+                        const float val = has ? __uint_as_float(cur[8 * h + ip]) * cs : 0.0f;
+                        if (!EDGE || m0 + (uint32_t)(r0 + Cfg::kRowStep * ip) < w.N_t0) {
+                            if (C16) *reinterpret_cast<__half *>(d) = __float2half_rn(val);
+                            else *reinterpret_cast<float *>(d) = val;
                         }
+                        d += rowstep;
+                        asm volatile("" : "+l"(d));  // one running pointer: keeps nvcc from materialising 64 row addresses
                     }
                 }
             };
             // (a unit without MMAs -- no atom in any of its windows -- reads whatever TMEM holds and stores zeros)
             TCX_LD32(va, tbase);
 #pragma unroll 1
-            for (int jj = 0; jj < 4; jj++) {
+            for (int jj = 0; jj < NPAIR; jj++) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 TCX_LD32(vb, tbase + (uint32_t)(32 * (2 * jj + 1)));
                 store32(va, 2 * jj);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (jj < 3) TCX_LD32(va, tbase + (uint32_t)(32 * (2 * jj + 2)));
+                if (jj + 1 < NPAIR) TCX_LD32(va, tbase + (uint32_t)(32 * (2 * jj + 2)));
                 store32(vb, 2 * jj + 1);
             }
         };
@@ -555,11 +571,11 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                 using A16 = std::integral_constant<bool, TcxC::kA16>;
                 using F16c = std::integral_constant<bool, TcxC::kF16>;
                 if (hh == 0) {
-                    if (edge) drain_unit(A16{}, std::true_type{}, tl, 0, buf);
-                    else drain_unit(A16{}, std::false_type{}, tl, 0, buf);
+                    if (edge) drain_unit(std::true_type{}, A16{}, std::true_type{}, tl, buf);
+                    else drain_unit(std::true_type{}, A16{}, std::false_type{}, tl, buf);
                 } else {
-                    if (edge) drain_unit(F16c{}, std::true_type{}, tl, 1, buf);
-                    else drain_unit(F16c{}, std::false_type{}, tl, 1, buf);
+                    if (edge) drain_unit(std::false_type{}, F16c{}, std::true_type{}, tl, buf);
+                    else drain_unit(std::false_type{}, F16c{}, std::false_type{}, tl, buf);
                 }
                 tcx_fence_before();
                 mbar_arrive_plain(&tmem_empty[buf]);

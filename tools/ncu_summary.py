@@ -27,6 +27,9 @@ KEYS = [
     "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "gpc__cycles_elapsed.avg.per_second",
     "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
     "smsp__cycles_active.avg",
 ]

@@ -127,6 +127,22 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.rows = []
         self.proc = None
+        self.mark_at = 0
+
+    def wait_first(self, timeout=6.0):
+        """nvidia-smi needs up to a second to produce its first line (longer with 8 ranks starting one each):
+        wait for it BEFORE the timed region, so that the region itself is sampled."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+        return self
+
+    def mark(self):
+        """Samples taken before this point are not part of the record."""
+        self.mark_at = len(self.rows)
+
+    def count(self):
+        return len(self.rows) - self.mark_at
 
     def start(self):
         try:
@@ -154,7 +170,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.mark_at:]:
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -456,14 +472,22 @@ def run_gpu(args):
     peaks = h.microbench() if rank == 0 else None
 
     def measure():
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank).start().wait_first()
         barrier()
-        sampler.start()
+        sampler.mark()
         launches0 = h.launch_count
         ms, stages = timed_steps(h, spec["w"], flags, args.steps, args.warmup)
         launches = h.launch_count - launches0
+        in_region = sampler.count()
+        # a default run's timed region lasts ~0.15 s, one or two 100-ms samples: keep the SAME steps running
+        # (untimed) until the record has at least 4 samples of this load
+        t0 = time.time()
+        while sampler.proc is not None and sampler.count() < 4 and time.time() - t0 < 3.0:
+            h.map_resident(spec["w"], flags)
+            h.synchronize()
         barrier()
         clocks = sampler.stop()
+        clocks["samples_in_timed_region"] = in_region
         return ms, stages, launches, clocks
 
     ms, stages, launches, clocks = measure()
@@ -485,24 +509,34 @@ def run_gpu(args):
 
     # ---- e2e: the public sharding driver, pinned host atoms in, gathered records out ----
     def e2e_loop(batch_local, T_all, n_timed, n_warm):
-        def make_shard(a, b):  # this rank's templates are pre-staged in pinned host memory
-            a0 = shard_range(T_all, rank, world)[0]
-            return batch_local[a - a0:b - a0]
+        """A JOB of n_timed steps through the public sharding driver: ONE map_sharded call over n_timed x T_all
+        templates, each rank walking its contiguous block one step's worth at a time (chunk: a pinned H2D copy, the
+        kernels and a D2H read of the records per step) and one all_gather of all records at the end -- the
+        shape of BatchedTransientGridSearch.run(group).  (A collective per step makes every step wait for the
+        slowest of N ranks: measured 7.5x instead of 7.9x at N = 8.)  The pre-staged pinned batch stands for
+        every step's atoms."""
+        T_loc = len(batch_local)
+        assert T_loc * world == T_all
 
-        times, rec = [], None
+        def make_shard(a, b):
+            assert b - a == T_loc
+            return batch_local
+
+        def job(n):
+            return map_sharded(make_shard, T_all * n, spec["w"], BtSG=True, device=local_rank, chunk=T_loc)
+
+        if n_warm:
+            job(n_warm)
         barrier()
-        for i in range(n_warm + n_timed):
-            t0 = time.perf_counter()
-            rec = map_sharded(make_shard, T_all, spec["w"], BtSG=True, device=local_rank)
-            dt = time.perf_counter() - t0
-            if i >= n_warm:
-                times.append(dt)
+        t0 = time.perf_counter()
+        rec = job(n_timed)
+        dt = time.perf_counter() - t0
         barrier()
-        return max_over_ranks(sum(times)), rec
+        return max_over_ranks(dt), rec
 
     e2e_total, rec = e2e_loop(batch, T_total, args.steps, args.warmup)
     e2e_value = cells_all / e2e_total
-    assert len(rec) == T_total and np.all(rec["status"] == 0) and np.all(np.isfinite(rec["lnBtSG"]))
+    assert len(rec) == T_total * args.steps and np.all(rec["status"] == 0) and np.all(np.isfinite(rec["lnBtSG"]))
     crc_first = records_crc(rec[:T])  # global templates 0..T-1 exist at every N
 
     # ---- strong scaling: a FIXED template set through the same driver ----
@@ -513,11 +547,15 @@ def run_gpu(args):
         sbatch = pinned_batch(L, shi - slo, spec, seed0 + 500 + slo)
         n_timed = max(2, min(args.steps, 3))
         s_total, srec = e2e_loop(sbatch, Ts, n_timed, 1)
-        assert len(srec) == Ts and np.all(srec["status"] == 0)
+        assert len(srec) == Ts * n_timed and np.all(srec["status"] == 0)
+        # rank r's block of the job holds its (shi - slo) templates n_timed times: the first pass of every rank,
+        # in rank order, is the fixed set in global template order
+        per = len(srec) // world
+        srec = np.concatenate([srec[r * per:r * per + per // n_timed] for r in range(world)])
         strong = {
             "templates_total": Ts, "steps": n_timed, "value": Ts * spec["cells"] * n_timed / s_total,
             "unit": "cells/s", "ms_per_step": 1e3 * s_total / n_timed, "records_crc": records_crc(srec),
-            "api": "pyfstat_b200.batch.map_sharded (contiguous template blocks per rank, one all_gather of records)",
+            "api": "pyfstat_b200.batch.map_sharded (contiguous template blocks per rank, one all_gather of the job's records)",
             "note": "end to end (pinned host atoms in, gathered records out); records_crc must be identical at every N",
         }
         del sbatch
@@ -556,8 +594,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "cells/s", "templates_per_s": e2e_value / spec["cells"],
                     "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int((hi - lo) * L.RESULT_DTYPE.itemsize),
                     "ms_per_step": 1e3 * e2e_total / args.steps,
-                    "api": "pyfstat_b200.batch.map_sharded -> tcw_map_batch (C ABI), pinned host atoms in, records out"
-                           + (" + NCCL all_gather of the records" if world > 1 else "")},
+                    "api": "pyfstat_b200.batch.map_sharded(chunk = one step's templates) -> tcw_map_batch (C ABI) per step: "
+                           "pinned host atoms in, records out; ONE job of `steps` steps per rank"
+                           + (", one NCCL all_gather of all records at its end" if world > 1 else "")},
             "gpu_launches": launches_all,
             "roofline": roofline,
             "stage_ms": mean_stage(stages),
@@ -589,7 +628,8 @@ def run_gpu(args):
 # the other BASELINE configs (N = 1), each with its own clocks record
 # ---------------------------------------------------------------------------------------
 def with_clocks(fn, gpu_index):
-    sampler = ClockSampler(gpu_index).start()
+    sampler = ClockSampler(gpu_index).start().wait_first()
+    sampler.mark()
     out = fn()
     out["clocks"] = sampler.stop()
     return out

@@ -782,7 +782,7 @@ def test_exp_recurrence_sub_batches_and_segment_counts(gpu, monkeypatch):
 @pytest.mark.gpu
 def test_exp_recurrence_ragged_templates_and_segments(gpu, oracle):
     """Templates of different lengths (same first atom) in one launch, maps whose row count is not a
-    multiple of anything (row segments of the walk, 256-row tensor-core tiles, 128-column tiles with a
+    multiple of anything (row segments of the walk, 64-row tensor-core tiles, 128-column tiles with a
     ragged edge), three detectors; recurrence path vs the oracle and vs the tiled direct sum, both modes."""
     n, TA = 523, 1800
     full = synth_atoms(3, n, ("H1", "L1", "V1"), seed=909)
@@ -803,6 +803,24 @@ def test_exp_recurrence_ragged_templates_and_segments(gpu, oracle):
             assert float(res["lnBtSG"][t]) == pytest.approx(
                 oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=not exact)["lnBtSG"], abs=ATOL_PASS)
             assert int(res["status"][t]) == int(resd["status"][t])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [12, 40, 70, 130])
+def test_exp_recurrence_maps_smaller_than_a_tile(gpu, oracle, n):
+    """Maps of fewer rows / window lengths than one tensor-core tile (64 x 128), a single template and an odd
+    number of them: edge predicates of the epilogue, units without any k stage."""
+    TA = 1800
+    for T in (1, 3):
+        b = synth_atoms(T, n, ("H1", "L1"), seed=4000 + n + T)
+        w = canonical_window("exp", 10**9, n)
+        res, F = run_gpu(gpu, b, w, L.ALLOW_DEGENERATE)
+        assert np.all(res["path"] == 2)
+        for t in range(T):
+            o = oracle.compute_map(b.template(t), TA, w, allow_degenerate=True)
+            rel = np.abs(F[t] - o["F_mn"]) / np.maximum(np.abs(o["F_mn"]), 1e-30)
+            assert rel.max() <= RTOL, (n, T, t, rel.max())
+            assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(int(np.argmax(F[t])), F.shape[2])
 
 
 @pytest.mark.gpu
@@ -905,6 +923,12 @@ def test_exp_lut_geometries_really_differ(gpu, oracle):
         assert gpu.get_exp_lut() == (20.0, 2000, False)
         moved, _ = run_gpu(gpu, b, wr, 0)
         assert float(moved["lnBtSG"][0]) == pytest.approx(float(base["lnBtSG"][0]) + math.log(1.001), abs=1e-9)
+        # ... and the exponential window leaves the tensor-core path, which relies on the table's deviation from
+        # e^{-x} being small: direct sum (path 1); the common factor (1.001 on w, 1.001^2 on w^2) cancels in F
+        assert int(r2["path"][0]) == 2
+        re_, Fe = run_gpu(gpu, b, w, 0)
+        assert int(re_["path"][0]) == 1
+        assert (np.abs(Fe - F2) / np.abs(F2)).max() <= RTOL
         with pytest.raises(ValueError):
             gpu.set_exp_lut(20.0, 2000, tab[:-1])
         with pytest.raises(L.TcwError):

@@ -358,6 +358,42 @@ def exp_variants(h, L, spec, batch, peaks, steps=2, warmup=1):
     return out
 
 
+def exp_dispatch_ladder(h, L, spec, batch):
+    """What a grid that is NOT canonical costs (exp window, 30-d data): the host planner's fallbacks, so that the
+    cliffs between them are on record.  `path` is the result record's path field (2 recurrence + tensor cores,
+    1 tiled direct sum, 0 generic kernels)."""
+    from pyfstat_b200.window import TransientWindowRange
+
+    n, TA = spec["n"], TATOM
+    ladder = {
+        # rows two atoms apart (dt0 = 2 TAtom): tiled direct sum, rows fetch their own records
+        "dt0_2TAtom_tiled": (TransientWindowRange(2, T0_DATA, (n - 2) * TA, 2 * TA, 2 * TA, n * TA, TA), 0, 16),
+        # a grid offset from the atom grid by a third of an atom, dt0 = TAtom: still canonical (one row class)
+        "offset_grid_recurrence": (TransientWindowRange(2, T0_DATA + TA // 3, (n - 3) * TA, TA, 2 * TA, n * TA, TA), 0, 16),
+        # dt0 = 1.5 TAtom: two row classes, tiled direct sum
+        "dt0_1p5TAtom_tiled": (TransientWindowRange(2, T0_DATA, (n - 2) * TA, 3 * TA // 2, 2 * TA, n * TA, TA), 0, 16),
+        # the generic kernels (one thread per cell, the reference's sequential sums: the parity anchor)
+        "generic_kernel": (spec["w"], L.FORCE_GENERIC, 2),
+    }
+    out = {}
+    for name, (w, fl, T) in ladder.items():
+        sub = batch[:T]
+        h.upload(sub)
+        h.map_resident(w, L.WANT_BTSG | L.ALLOW_DEGENERATE | fl)  # warm-up (weight tables, allocations)
+        h.synchronize()
+        h.flush_l2()
+        h.synchronize()
+        h.timer_start()
+        h.map_resident(w, L.WANT_BTSG | L.ALLOW_DEGENERATE | fl)
+        ms = h.timer_stop()
+        rec = h.fetch_results()
+        cells = int(rec["N_t0"][0]) * int(rec["N_tau"][0]) if "N_t0" in rec.dtype.names else None
+        out[name] = {"templates": T, "ms_per_template": ms / T, "path": int(rec["path"][0]),
+                     "cells_per_s": (cells * T / (ms * 1e-3)) if cells else None}
+    h.upload(batch)
+    return out
+
+
 def pinned_batch(L, T, spec, seed):
     from pyfstat_b200.atoms import synth_atoms
 
@@ -695,7 +731,8 @@ def sec_exp30(h, L, peaks, steps=10, warmup=3):
                 "h2d_bytes_per_step": int(batch.nbytes), "d2h_bytes_per_step": int(T * L.RESULT_DTYPE.itemsize),
                 "api": "tcw_map_batch (C ABI), pinned host atoms in, records out"},
         "roofline": exp_rec_roofline(spec, T, exp_split(stages), *measured_peaks()), "stage_ms": mean_stage(stages),
-        "other_paths": exp_variants(h, L, spec, batch, peaks), "config": workload_config(spec),
+        "other_paths": exp_variants(h, L, spec, batch, peaks), "dispatch_ladder": exp_dispatch_ladder(h, L, spec, batch),
+        "config": workload_config(spec),
     }
 
 

@@ -796,6 +796,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         for (int c = 0; c < TCW_NCH; c++) U[c] = fma(c < 3 ? rho2 : rho, U[c], fma(-(c < 3 ? rhoL2 : rhoL), x1[c], x0[c]));
     };
     // cc: the slot of the correction-sum ring holding row m
+    // (running pointers instead of row * pitch products: the walk is bound by instruction issue, and the 64-bit
+    // multiply-adds of the addresses were ~20 of its ~170 instructions per row)
+    float *Fp = nullptr;  // &Ft[m * pitch] of the row about to be emitted
     auto cell = [&](int m, const unsigned char *cc) {
         float S[TCW_NCH];
 #pragma unroll
@@ -812,12 +815,13 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
         if (empty_win) F = 2.0f;  // no atom in the window: all sums zero in the reference -> its fallback value
         if (active) {
-            if (Ft) Ft[(size_t)m * w.pitch] = F;
+            if (Ft) *Fp = F;
             if (F >= best) {  // rows are walked downwards: among equal F the smaller row wins (np.argmax order)
                 best = F;
                 best_m = m;
             }
         }
+        Fp -= w.pitch;
     };
 
     if (NSEG > 1) {
@@ -880,31 +884,37 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             dsto[hq] = (uint32_t)(isA ? ci * TcxC::kRowA : 3 * TcxC::kRowA + ci * TcxC::kRowF) + 16u * pi;
         }
         const int m_top = m;
-        auto fetch_c = [&](int row, int slot) {
+        // source pointers of the row to fetch next, destination offset of its ring slot
+        const unsigned char *s0 = src[0] + (size_t)m_top * rowb[0], *s1 = src[1] + (size_t)m_top * rowb[1];
+        const bool two = lane + 32 < TcxC::kPiecesA + TcxC::kPiecesF;
+        auto fetch_c = [&](int row, uint32_t slot_off) {
             if (row >= lo) {
-                cp_async16(ringC + slot * TcxC::kRowBytes + dsto[0], src[0] + (size_t)row * rowb[0]);
-                if (lane + 32 < TcxC::kPiecesA + TcxC::kPiecesF)
-                    cp_async16(ringC + slot * TcxC::kRowBytes + dsto[1], src[1] + (size_t)row * rowb[1]);
+                cp_async16(ringC + slot_off + dsto[0], s0);
+                if (two) cp_async16(ringC + slot_off + dsto[1], s1);
             }
+            s0 -= rowb[0];
+            s1 -= rowb[1];
         };
 #pragma unroll 1
         for (int r = 0; r < Cfg::kDepth; r++) {
-            fetch_c(m_top - r, r);
+            fetch_c(m_top - r, (uint32_t)r * TcxC::kRowBytes);
             cp_async_commit();
         }
-        int slot = 0;
+        uint32_t slot_off = 0;
+        Fp = Ft + (ptrdiff_t)m * (ptrdiff_t)w.pitch;
 #pragma unroll 1
         for (; m >= lo; m--) {
             cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
             __syncwarp();                         // ... and every other lane's
             step(m);
-            cell(m, ringC + slot * TcxC::kRowBytes);
+            cell(m, ringC + slot_off);
             __syncwarp();  // all lanes have read the slots before they are refilled
-            fetch_c(m - Cfg::kDepth, slot);
+            fetch_c(m - Cfg::kDepth, slot_off);
             row_end(m);
-            slot = slot + 1 == Cfg::kDepth ? 0 : slot + 1;
+            slot_off = slot_off + TcxC::kRowBytes == (uint32_t)Cfg::kDepth * TcxC::kRowBytes ? 0u : slot_off + TcxC::kRowBytes;
         }
     } else {
+        Fp = Ft + (ptrdiff_t)m * (ptrdiff_t)w.pitch;
 #pragma unroll 1
         for (; m >= lo; m--) {
             cp_async_wait<Cfg::kDepth - 1>();

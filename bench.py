@@ -418,7 +418,7 @@ def exp_rec_roofline(spec, T, xs, hbm_peak, hbm_src):
     """Rooflines of the exponential window's default path (tcw_exp_rec.cuh): the tensor-core pass for the
     lookup table's deviation from the exact exponential (dominant kernel) and the FP64 walk."""
     burst, sustained, src = measured_tensor_peaks()
-    tc_flop = 14 * spec["visits"]  # 7 channel MACs per atom visit; the kernel issues exactly that plus ~1 % tile padding
+    tc_flop = 14 * spec["visits"]  # 7 channel MACs per atom visit; the kernel issues that plus ~5 % k-range padding
     achieved = T * tc_flop / (xs["tensor"] * 1e-3) / 1e12
     walk_bytes = (20 + 4) * spec["cells"]  # correction sums in (3 x FP32 + 4 x FP16), F_mn out (the lnBtSG pass re-reads it)
     walk = T * walk_bytes / (xs["walk"] * 1e-3) / 1e9
@@ -429,7 +429,7 @@ def exp_rec_roofline(spec, T, xs, hbm_peak, hbm_src):
         "algorithmic_flop_per_template": tc_flop, "atom_visits_per_template": spec["visits"],
         "launch_ms": xs["tensor"],
         "note": ("algorithmic flop = 2 x 7 channels x atom visits of the map (the direct sum's MAC count) = what the kernel "
-                 "executes up to ~1 % tile padding (7 x 64 = 448 MMA columns per tile and k step, none idle); the tensor pipe "
+                 "executes up to ~5 % k-range padding (7 x 64 = 448 MMA columns per tile and k step, none idle); the tensor pipe "
                  "runs at the rate cuBLAS sustains on this board (power cap), DESIGN.md section 5"),
         "walk_kernel": {"bound": "hbm", "kernel": "tcw_exp_walk_kernel", "achieved": walk, "peak": hbm_peak, "unit": "GB/s",
                         "frac": walk / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_template": walk_bytes,

@@ -43,7 +43,7 @@
 // apart (SBO); a prep kernel lays the atoms out in that chunked form -- per channel pair p and atom
 // block u: [group][c'][chunk] -- so a stage's A operand of a pair is one contiguous 4-KB bulk copy.
 // 128 window lengths per tile.  A tile is processed as two units -- the channels a2, b2, ab with the w^2
-// table (one MMA of 3 x 64 rows per 32 bytes of K), then Fa | Fb with the w table (two MMAs of 2 x 64
+// table (one MMA of N = 3 x 64 rows per 32 bytes of K), then Fa | Fb with the w table (one MMA of N = 4 x 64
 // rows) -- each unit in one half of TMEM.  The MMAs compute the TRANSPOSED tile (M = window lengths,
 // N = channel x row), see the kernel.  Warp
 // roles: TMA producer, MMA issuer, 4 epilogue warps (TMEM -> HBM scratch C); persistent CTAs, one
@@ -417,10 +417,13 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- MMA issuer ----
-            constexpr uint32_t idesc = tcx_idesc(128, 128, F16), idesc3 = tcx_idesc(128, 192, F16);
+            constexpr uint32_t idesc = tcx_idesc(128, 128, F16), idesc3 = tcx_idesc(128, 192, F16), idesc4 = tcx_idesc(128, 256, F16);
+            (void)idesc;
             // The MMA computes the TRANSPOSED tile: its A operand (M = 128) are the window lengths -- the weights
-            // V[k, n] -- its B operand the Hankel atoms: N = 3 x 64 (a2, b2, ab: unit 0) or 2 x 64 rows (a pair of
-            // unit 1).  TMEM lane = window length: the epilogue's stores are coalesced as they come (32 lanes = 32
+            // V[k, n] -- its B operand the Hankel atoms: N = 3 x 64 (a2, b2, ab: unit 0) or 4 x 64 rows (Fa_re, Fa_im,
+            // Fb_re, Fb_im: unit 1) -- ONE MMA per unit and 32 bytes of K, so the weights are read from shared memory
+            // once (two N = 128 MMAs for unit 1, -DTCX_UNIT1_SPLIT, read them twice: 7.65 instead of 6.77 ms per
+            // 8 x 120-d maps).  TMEM lane = window length: the epilogue's stores are coalesced as they come (32 lanes = 32
             // consecutive window lengths of one row).  (The first versions stacked the channels in M, two per MMA:
             // unit 0 then needs two M128 MMAs with a quarter of their lanes idle; as N = 192 it is one MMA of 3/4 the
             // duration -- 1/8 fewer tensor-pipe cycles per tile, and this pass runs at the board's power cap.)
@@ -463,6 +466,7 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                             const uint64_t vd = dv | (uint64_t)(((b0 + q * 4096) >> 4) & 0x3FFF);
                             const uint64_t xd0 = dx | (uint64_t)(((a0 + q * 32) >> 4) & 0x3FFF);
                             const uint32_t acc = (c > 0 || q > 0) ? 1u : 0u;
+#ifdef TCX_UNIT1_SPLIT  // two N = 128 MMAs (one per pair) instead of one N = 256: the weights are read twice
                             if (hh == 0) {
                                 tcx_mma<F16>(d0, vd, xd0, idesc3, acc);
                             } else {
@@ -470,6 +474,10 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
                                 tcx_mma<F16>(d0, vd, xd0, idesc, acc);
                                 tcx_mma<F16>(d0 + 128, vd, xd1, idesc, acc);
                             }
+#else
+                            // unit 0: N = 192 (24 chunks), unit 1: N = 256 (the two pairs' 2 x 16 chunks are adjacent)
+                            tcx_mma<F16>(d0, vd, xd0, hh == 0 ? idesc3 : idesc4, acc);
+#endif
                         }
                         tcx_commit(&empty[s]);  // the stage is free once these MMAs have read it
                     }

@@ -566,6 +566,8 @@ struct ExpPlan {
     bool ok = false;
     bool slide = true;   // A == 1: register sliding-window kernel
     bool canon = false;  // one class, A == 1, no shifts, no start beyond the data end: round 1's kernel
+    uint32_t rec_A = 0;  // > 0: the recurrence path applies (one class, rows rec_A atoms apart, no shifts, no start
+                         // beyond the data end); `ok` = the tiled direct-sum kernels apply
     uint32_t KW = 0;
     ExpClasses ec = {};
     int32_t delta[TCW_EXP_PMAX] = {0, 0, 0, 0};
@@ -603,7 +605,9 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
     const uint32_t P = rem ? TAtom / gcd_u32(rem, TAtom) : 1u;
     if (P > TCW_EXP_PMAX) return p;
     const uint64_t A64 = (uint64_t)P * w.dt0 / TAtom;  // exact by construction
-    if (A64 < 1 || A64 > TCW_EXP_AMAX) return p;
+    // rows more than AMAX atoms apart: no tiled direct sum, but the recurrence path (one row class) walks any step
+    const bool tiled = A64 <= TCW_EXP_AMAX;
+    if (A64 < 1 || (!tiled && (P != 1 || A64 > 4096))) return p;
     const uint32_t t0_data = h->meta[0].t0_data;
     p.shift.resize(h->T);
     for (int t = 0; t < h->T; t++) {
@@ -644,16 +648,19 @@ static ExpPlan plan_exp(const tcw_handle *h, const MapWindow &w) {
         }
     }
     for (uint32_t r = P; r <= TCW_EXP_PMAX; r++) p.ec.ybeg[r] = ytiles;
-    if (ytiles > 65535u) return p;  // grid.y limit -> generic kernels
+    const bool tiled_grid_ok = ytiles <= 65535u;  // grid.y limit of the tiled kernels
     if (Kmax > (int64_t)h->Nmax + 64) Kmax = (int64_t)h->Nmax + 64;  // never need k beyond the data
     for (auto &K : p.Kn) K = (int32_t)std::min<int64_t>(K, Kmax);
     p.KW = (uint32_t)((std::max<int64_t>(Kmax, 0) + 1 + TCW_EXP_KC - 1) / TCW_EXP_KC * TCW_EXP_KC);
     const uint64_t n_tiles = (w.N_tau + TN - 1) / TN;
-    if ((uint64_t)P * n_tiles * p.KW * TN * 4ull * TCW_EXP_WP > (8ull << 30)) return p;  // table too large
-    p.canon = P == 1 && A64 == 1;
-    for (int t = 0; t < h->T && p.canon; t++)
-        p.canon = p.shift[t] == 0 && (int64_t)p.ec.i00[0] + (int64_t)w.N_t0 - 1 <= (int64_t)h->meta[t].numAtoms - 1;
-    p.ok = true;
+    const bool table_ok = (uint64_t)P * n_tiles * p.KW * TN * 4ull * TCW_EXP_WP <= (8ull << 30);  // direct-sum weight table
+    bool rec = P == 1;
+    for (int t = 0; t < h->T && rec; t++)
+        rec = p.shift[t] == 0 &&
+              (int64_t)p.ec.i00[0] + (int64_t)A64 * ((int64_t)w.N_t0 - 1) <= (int64_t)h->meta[t].numAtoms - 1;
+    p.rec_A = rec ? (uint32_t)A64 : 0u;
+    p.canon = rec && A64 == 1;
+    p.ok = tiled && tiled_grid_ok && table_ok;
     return p;
 }
 
@@ -893,22 +900,29 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             if (ok) path = PATH_FAST;
         } else {
             ep = plan_exp(h, w);
-            if (ep.ok) path = PATH_FAST;
+            const bool rec_ok = ep.rec_A > 0 && !(flags & TCW_EXP_DIRECT) && (exact || h->lut_canonical);
+            if (ep.ok || rec_ok) path = PATH_FAST;
         }
     }
     // exponential window on a canonical grid: FP64 recurrence down the rows (+ the tensor-core correction
     // in lookup-table mode), tcw_exp_rec.cuh; TCW_EXP_DIRECT keeps the tiled direct sum
     // (an uploaded table that is not e^{-i dx} takes the direct sum: the tensor-core pass relies on the table's
     // deviation from the exact exponential being small)
-    const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.canon && !(flags & TCW_EXP_DIRECT) &&
+    // Rows rec_A > 1 atoms apart (dt0 a multiple of TAtom): the same two kernels on the REFINED grid of one row per
+    // atom -- the recurrence has to step through every atom anyway, the tensor-core pass computes the correction
+    // sums of all refined rows (as much work as the dt0 = TAtom map of the same data, still far below the direct
+    // sum's) -- and the walk emits every rec_A-th row.
+    const bool exp_rec = path == PATH_FAST && w.type == TCW_WINDOW_EXP && ep.rec_A > 0 && !(flags & TCW_EXP_DIRECT) &&
                          (exact || h->lut_canonical);
+    const uint32_t rec_A = exp_rec ? ep.rec_A : 1u;
+    const uint32_t tc_rows = exp_rec ? rec_A * (w.N_t0 - 1u) + 1u : w.N_t0;  // refined rows
     const bool exp_tc = exp_rec && !exact;
     const bool tc_f16 = h->tc_f16 != 0;
     const uint32_t tc_rs = tc_f16 ? TcxCfg<true>::kRowStep : TcxCfg<false>::kRowStep, tc_kc = 8 * tc_rs, tc_span = TCX_IROWS;
-    const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (w.N_t0 + tc_span - 1) / tc_span;
+    const uint32_t tc_n_nt = (w.N_tau + TCX_TAUS - 1) / TCX_TAUS, tc_n_mb = (tc_rows + tc_span - 1) / tc_span;
     const uint32_t tc_cpitch = tc_n_nt * TCX_TAUS, tc_U = (h->Nmax + tc_kc - 1) / tc_kc + 10;
     const uint32_t tc_chunks = path == PATH_FAST && w.type == TCW_WINDOW_EXP ? (ep.KW + tc_kc - 1) / tc_kc : 0;
-    const size_t tc_c_per_tpl = (size_t)w.N_t0 * tc_cpitch * TcxC::kBytesPerCell;
+    const size_t tc_c_per_tpl = (size_t)tc_rows * tc_cpitch * TcxC::kBytesPerCell;
 
     // ---- buffers ----
     int rc;
@@ -1205,7 +1219,9 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         } else if (exp_rec) {
             // correction sums of the sub-batch: group A (a2, b2, ab) then group F (Fa, Fb), TcxC
             unsigned char *c_a = (unsigned char *)h->d_C.p;
-            unsigned char *c_f = c_a + (size_t)cnt * 3 * w.N_t0 * tc_cpitch * TcxC::kElemA;
+            unsigned char *c_f = c_a + (size_t)cnt * 3 * tc_rows * tc_cpitch * TcxC::kElemA;
+            MapWindow wt = w;  // the tensor-core pass works on the refined rows
+            wt.N_t0 = tc_rows;
             const unsigned char *corr = nullptr;
             tcw_exp_atoms_f64_kernel<<<dim3((h->xpad + 255) / 256, cnt), 256, 0, st>>>(
                 (const float *)h->d_X.p, h->xpad, t_base, (double *)h->d_Xd.p);
@@ -1238,11 +1254,11 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 if (tc_f16)
                     tcw_exptc_map_kernel<true><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, -tc_shift), c_a, c_f, tc_cpitch);
+                        (uint32_t)cnt, wt, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, -tc_shift), c_a, c_f, tc_cpitch);
                 else
                     tcw_exptc_map_kernel<false><<<ctas, TCX_THREADS, TCX_SMEM, st>>>(
                         h->d_G.p, tc_U, h->d_W.p, tc_chunks, (const int32_t *)h->d_Kn.p, (const TplMeta *)h->d_meta.p, t_base,
-                        (uint32_t)cnt, w, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, TCX_VSCALE_LOG2 - tc_shift), c_a, c_f,
+                        (uint32_t)cnt, wt, ep.ec.i00[0], tc_n_nt, tc_n_mb, n_tiles, ldexpf(1.0f, TCX_VSCALE_LOG2 - tc_shift), c_a, c_f,
                         tc_cpitch);
                 h->launches++;
                 CUDA_TRY(h, cudaGetLastError());
@@ -1264,7 +1280,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         tcw_exp_walk_kernel<HASC, NS><<<grid, WC::kThreads, smem, st>>>(                                           \
             (const double *)h->d_Xd.p, h->xpad, (const int32_t *)h->d_Kn.p,                                        \
             (const TplMeta *)h->d_meta.p, t_base, w,                                                               \
-            ep.ec.i00[0], ep.delta[0], TAtom, corr, c_f, tc_cpitch, (const float *)h->d_scale.p,                   \
+            ep.ec.i00[0], ep.delta[0], TAtom, (int)rec_A, corr, c_f, tc_rows, tc_cpitch,                         \
+            (const float *)h->d_scale.p,                                                                         \
             ldexpf(1.0f, tc_shift), fmn, p_maxkey, p_flags);                                                       \
     } while (0)
             if (exp_tc) {

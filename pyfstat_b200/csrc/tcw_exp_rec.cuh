@@ -676,8 +676,8 @@ template <bool HAS_C, int NSEG>
 __global__ void __launch_bounds__(WalkCfg<NSEG>::kThreads)
 tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
                     const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, MapWindow w,
-                    uint32_t i00, int32_t delta, uint32_t TAtom, const unsigned char *__restrict__ CA,
-                    const unsigned char *__restrict__ CF, uint32_t cpitch, const float *__restrict__ cscale, float cunshift, float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+                    uint32_t i00, int32_t delta, uint32_t TAtom, int rowstep, const unsigned char *__restrict__ CA,
+                    const unsigned char *__restrict__ CF, uint32_t c_rows, uint32_t cpitch, const float *__restrict__ cscale, float cunshift, float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     using Cfg = WalkCfg<NSEG>;
     extern __shared__ __align__(16) unsigned char walk_smem[];
     __shared__ unsigned long long red[Cfg::kWarps];
@@ -727,8 +727,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     const bool use_ring = off_max - off_min <= TCX_WALK_XRING - 32;
     const int off = empty_win ? off_min : off_own;
 
-    // rows 0 .. R-1 (rows >= N_t0 lie beyond the map -- the canonical plan guarantees R >= N_t0 -- and
-    // give no output); segment `seg` owns rows [lo, hi)
+    // REFINED rows 0 .. R-1, one per atom; map row m is refined row rowstep * m (rowstep = dt0 / TAtom; the plan
+    // guarantees that the last map row lies within the data), the others and those beyond the map give no
+    // output; segment `seg` owns refined rows [lo, hi)
     const int R = (int)numAtoms - (int)i00;
     const int SEG = (R + NSEG - 1) / NSEG;
     const int lo = min(seg * SEG, R), hi = min(lo + SEG, R);
@@ -862,18 +863,23 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     }
 
     // ---- pass 2: the segment (again) from its true state, with output ----
+    const int last_emit = rowstep * ((int)w.N_t0 - 1);  // the highest refined row that is a map row
     int m = hi - 1;
     if (hi > lo) {
         fill_ring(m);
     }
 #pragma unroll 1
-    for (; m >= lo && m >= (int)w.N_t0; m--) {  // rows beyond the map: no output
+    for (; m >= lo && m > last_emit; m--) {  // rows beyond the map: no output
         cp_async_wait<Cfg::kDepth - 1>();
         __syncwarp();
         step(m);
         __syncwarp();
         row_end(m);
     }
+    // m <= last_emit from here on: map row mr = m / rowstep is emitted when phase == 0
+    int mr = m >= 0 ? m / rowstep : 0;
+    int phase = m >= 0 ? m - mr * rowstep : 0;
+    Fp = Ft + (ptrdiff_t)mr * (ptrdiff_t)w.pitch;
     if (HAS_C) {
         // a row of the warp: 16-byte pieces, group A first; piece q is fetched by lane q % 32
         const unsigned char *src[2];
@@ -887,48 +893,59 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             const int ppc = (isA ? TcxC::kRowA : TcxC::kRowF) / 16;  // pieces per channel
             const int ci = isA ? qq / ppc : qf / ppc, pi = isA ? qq % ppc : qf % ppc;
             const int es = isA ? TcxC::kElemA : TcxC::kElemF, nch = isA ? 3 : 4;
-            src[hq] = (isA ? CA : CF) + (((size_t)tz * nch + ci) * w.N_t0 * cpitch + (size_t)(n - lane)) * es + 16 * pi;
-            rowb[hq] = (size_t)cpitch * es;
+            src[hq] = (isA ? CA : CF) + (((size_t)tz * nch + ci) * c_rows * cpitch + (size_t)(n - lane)) * es + 16 * pi;
+            rowb[hq] = (size_t)cpitch * es * (size_t)rowstep;  // the correction sums are indexed by REFINED row
             dsto[hq] = (uint32_t)(isA ? ci * TcxC::kRowA : 3 * TcxC::kRowA + ci * TcxC::kRowF) + 16u * pi;
         }
-        const int m_top = m;
-        // source pointers of the row to fetch next, destination offset of its ring slot
-        const unsigned char *s0 = src[0] + (size_t)m_top * rowb[0], *s1 = src[1] + (size_t)m_top * rowb[1];
+        const int mr_top = mr;
+        // source pointers of the map row to fetch next, destination offset of its ring slot
+        const unsigned char *s0 = src[0] + (size_t)mr_top * rowb[0], *s1 = src[1] + (size_t)mr_top * rowb[1];
         const bool two = lane + 32 < TcxC::kPiecesA + TcxC::kPiecesF;
-        auto fetch_c = [&](int row, uint32_t slot_off) {
-            if (row >= lo) {
+        auto fetch_c = [&](int row, uint32_t slot_off) {  // row: map row
+            if (row >= 0 && row * rowstep >= lo) {
                 cp_async16(ringC + slot_off + dsto[0], s0);
                 if (two) cp_async16(ringC + slot_off + dsto[1], s1);
             }
             s0 -= rowb[0];
             s1 -= rowb[1];
         };
+        // (the rows of a segment are fetched kDepth EMITTED rows ahead; a copy is issued at least kDepth refined
+        // rows -- commit groups -- before it is read, so the fixed wait count below covers it)
 #pragma unroll 1
         for (int r = 0; r < Cfg::kDepth; r++) {
-            fetch_c(m_top - r, (uint32_t)r * TcxC::kRowBytes);
+            fetch_c(mr_top - r, (uint32_t)r * TcxC::kRowBytes);
             cp_async_commit();
         }
         uint32_t slot_off = 0;
-        Fp = Ft + (ptrdiff_t)m * (ptrdiff_t)w.pitch;
 #pragma unroll 1
         for (; m >= lo; m--) {
             cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
             __syncwarp();                         // ... and every other lane's
             step(m);
-            cell(m, ringC + slot_off);
+            const bool emit = phase == 0;
+            if (emit) cell(mr, ringC + slot_off);
             __syncwarp();  // all lanes have read the slots before they are refilled
-            fetch_c(m - Cfg::kDepth, slot_off);
+            if (emit) {
+                fetch_c(mr - Cfg::kDepth, slot_off);
+                slot_off = slot_off + TcxC::kRowBytes == (uint32_t)Cfg::kDepth * TcxC::kRowBytes ? 0u : slot_off + TcxC::kRowBytes;
+                mr--;
+                phase = rowstep;
+            }
+            phase--;
             row_end(m);
-            slot_off = slot_off + TcxC::kRowBytes == (uint32_t)Cfg::kDepth * TcxC::kRowBytes ? 0u : slot_off + TcxC::kRowBytes;
         }
     } else {
-        Fp = Ft + (ptrdiff_t)m * (ptrdiff_t)w.pitch;
 #pragma unroll 1
         for (; m >= lo; m--) {
             cp_async_wait<Cfg::kDepth - 1>();
             __syncwarp();
             step(m);
-            cell(m, nullptr);
+            if (phase == 0) {
+                cell(mr, nullptr);
+                mr--;
+                phase = rowstep;
+            }
+            phase--;
             __syncwarp();
             row_end(m);
         }
@@ -937,9 +954,11 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     // single-atom cells (Exp.cu's i_t1 == i_t0): a column whose window holds one atom, or the row that starts
     // on the last atom
     {
-        const int m_last = (int)numAtoms - 1 - (int)i00;
-        const int top = min(hi, (int)w.N_t0);
-        const bool degenerate = active && K >= 0 && top > lo && (K == 0 || (m_last >= lo && m_last < top));
+        const int m_last = (int)numAtoms - 1 - (int)i00;  // refined row
+        const int top = min(hi, last_emit + 1);
+        const bool any_emit = top > lo && (top - 1) / rowstep * rowstep >= lo;
+        const bool degenerate = active && K >= 0 && any_emit &&
+                                (K == 0 || (m_last >= lo && m_last < top && m_last % rowstep == 0));
         if (degenerate) atomicOr(&flags[t], TCW_FLAG_DEGENERATE);
     }
     const unsigned long long key = (active && best > -1.0f) ? pack_key(best, (uint32_t)best_m * w.N_tau + n) : 0ull;

@@ -806,6 +806,40 @@ def test_exp_recurrence_ragged_templates_and_segments(gpu, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,off", [(2, 0), (3, 600), (4, 0), (7, 1000), (16, 0)])
+def test_exp_recurrence_rows_several_atoms_apart(gpu, oracle, k, off):
+    """dt0 = k TAtom (one row class, rows k atoms apart; any dtau): the recurrence path on the refined grid of
+    one row per atom, the walk emitting every k-th row -- also beyond the tiled direct sum's limit of 4 atoms
+    per row.  Against the oracle in both exp modes, ragged templates, with and without row segments."""
+    n, TA = 420, 1800
+    full = synth_atoms(3, n, ("H1", "L1"), seed=7000 + k)
+    tpls = [full.template(0), [a[: n - 5] for a in full.template(1)], [a[: n - 2 * k] for a in full.template(2)]]
+    b = batch_from_detector_lists(tpls, TA)
+    n_rows = (n - 2 * k - 3) // k  # the last row starts within the shortest template
+    w = TransientWindowRange(2, 10**9 + off, (n_rows - 1) * k * TA, k * TA, 2 * TA, 300 * TA, 2 * TA)
+    for exact in (0, L.EXP_EXACT):
+        res, F = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE)
+        assert np.all(res["path"] == 2), res["path"]
+        assert F.shape[1] == n_rows
+        strict = run_gpu(gpu, b, w, exact, fmn=False)[0]
+        for t in range(b.T):
+            o = oracle.compute_map(b.template(t), TA, w, exact_exp=bool(exact), allow_degenerate=True)
+            rel = np.abs(F[t] - o["F_mn"]) / np.maximum(np.abs(o["F_mn"]), 1e-30)
+            assert rel.max() <= RTOL, (k, t, exact, rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+            flat = int(np.argmax(F[t]))
+            assert (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
+            assert float(res["maxF"][t]) == float(F[t].max())
+            assert float(res["lnBtSG"][t]) == pytest.approx(
+                oracle.bstat(F[t].astype(np.float64), float(res["maxF"][t]), w, use_lut=not exact)["lnBtSG"], abs=ATOL_PASS)
+            o_strict = oracle.compute_map(b.template(t), TA, w, exact_exp=bool(exact), want_btsg=False)
+            assert int(strict["status"][t]) == o_strict["status"], (k, t, exact)
+        if k <= 4:  # the tiled direct sum handles these too: same maps
+            resd, Fd = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE | L.EXP_DIRECT)
+            assert np.all(resd["path"] == 1)
+            assert (np.abs(F - Fd) / np.abs(Fd)).max() <= RTOL
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [12, 40, 70, 130])
 def test_exp_recurrence_maps_smaller_than_a_tile(gpu, oracle, n):
     """Maps of fewer rows / window lengths than one tensor-core tile (64 x 128), a single template and an odd

@@ -366,8 +366,12 @@ def exp_dispatch_ladder(h, L, spec, batch):
 
     n, TA = spec["n"], TATOM
     ladder = {
-        # rows two atoms apart (dt0 = 2 TAtom): tiled direct sum, rows fetch their own records
-        "dt0_2TAtom_tiled": (TransientWindowRange(2, T0_DATA, (n - 2) * TA, 2 * TA, 2 * TA, n * TA, TA), 0, 16),
+        # rows two atoms apart (dt0 = 2 TAtom): the recurrence path on the refined grid (every second row emitted) ...
+        "dt0_2TAtom_recurrence": (TransientWindowRange(2, T0_DATA, (n - 2) * TA, 2 * TA, 2 * TA, n * TA, TA), 0, 16),
+        # ... and the same grid through the tiled direct sum (rows fetch their own records)
+        "dt0_2TAtom_tiled": (TransientWindowRange(2, T0_DATA, (n - 2) * TA, 2 * TA, 2 * TA, n * TA, TA), L.EXP_DIRECT, 16),
+        # dt0 = dtau = 8 TAtom (a coarse grid over the same data: beyond the tiled kernels' 4 atoms per row)
+        "dt0_8TAtom_recurrence": (TransientWindowRange(2, T0_DATA, (n - 8) * TA, 8 * TA, 8 * TA, n * TA, 8 * TA), 0, 16),
         # a grid offset from the atom grid by a third of an atom, dt0 = TAtom: still canonical (one row class)
         "offset_grid_recurrence": (TransientWindowRange(2, T0_DATA + TA // 3, (n - 3) * TA, TA, 2 * TA, n * TA, TA), 0, 16),
         # dt0 = 1.5 TAtom: two row classes, tiled direct sum

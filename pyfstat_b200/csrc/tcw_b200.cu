@@ -368,17 +368,21 @@ extern "C" int tcw_create(int device, tcw_handle **out) {
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exptc_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCX_SMEM));
     if (const char *v = getenv("TCW_TC_TF32")) h->tc_f16 = atoi(v) ? 0 : 1;
-#define WALK_ATTR(NS)                                                                                              \
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<true, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           WalkCfg<NS>::smem(true)));                                                  \
-    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<false, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           WalkCfg<NS>::smem(false)))
+#define WALK_ATTR1(HASC, NS, S1)                                                                                     \
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_exp_walk_kernel<HASC, NS, S1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           WalkCfg<NS>::smem(HASC)))
+#define WALK_ATTR(NS)             \
+    WALK_ATTR1(true, NS, true);   \
+    WALK_ATTR1(true, NS, false);  \
+    WALK_ATTR1(false, NS, true);  \
+    WALK_ATTR1(false, NS, false)
     WALK_ATTR(1);
     WALK_ATTR(2);
     WALK_ATTR(4);
     WALK_ATTR(8);
     WALK_ATTR(16);
 #undef WALK_ATTR
+#undef WALK_ATTR1
     CUDA_TRY(nullptr, cudaFuncSetAttribute(tcw_rect_map_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TCW_RECTP_SMEM));
     if (const char *v = getenv("TCW_RECT_PERSIST")) h->rect_persist = atoi(v);
@@ -1277,7 +1281,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         using WC = WalkCfg<NS>;                                                                                    \
         const size_t smem = WC::smem(HASC);                                                                        \
         dim3 grid((w.N_tau + 32 * WC::kCG - 1) / (32 * WC::kCG), cnt);                                             \
-        tcw_exp_walk_kernel<HASC, NS><<<grid, WC::kThreads, smem, st>>>(                                           \
+        auto kern = rec_A == 1 ? tcw_exp_walk_kernel<HASC, NS, true> : tcw_exp_walk_kernel<HASC, NS, false>;        \
+        kern<<<grid, WC::kThreads, smem, st>>>(                                                                    \
             (const double *)h->d_Xd.p, h->xpad, (const int32_t *)h->d_Kn.p,                                        \
             (const TplMeta *)h->d_meta.p, t_base, w,                                                               \
             ep.ec.i00[0], ep.delta[0], TAtom, (int)rec_A, corr, c_f, tc_rows, tc_cpitch,                         \

@@ -672,6 +672,12 @@ __global__ void tcw_exp_atoms_f64_kernel(const float *__restrict__ X, uint32_t x
     }
 }
 
+struct WalkRingOn {
+    __device__ constexpr operator bool() const { return true; }
+};
+struct WalkRingOff {
+    __device__ constexpr operator bool() const { return false; }
+};
 // STEP1: rows one atom apart (rowstep == 1, every refined row is a map row): the emission test is compiled out --
 // with it in the loop the canonical maps run 8-25 % slower (the F-statistic epilogue becomes conditional code).
 template <bool HAS_C, int NSEG, bool STEP1>
@@ -775,23 +781,24 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         __syncwarp();
     };
     // end of row m: the block needed 16 rows from now joins this row's commit group
-    auto row_end = [&](int m) {
+    auto row_end = [&](int m, auto ring) {
         const int jl = m + off_min, j0 = m + off0;
-        if (use_ring && (jl & 15) == 15) fetch_block((jl >> 4) - 1, false);
+        if (ring && (jl & 15) == 15) fetch_block((jl >> 4) - 1, false);
         if ((j0 & 15) == 15) fetch_block((j0 >> 4) - 1, true);  // into the half the rows above have left
         cp_async_commit();
     };
 
     // entering atom of a row, fetched one row ahead (one broadcast 32-byte record)
     // (rows m < 0 and atoms beyond the data read the zero padding of the array: xpad >= numAtoms + 64)
-    auto step = [&](int m) {
+    // `ring`: use_ring as a bool, or as a compile-time constant in the main loops (a warp-uniform branch per row less)
+    auto step = [&](int m, auto ring) {
         double x0[TCW_NCH], x1[TCW_NCH];
         {
             const int slot0 = (m + off0) & 31;  // the same address in every lane: a broadcast read
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++) x0[c] = ringX0[c][slot0];
         }
-        if (use_ring) {
+        if (ring) {
             const int slot = (m + off) & (TCX_WALK_XRING - 1);
 #pragma unroll
             for (int c = 0; c < TCW_NCH; c++) x1[c] = ringX[c][slot];
@@ -843,9 +850,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             for (int m = hi - 1; m >= lo; m--) {
                 cp_async_wait<Cfg::kDepth - 1>();
                 __syncwarp();
-                step(m);
+                step(m, use_ring);
                 __syncwarp();
-                row_end(m);
+                row_end(m, use_ring);
             }
         }
         cp_async_wait<0>();  // no copy into the ring is in flight any more
@@ -874,9 +881,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     for (; m >= lo && m > last_emit; m--) {  // rows beyond the map: no output
         cp_async_wait<Cfg::kDepth - 1>();
         __syncwarp();
-        step(m);
+        step(m, use_ring);
         __syncwarp();
-        row_end(m);
+        row_end(m, use_ring);
     }
     // m <= last_emit from here on: map row mr = m / rowstep is emitted when phase == 0
     int mr = STEP1 ? m : (m >= 0 ? m / rowstep : 0);
@@ -919,38 +926,46 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             cp_async_commit();
         }
         uint32_t slot_off = 0;
+        auto main_loop = [&](auto ring) {
 #pragma unroll 1
-        for (; m >= lo; m--) {
-            cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
-            __syncwarp();                         // ... and every other lane's
-            step(m);
-            const bool emit = STEP1 || phase == 0;
-            if (emit) cell(mr, ringC + slot_off);
-            __syncwarp();  // all lanes have read the slots before they are refilled
-            if (emit) {
-                fetch_c(mr - Cfg::kDepth, slot_off);
-                slot_off = slot_off + TcxC::kRowBytes == (uint32_t)Cfg::kDepth * TcxC::kRowBytes ? 0u : slot_off + TcxC::kRowBytes;
-                mr--;
-                if (!STEP1) phase = rowstep;
+            for (; m >= lo; m--) {
+                cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
+                __syncwarp();                         // ... and every other lane's
+                step(m, ring);
+                const bool emit = STEP1 || phase == 0;
+                if (emit) cell(mr, ringC + slot_off);
+                __syncwarp();  // all lanes have read the slots before they are refilled
+                if (emit) {
+                    fetch_c(mr - Cfg::kDepth, slot_off);
+                    slot_off = slot_off + TcxC::kRowBytes == (uint32_t)Cfg::kDepth * TcxC::kRowBytes ? 0u : slot_off + TcxC::kRowBytes;
+                    mr--;
+                    if (!STEP1) phase = rowstep;
+                }
+                if (!STEP1) phase--;
+                row_end(m, ring);
             }
-            if (!STEP1) phase--;
-            row_end(m);
-        }
+        };
+        if (use_ring) main_loop(WalkRingOn{});
+        else main_loop(WalkRingOff{});
     } else {
+        auto main_loop = [&](auto ring) {
 #pragma unroll 1
-        for (; m >= lo; m--) {
-            cp_async_wait<Cfg::kDepth - 1>();
-            __syncwarp();
-            step(m);
-            if (STEP1 || phase == 0) {
-                cell(mr, nullptr);
-                mr--;
-                if (!STEP1) phase = rowstep;
+            for (; m >= lo; m--) {
+                cp_async_wait<Cfg::kDepth - 1>();
+                __syncwarp();
+                step(m, ring);
+                if (STEP1 || phase == 0) {
+                    cell(mr, nullptr);
+                    mr--;
+                    if (!STEP1) phase = rowstep;
+                }
+                if (!STEP1) phase--;
+                __syncwarp();
+                row_end(m, ring);
             }
-            if (!STEP1) phase--;
-            __syncwarp();
-            row_end(m);
-        }
+        };
+        if (use_ring) main_loop(WalkRingOn{});
+        else main_loop(WalkRingOff{});
     }
     cp_async_wait<0>();
     // single-atom cells (Exp.cu's i_t1 == i_t0): a column whose window holds one atom, or the row that starts

@@ -768,6 +768,9 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     const int off0 = (int)i00 + ka;  // entering atom of row m: index m + off0
     // everything the pass starting at row m_first needs at once: blocks from one below the lowest
     // leaving atom up to the highest
+    // next rows at whose end a ring block is refilled (every 16 rows each, at their own phases): one compare per
+    // row instead of two masked tests
+    int evL = 0, evE = 0, ev = 0;
     auto fill_ring = [&](int m_first) {
         __syncwarp();
         if (use_ring) {
@@ -779,12 +782,24 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
+        // the largest m <= m_first with ((m + o) & 15) == 15
+        evL = use_ring ? m_first - (((m_first + off_min) + 1) & 15) : -0x40000000;
+        evE = m_first - (((m_first + off0) + 1) & 15);
+        ev = max(evL, evE);
     };
     // end of row m: the block needed 16 rows from now joins this row's commit group
     auto row_end = [&](int m, auto ring) {
-        const int jl = m + off_min, j0 = m + off0;
-        if (ring && (jl & 15) == 15) fetch_block((jl >> 4) - 1, false);
-        if ((j0 & 15) == 15) fetch_block((j0 >> 4) - 1, true);  // into the half the rows above have left
+        if (m == ev) {
+            if (ring && m == evL) {
+                fetch_block(((m + off_min) >> 4) - 1, false);
+                evL -= 16;
+            }
+            if (m == evE) {
+                fetch_block(((m + off0) >> 4) - 1, true);  // into the half the rows above have left
+                evE -= 16;
+            }
+            ev = max(evL, evE);
+        }
         cp_async_commit();
     };
 
@@ -817,7 +832,7 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     // (running pointers instead of row * pitch products: the walk is bound by instruction issue, and the 64-bit
     // multiply-adds of the addresses were ~20 of its ~170 instructions per row)
     float *Fp = nullptr;  // &Ft[m * pitch] of the row about to be emitted
-    auto cell = [&](int m, const unsigned char *cc) {
+    auto cell = [&](int m, const unsigned char *cc, auto has_f) {
         float S[TCW_NCH];
 #pragma unroll
         for (int c = 0; c < TCW_NCH; c++) {
@@ -833,13 +848,13 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
         float F = fstat_fast(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
         if (empty_win) F = 2.0f;  // no atom in the window: all sums zero in the reference -> its fallback value
         if (active) {
-            if (Ft) *Fp = F;
+            if (has_f) *Fp = F;
             if (F >= best) {  // rows are walked downwards: among equal F the smaller row wins (np.argmax order)
                 best = F;
                 best_m = m;
             }
         }
-        Fp -= w.pitch;
+        if (has_f) Fp -= w.pitch;
     };
 
     if (NSEG > 1) {
@@ -926,14 +941,14 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
             cp_async_commit();
         }
         uint32_t slot_off = 0;
-        auto main_loop = [&](auto ring) {
+        auto main_loop = [&](auto ring, auto has_f) {
 #pragma unroll 1
             for (; m >= lo; m--) {
                 cp_async_wait<Cfg::kDepth - 1>();  // the oldest row in flight has landed (this lane's pieces)
                 __syncwarp();                         // ... and every other lane's
                 step(m, ring);
                 const bool emit = STEP1 || phase == 0;
-                if (emit) cell(mr, ringC + slot_off);
+                if (emit) cell(mr, ringC + slot_off, has_f);
                 __syncwarp();  // all lanes have read the slots before they are refilled
                 if (emit) {
                     fetch_c(mr - Cfg::kDepth, slot_off);
@@ -945,17 +960,23 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
                 row_end(m, ring);
             }
         };
-        if (use_ring) main_loop(WalkRingOn{});
-        else main_loop(WalkRingOff{});
+        // (use_ring is warp-uniform, Ft kernel-uniform: four compiled loop bodies, no such branch per row)
+        if (use_ring) {
+            if (Ft) main_loop(WalkRingOn{}, WalkRingOn{});
+            else main_loop(WalkRingOn{}, WalkRingOff{});
+        } else {
+            if (Ft) main_loop(WalkRingOff{}, WalkRingOn{});
+            else main_loop(WalkRingOff{}, WalkRingOff{});
+        }
     } else {
-        auto main_loop = [&](auto ring) {
+        auto main_loop = [&](auto ring, auto has_f) {
 #pragma unroll 1
             for (; m >= lo; m--) {
                 cp_async_wait<Cfg::kDepth - 1>();
                 __syncwarp();
                 step(m, ring);
                 if (STEP1 || phase == 0) {
-                    cell(mr, nullptr);
+                    cell(mr, nullptr, has_f);
                     mr--;
                     if (!STEP1) phase = rowstep;
                 }
@@ -964,8 +985,14 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
                 row_end(m, ring);
             }
         };
-        if (use_ring) main_loop(WalkRingOn{});
-        else main_loop(WalkRingOff{});
+        // (use_ring is warp-uniform, Ft kernel-uniform: four compiled loop bodies, no such branch per row)
+        if (use_ring) {
+            if (Ft) main_loop(WalkRingOn{}, WalkRingOn{});
+            else main_loop(WalkRingOn{}, WalkRingOff{});
+        } else {
+            if (Ft) main_loop(WalkRingOff{}, WalkRingOn{});
+            else main_loop(WalkRingOff{}, WalkRingOff{});
+        }
     }
     cp_async_wait<0>();
     // single-atom cells (Exp.cu's i_t1 == i_t0): a column whose window holds one atom, or the row that starts

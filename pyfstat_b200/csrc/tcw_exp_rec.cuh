@@ -37,11 +37,11 @@
 // + R i'): the 64 rows of a channel are 64 CONSECUTIVE map rows, whose k ranges differ by less than
 // one stage.  (The first version laid one descriptor over 64 rows of ONE class -- a band of 64 R = 512
 // map rows per tile, executing 8 % more MMAs than needed at 120 d and 33 % more at 30 d because the k
-// range of a tile is that of its longest row.)  Channels are stacked in M: the 128 lanes of an MMA are
-// 2 channels x 64 rows, each 8-row group reading its own 256-byte chunk of atoms (its rows' span + one
+// range of a tile is that of its longest row.)  Channels are stacked next to the rows: an MMA covers 3 or 4
+// channels x 64 rows, each 8-row group reading its own 256-byte chunk of atoms (its rows' span + one
 // stage of k; a start shifted by the class needs its own 16-byte aligned copy), the chunks 256 bytes
-// apart (SBO); a prep kernel lays the atoms out in that chunked form -- per channel pair p and atom
-// block u: [group][c'][chunk] -- so a stage's A operand of a pair is one contiguous 4-KB bulk copy.
+// apart (SBO); a prep kernel lays the atoms out in that chunked form -- per unit and atom block u:
+// [group][channel][chunk] -- so a stage's atom operand is one or two contiguous bulk copies (6 KB, 2 x 4 KB).
 // 128 window lengths per tile.  A tile is processed as two units -- the channels a2, b2, ab with the w^2
 // table (one MMA of N = 3 x 64 rows per 32 bytes of K), then Fa | Fb with the w table (one MMA of N = 4 x 64
 // rows) -- each unit in one half of TMEM.  The MMAs compute the TRANSPOSED tile (M = window lengths,
@@ -61,7 +61,7 @@
 #ifndef TCX_STAGES
 #define TCX_STAGES 8
 #endif
-#define TCX_A_BYTES 8192   // 2 pairs x 16 chunks x 256 B
+#define TCX_A_BYTES 8192   // atoms of a stage: 24 (unit 0) or 32 (unit 1) chunks of 256 B
 #define TCX_B_BYTES 16384  // 128 taus x 32 k x 4 B (one table)
 #define TCX_STAGE_BYTES (TCX_A_BYTES + TCX_B_BYTES)
 #define TCX_THREADS 192
@@ -327,9 +327,9 @@ __device__ __forceinline__ TcxTile tcx_tile_finish(uint32_t j, const TcxRaw &raw
 // CA[tz][3][m][cpitch], CF[tz][4][m][cpitch]: correction sums of every cell of the sub-batch (cpitch = n_nt * 128)
 // in the accumulators' own (scaled) units times the power of two `cs`, which the host derives from a bound on
 // sum_k |X V| so that no FP16 value can overflow; the walk undoes the scaling.  Precision per group: TcxC.
-// A tile is processed as two UNITS -- channel pairs (a2,b2 | ab,-) with the w^2 table, then (Fa | Fb) with
-// the w table; no operand is shared between them, so the split costs no traffic -- each accumulating into
-// one half of TMEM (2 x 128 columns): the epilogue warps drain unit u while the MMAs of unit u + 1 run.
+// A tile is processed as two UNITS -- the channels a2, b2, ab with the w^2 table, then Fa_re, Fa_im, Fb_re, Fb_im
+// with the w table; no operand is shared between them, so the split costs no traffic -- each accumulating into
+// one half of TMEM (192 / 256 of its 256 columns): the epilogue warps drain unit u while the MMAs of unit u + 1 run.
 template <bool F16>
 __global__ void __launch_bounds__(TCX_THREADS, 1)
 tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__restrict__ Vtv, uint32_t n_chunks_tab,
@@ -518,8 +518,8 @@ tcw_exptc_map_kernel(const void *__restrict__ Gv, uint32_t U, const void *__rest
           "=r"(V[17]), "=r"(V[18]), "=r"(V[19]), "=r"(V[20]), "=r"(V[21]), "=r"(V[22]), "=r"(V[23]), "=r"(V[24]),            \
           "=r"(V[25]), "=r"(V[26]), "=r"(V[27]), "=r"(V[28]), "=r"(V[29]), "=r"(V[30]), "=r"(V[31])                          \
         : "r"(TADDR))
-        // one unit (`u0`: unit 0 = a2, b2, ab in 192 columns [gg][c 3][i']; else Fa | Fb in 2 x 128 columns
-        // [pair][gg][c' 2][i']); `c16`: its group is stored as FP16; `edge`: the tile reaches beyond the last map row
+        // one unit (`u0`: unit 0 = a2, b2, ab in 192 columns [gg][c 3][i']; else Fa | Fb in 256 columns
+        // [Fa | Fb][gg][re | im][i']); `c16`: its group is stored as FP16; `edge`: the tile reaches beyond the last map row
         auto drain_unit = [&](auto u0, auto c16, auto edge, const TcxTile &tl, uint32_t buf) __attribute__((always_inline)) {
             constexpr bool U0 = decltype(u0)::value, C16 = decltype(c16)::value, EDGE = decltype(edge)::value;
             constexpr int ES = C16 ? 2 : 4, NPAIR = U0 ? 3 : 4;  // pairs of 32-column loads

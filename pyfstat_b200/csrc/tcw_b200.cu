@@ -1269,10 +1269,10 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
                 CUDA_TRY(h, cudaEventRecord(h->ev_x[2 * sb + 1], st));
                 corr = c_a;
             }
-            // row segments per column: measured (B200, 120-d maps): with 8 templates (46 000 columns) one
-            // segment is fastest (1.80 ms; 2: 1.89, 4: 2.01, 8: 2.15 -- pass 1 of the segmented walk costs more
-            // than the extra warps bring); with 4 templates 2-8 segments tie.  So: segments only until the
-            // launch has ~256 columns per SM.
+            // row segments per column: measured (B200, 120-d maps, final kernels): with 8 templates (46 000 columns)
+            // one segment is fastest (1.99 ms; 2: 2.96, 4: 2.55 -- pass 1 of the segmented walk costs more than the
+            // extra warps bring); with 4 templates 2-8 segments tie.  So: segments only until the launch has ~256
+            // columns per SM.
             int nseg = 1;
             while (nseg < 16 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 256) nseg *= 2;
             if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(16, atoi(env)));

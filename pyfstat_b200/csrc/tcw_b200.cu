@@ -945,7 +945,9 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
     int S = T;
     if (want_btsg) S = (int)std::max<size_t>(1, std::min<size_t>((size_t)T, subbatch_bytes() / (pcells * 4)));
     S = std::min(S, 32768);
-    if (host_atoms && T >= 16) {  // sub-batches double as upload chunks: upload/compute overlap
+    // exponential window on the fast kernels: compute >> upload, see the small first chunk below
+    const bool small_first = host_atoms && T >= 16 && w.type == TCW_WINDOW_EXP && path == PATH_FAST;
+    if (host_atoms && T >= 16 && !small_first) {  // sub-batches double as upload chunks: upload/compute overlap
         int chunks = 2;  // measured: MCMC step (23.6 MB, little compute) 1.29 ms with 1-2 chunks, 1.48 with 4, 1.92 with 8
         if (const char *env = getenv("TCW_UPLOAD_CHUNKS")) chunks = std::max(1, atoi(env));
         S = std::min(S, std::max(8, (T + chunks - 1) / chunks));
@@ -982,7 +984,14 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         if ((rc = ensure(h, h->d_scratch, (size_t)S * pcells * sizeof(float)))) return rc;
         fmn_scratch = (float *)h->d_scratch.p;
     }
-    const int n_sub = (T + S - 1) / S;
+    // Sub-batches double as upload chunks.  Where the kernels of a template take much longer than its upload (the
+    // exponential window), the FIRST chunk is made small -- nothing can run before it has arrived -- and the rest go
+    // in sub-batches of S: sub-batch sb covers templates [sub_lo(sb), sub_lo(sb + 1)).
+    int S0 = S;
+    if (small_first) S0 = std::min(S, std::max(4, T / 16));
+    if (small_first && getenv("TCW_UPLOAD_FIRST")) S0 = std::max(1, std::min(S, atoi(getenv("TCW_UPLOAD_FIRST"))));
+    const int n_sub = T <= S0 ? 1 : 1 + (T - S0 + S - 1) / S;
+    auto sub_lo = [&](int sb) { return sb == 0 ? 0 : std::min(T, S0 + (sb - 1) * S); };
     // rect tile plan + its group-max table: decided and allocated before anything is enqueued; a map
     // whose row tiles exceed the grid limit takes the generic kernels instead of failing
     uint32_t *groupmax = nullptr;
@@ -1127,7 +1136,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         }
         const size_t per_tpl = (size_t)h->numDet * h->stride;
         for (int sb = 0; sb < n_sub; sb++) {
-            const int lo = sb * S, cnt = std::min(S, T - lo);
+            const int lo = sub_lo(sb), cnt = sub_lo(sb + 1) - lo;
             CUDA_TRY(h, cudaMemcpyAsync((tcw_atom *)h->d_atoms.p + (size_t)lo * per_tpl, host_atoms + (size_t)lo * per_tpl,
                                         (size_t)cnt * per_tpl * sizeof(tcw_atom), cudaMemcpyHostToDevice,
                                         h->copy_stream));
@@ -1135,8 +1144,8 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
         }
     }
     for (int sb = 0; sb < n_sub; sb++) {
-        const int t_base = sb * S;
-        const int cnt = std::min(S, T - t_base);
+        const int t_base = sub_lo(sb);
+        const int cnt = sub_lo(sb + 1) - t_base;
         if (host_atoms) CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_up[sb], 0));
         // merge detectors, transpose to channels, FP64 prefix scan
         {

@@ -1282,6 +1282,22 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             // one segment is fastest (1.99 ms; 2: 2.96, 4: 2.55 -- pass 1 of the segmented walk costs more than the
             // extra warps bring); with 4 templates 2-8 segments tie.  So: segments only until the launch has ~256
             // columns per SM.
+            // lookup-table mode: the columns whose windows hold only a few atoms go to the generic kernel (TCX_SHORT_K)
+            uint32_t n_short = 0;
+            if (exp_tc) {
+                while (n_short < w.N_tau && ep.Kn[n_short] < TCX_SHORT_K) n_short++;
+                if (n_short) {
+                    MapWindow ws = w;
+                    ws.N_tau = n_short;
+                    const size_t cells_s = (size_t)w.N_t0 * n_short;
+                    dim3 grid_s((unsigned)((cells_s + TCW_GENERIC_THREADS - 1) / TCW_GENERIC_THREADS), 1, cnt);
+                    tcw_map_generic_kernel<TCW_WINDOW_EXP, false><<<grid_s, TCW_GENERIC_THREADS, 0, st>>>(
+                        (const float *)h->d_X.p, h->xpad, (const TplMeta *)h->d_meta.p, t_base, ws, nullptr, 0, g, lut, fmn,
+                        p_maxkey, p_flags, w.N_tau);
+                    h->launches++;
+                    CUDA_TRY(h, cudaGetLastError());
+                }
+            }
             int nseg = 1;
             while (nseg < 16 && (uint64_t)cnt * w.N_tau * nseg < (uint64_t)h->prop.multiProcessorCount * 256) nseg *= 2;
             if (const char *env = getenv("TCW_WALK_NSEG")) nseg = std::max(1, std::min(16, atoi(env)));
@@ -1296,7 +1312,7 @@ static int map_impl_inner(tcw_handle *h, const tcw_window_range *win, uint32_t f
             (const TplMeta *)h->d_meta.p, t_base, w,                                                               \
             ep.ec.i00[0], ep.delta[0], TAtom, (int)rec_A, corr, c_f, tc_rows, tc_cpitch,                         \
             (const float *)h->d_scale.p,                                                                         \
-            ldexpf(1.0f, tc_shift), fmn, p_maxkey, p_flags);                                                       \
+            ldexpf(1.0f, tc_shift), n_short, fmn, p_maxkey, p_flags);                                              \
     } while (0)
             if (exp_tc) {
                 if (nseg == 1) LAUNCH_WALK(true, 1);

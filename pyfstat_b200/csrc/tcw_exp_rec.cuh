@@ -95,6 +95,13 @@ struct TcxCfg {
     __host__ __device__ static constexpr int atom_of(int gg) { return gg % kRowStep + kKC * (gg / kRowStep); }
 };
 #define TCX_VSCALE_LOG2 12
+// Windows of fewer than TCX_SHORT_K + 1 atoms (the first columns of a map whose tau range starts at an atom or
+// two) are not taken from this path in lookup-table mode: with three or four terms nothing averages the 2^-11
+// operand roundings of the tensor-core pass (~1e-6 of the window sums), and few-atom windows have badly conditioned
+// antenna-pattern matrices (cond ~ 400 at 3 atoms, two detectors) -- measured 2e-4 on F_mn there, above the 1e-4
+// bar.  The generic kernel (the reference's own sequential sums, bit-identical to the oracle) computes those
+// columns -- a few thousand cells per template.
+#define TCX_SHORT_K 16
 
 // Storage of the correction sums C between the tensor-core pass and the walk, per channel GROUP:
 //   group A = a2, b2, ab (the antenna-pattern matrix M), group F = Fa, Fb (the data vector v), F = v^T M^-1 v.
@@ -685,7 +692,9 @@ __global__ void __launch_bounds__(WalkCfg<NSEG>::kThreads)
 tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
                     const int32_t *__restrict__ Kn, const TplMeta *__restrict__ meta, int t_base, MapWindow w,
                     uint32_t i00, int32_t delta, uint32_t TAtom, int rowstep, const unsigned char *__restrict__ CA,
-                    const unsigned char *__restrict__ CF, uint32_t c_rows, uint32_t cpitch, const float *__restrict__ cscale, float cunshift, float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
+                    const unsigned char *__restrict__ CF, uint32_t c_rows, uint32_t cpitch,
+                    const float *__restrict__ cscale, float cunshift, uint32_t n_skip, float *__restrict__ Fmn,
+                    unsigned long long *__restrict__ maxkey, uint32_t *__restrict__ flags) {
     using Cfg = WalkCfg<NSEG>;
     extern __shared__ __align__(16) unsigned char walk_smem[];
     __shared__ unsigned long long red[Cfg::kWarps];
@@ -703,11 +712,12 @@ tcw_exp_walk_kernel(const double *__restrict__ X, uint32_t xpad,
     // the correction sums come in the tensor-core pass's scaled units (tcw_exptc_scale_kernel, times 2^-shift)
     const float cf2 = HAS_C ? cscale[4 * tz + 2] * cunshift : 0.0f, cf1 = HAS_C ? cscale[4 * tz + 3] * cunshift : 0.0f;
     const uint32_t n = (blockIdx.x * Cfg::kCG + cg) * 32 + lane;
-    const bool active = n < w.N_tau;
+    // the first n_skip columns (windows of a few atoms) are computed by the generic kernel, see the host
+    const bool in_range = n < w.N_tau, active = in_range && n >= n_skip;
     const double *Xs = X + (size_t)t * TCW_NCH * xpad;
 
     // the column's window: k in [ka, kb], weights w0 rho^(k - ka)
-    const uint32_t nn = active ? n : w.N_tau - 1;
+    const uint32_t nn = in_range ? n : w.N_tau - 1;  // (skipped columns keep their own geometry: the warp's ring span)
     const int K = Kn[nn];
     const long long tau_n = (long long)w.tau + (long long)nn * w.dtau;
     const int ka = delta < 0 ? 1 : 0;

@@ -29,7 +29,10 @@ tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta
                        int t_base, MapWindow w, const MapWindow *__restrict__ wins, int none_window,
                        IndexGeom g, const ExpLut lut,
                        float *__restrict__ Fmn, unsigned long long *__restrict__ maxkey,
-                       uint32_t *__restrict__ flags) {
+                       uint32_t *__restrict__ flags, uint32_t idx_ntau = 0) {
+    // idx_ntau != 0: the launch covers the first w.N_tau columns of a map that has idx_ntau of them (the few-atom
+    // windows of an exponential-window map whose other columns the recurrence path computes): the argmax index is
+    // that of the full map
     __shared__ unsigned long long red[TCW_GENERIC_THREADS / 32];
     const int tz = blockIdx.z;
     const int t = t_base + tz;
@@ -79,7 +82,8 @@ tcw_map_generic_kernel(const float *__restrict__ X, uint32_t xpad, const TplMeta
         }
         const float F = fstat_faithful(S[0], S[1], S[2], S[3], S[4], S[5], S[6]);
         if (Fmn) Fmn[(size_t)tz * w.N_t0 * w.pitch + (size_t)m * w.pitch + n] = F;
-        if (F > -1.0f) key = pack_key(F, (uint32_t)flat);  // maxF starts at -1, strict > (tcw:135-139)
+        // maxF starts at -1, strict > (tcw:135-139)
+        if (F > -1.0f) key = pack_key(F, idx_ntau ? m * idx_ntau + n : (uint32_t)flat);
     }
     block_atomic_max_key<TCW_GENERIC_THREADS / 32>(key, &maxkey[t], red);
 }

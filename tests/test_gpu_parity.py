@@ -16,6 +16,7 @@ Nothing here reads /root/reference.
 """
 
 import math
+import os
 
 import numpy as np
 import pytest
@@ -837,6 +838,22 @@ def test_exp_recurrence_rows_several_atoms_apart(gpu, oracle, k, off):
             resd, Fd = run_gpu(gpu, b, w, exact | L.ALLOW_DEGENERATE | L.EXP_DIRECT)
             assert np.all(resd["path"] == 1)
             assert (np.abs(F - Fd) / np.abs(Fd)).max() <= RTOL
+
+
+@pytest.mark.gpu
+def test_exp_dispatch_fuzz_against_generic_kernels():
+    """tools/fuzz_exp_paths.py: 200 seeded random exponential-window grids (rows 1..9 atoms apart, offsets, dtau from
+    a quarter of an atom to several atoms, tau ranges starting at ONE atom, 1..5 ragged templates, 2..3 detectors)
+    through the default dispatch against the GPU's generic kernels (bit-identical to the oracle), both exp modes.
+    Seed 7 holds the grids that found the few-atom-window problem (3-atom windows, cond ~ 400: 2e-4 through the
+    tensor-core pass; those columns now go to the generic kernel, TCX_SHORT_K)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_exp_paths.py"), "200", "7"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
 @pytest.mark.gpu

@@ -1,0 +1,90 @@
+"""Differential fuzz of the exponential window's dispatch (development aid, run under gpurun):
+random grids (rows 1..9 atoms apart, offsets from the atom grid, dtau from a quarter of an atom to several
+atoms, short and long tau ranges), 1..5 ragged templates, 1..3 detectors -- default dispatch (recurrence +
+tensor-core pass where it applies) against the GPU's own generic kernels (bit-identical to the CPU oracle,
+tests/test_gpu_parity.py), in both exp modes.   python tools/fuzz_exp_paths.py [trials] [seed]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pyfstat_b200 import _lib as L  # noqa: E402
+from pyfstat_b200.atoms import batch_from_detector_lists, synth_atoms  # noqa: E402
+from pyfstat_b200.window import TransientWindowRange  # noqa: E402
+
+trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261017)
+h = L.Handle(0)
+TA = 1800
+RTOL = 1e-4
+paths = {0: 0, 1: 0, 2: 0}
+worst = 0.0
+for trial in range(trials):
+    n = int(rng.integers(40, 1300))
+    T = int(rng.integers(1, 6))
+    dets = ("H1", "L1", "V1")[: int(rng.integers(2, 4))]
+    full = synth_atoms(T, n, dets, seed=int(rng.integers(1, 10**6)))
+    tpls = []
+    for t in range(T):  # ragged ends (same first atom: the recurrence path needs equal t0_data)
+        cut = int(rng.integers(0, 12)) if t else 0
+        tpls.append([a[: n - cut] for a in full.template(t)])
+    b = batch_from_detector_lists(tpls, TA)
+    k = int(rng.choice([1, 1, 1, 2, 3, 4, 5, 9]))
+    off = int(rng.choice([0, 0, 300, 899, 901, 1500]))
+    dtau = int(rng.choice([TA, TA, TA // 4, TA // 2, 2 * TA, 3 * TA, 5 * TA]))
+    tau0 = int(rng.choice([2, 2, 1, 5, 40])) * TA
+    n_short = n - 11  # the shortest template
+    n_rows = max(1, int(rng.integers(1, max(2, (n_short - 3) // k))))
+    n_tau = int(rng.integers(1, max(2, min(900, 2 * n * TA // dtau))))
+    w = TransientWindowRange(2, 10**9 + off, (n_rows - 1) * k * TA, k * TA, tau0, (n_tau - 1) * dtau, dtau)
+    for exact in (0, L.EXP_EXACT):
+        fl = L.WANT_FMN | L.WANT_BTSG | L.ALLOW_DEGENERATE | exact
+        res, F = h.map_batch(b, w, fl, raise_on_degenerate=False)
+        ref, Fg = h.map_batch(b, w, fl | L.FORCE_GENERIC, raise_on_degenerate=False)
+        assert np.all(ref["path"] == 0)
+        paths[int(res["path"][0])] += 1
+        rel = np.abs(F - Fg) / np.maximum(np.abs(Fg), 1e-30)
+        worst = max(worst, float(rel.max()))
+        ok = rel.max() <= RTOL
+        for t in range(T):
+            flat = int(np.argmax(F[t]))
+            ok = ok and (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
+            ok = ok and int(res["status"][t]) == int(ref["status"][t])
+            ok = ok and abs(float(res["lnBtSG"][t]) - float(ref["lnBtSG"][t])) <= 3e-4
+        if not ok and rel.max() > RTOL:
+            # the documented exception: windows of a few atoms are ill-conditioned; every cell is
+            # bounded by 1e-4 max(1, cond / 2e3) with cond the condition number of its antenna-pattern matrix
+            bad = np.argwhere(rel > RTOL)
+            excused = True
+            for t, m, nn in bad:
+                tpl = b.template(int(t))
+                a2 = sum(x["a2_alpha"][: min(len(y) for y in tpl)].astype(np.float64) for x in tpl for y in [x])
+                nmin = min(len(x) for x in tpl)
+                a2 = sum(x["a2_alpha"][:nmin].astype(np.float64) for x in tpl)
+                b2 = sum(x["b2_alpha"][:nmin].astype(np.float64) for x in tpl)
+                ab = sum(x["ab_alpha"][:nmin].astype(np.float64) for x in tpl)
+                t0m = w.t0 + int(m) * w.dt0
+                tau = w.tau + int(nn) * w.dtau
+                i0 = max((t0m - 10**9 + TA // 2) // TA, 0)
+                i1 = min((t0m + 3 * tau - 10**9 + TA // 2) // TA - 1, nmin - 1)
+                ti = 10**9 + TA * np.arange(i0, i1 + 1)
+                wt = np.where(ti >= t0m, np.exp(-(ti - t0m) / tau), 0.0) ** 2
+                A, B, C = (a2[i0:i1 + 1] * wt).sum(), (b2[i0:i1 + 1] * wt).sum(), (ab[i0:i1 + 1] * wt).sum()
+                d = np.sqrt((A - B) ** 2 + 4 * C * C)
+                cond = (A + B + d) / max(A + B - d, 1e-300)
+                if rel[t, m, nn] > RTOL * max(1.0, cond / 2e3):
+                    excused = False
+                    print("  cell", (int(t), int(m), int(nn)), "rel", float(rel[t, m, nn]), "atoms", int(i1 - i0 + 1), "cond", float(cond))
+            if excused:
+                n_excused = globals().get("n_excused", 0) + len(bad)
+                globals()["n_excused"] = n_excused
+                ok = True
+        if not ok:
+            print("MISMATCH trial", trial, dict(n=n, T=T, dets=len(dets), k=k, off=off, dtau=dtau, tau0=tau0, n_rows=n_rows,
+                                               n_tau=n_tau, exact=bool(exact)), "max rel", float(rel.max()),
+                  "at", np.unravel_index(rel.argmax(), rel.shape), "path", int(res["path"][0]))
+            sys.exit(1)
+print("fuzz ok: %d trials x 2 exp modes, paths taken %s, worst relative difference %.2e, cells above 1e-4 but within the "
+      "conditioning bound: %d" % (trials, paths, worst, globals().get("n_excused", 0)))
+h.close()

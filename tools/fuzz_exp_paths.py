@@ -44,7 +44,10 @@ for trial in range(trials):
         ref, Fg = h.map_batch(b, w, fl | L.FORCE_GENERIC, raise_on_degenerate=False)
         assert np.all(ref["path"] == 0)
         paths[int(res["path"][0])] += 1
-        rel = np.abs(F - Fg) / np.maximum(np.abs(Fg), 1e-30)
+        # relative difference, with an absolute floor of 1e-7 / 1e-4 = 1e-3 on |F|: a cell whose F happens to be ~1e-5
+        # (the terms of the numerator cancel) carries the float32 noise of sums of O(1), in the reference as much as
+        # here -- seen: F = 5.4e-5 in a map of median F = 1.5, difference 5e-9
+        rel = np.abs(F - Fg) / np.maximum(np.abs(Fg), 1e-3)
         worst = max(worst, float(rel.max()))
         ok = rel.max() <= RTOL
         for t in range(T):
@@ -75,7 +78,8 @@ for trial in range(trials):
                 cond = (A + B + d) / max(A + B - d, 1e-300)
                 if rel[t, m, nn] > RTOL * max(1.0, cond / 2e3):
                     excused = False
-                    print("  cell", (int(t), int(m), int(nn)), "rel", float(rel[t, m, nn]), "atoms", int(i1 - i0 + 1), "cond", float(cond))
+                    print("  cell", (int(t), int(m), int(nn)), "rel", float(rel[t, m, nn]), "atoms", int(i1 - i0 + 1), "cond", float(cond),
+                          "F generic", float(Fg[t, m, nn]), "F", float(F[t, m, nn]), "median F of the map", float(np.median(Fg[t])))
             if excused:
                 n_excused = globals().get("n_excused", 0) + len(bad)
                 globals()["n_excused"] = n_excused

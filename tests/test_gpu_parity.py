@@ -851,9 +851,10 @@ def test_exp_dispatch_fuzz_against_generic_kernels():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_exp_paths.py"), "200", "7"],
-                         capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    for args in (("200", "7"), ("100", "1", "rect")):  # + rectangular window: tiled kernels (one tile per CTA / persistent)
+        res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_exp_paths.py"), *args],
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
 @pytest.mark.gpu

@@ -15,6 +15,8 @@ from pyfstat_b200.window import TransientWindowRange  # noqa: E402
 
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261017)
+WIN = 1 if (len(sys.argv) > 3 and sys.argv[3] == "rect") else 2  # window type: 2 exponential (default), 1 rectangular
+EF = 3 if WIN == 2 else 1
 h = L.Handle(0)
 TA = 1800
 RTOL = 1e-4
@@ -22,7 +24,7 @@ paths = {0: 0, 1: 0, 2: 0}
 worst = 0.0
 for trial in range(trials):
     n = int(rng.integers(40, 1300))
-    T = int(rng.integers(1, 6))
+    T = int(rng.integers(1, 6)) if WIN == 2 else int(rng.choice([1, 2, 5, 40, 70]))
     dets = ("H1", "L1", "V1")[: int(rng.integers(2, 4))]
     full = synth_atoms(T, n, dets, seed=int(rng.integers(1, 10**6)))
     tpls = []
@@ -33,12 +35,15 @@ for trial in range(trials):
     k = int(rng.choice([1, 1, 1, 2, 3, 4, 5, 9]))
     off = int(rng.choice([0, 0, 300, 899, 901, 1500]))
     dtau = int(rng.choice([TA, TA, TA // 4, TA // 2, 2 * TA, 3 * TA, 5 * TA]))
-    tau0 = int(rng.choice([2, 2, 1, 5, 40])) * TA
+    # (rect: single-atom windows are the case lalpulsar aborts on -- XLAL_EDOM -- and sit at the cond ~ 2e3..4e3 edge)
+    tau0 = int(rng.choice([2, 2, 1, 5, 40] if WIN == 2 else [2, 2, 3, 5, 40])) * TA
     n_short = n - 11  # the shortest template
     n_rows = max(1, int(rng.integers(1, max(2, (n_short - 3) // k))))
     n_tau = int(rng.integers(1, max(2, min(900, 2 * n * TA // dtau))))
-    w = TransientWindowRange(2, 10**9 + off, (n_rows - 1) * k * TA, k * TA, tau0, (n_tau - 1) * dtau, dtau)
-    for exact in (0, L.EXP_EXACT):
+    if WIN == 1 and rng.random() < 0.6:
+        dtau = k * TA  # dt0 == dtau: the skewed R = 4 tiles / the persistent kernel
+    w = TransientWindowRange(WIN, 10**9 + off, (n_rows - 1) * k * TA, k * TA, tau0, (n_tau - 1) * dtau, dtau)
+    for exact in ((0, L.EXP_EXACT) if WIN == 2 else (0,)):
         fl = L.WANT_FMN | L.WANT_BTSG | L.ALLOW_DEGENERATE | exact
         res, F = h.map_batch(b, w, fl, raise_on_degenerate=False)
         ref, Fg = h.map_batch(b, w, fl | L.FORCE_GENERIC, raise_on_degenerate=False)
@@ -54,7 +59,12 @@ for trial in range(trials):
             flat = int(np.argmax(F[t]))
             ok = ok and (int(res["m_ML"][t]), int(res["n_ML"][t])) == divmod(flat, F.shape[2])
             ok = ok and int(res["status"][t]) == int(ref["status"][t])
-            ok = ok and abs(float(res["lnBtSG"][t]) - float(ref["lnBtSG"][t])) <= 3e-4
+            # lnBtSG through the nearest-point table is a discontinuous function of F_mn: one last-digit difference in a
+            # dominant cell moves it by up to dx = 0.4 % of that term
+            ok = ok and abs(float(res["lnBtSG"][t]) - float(ref["lnBtSG"][t])) <= 2e-3
+            if not ok and rel.max() <= RTOL:
+                print("  record mismatch t", t, "argmax", (int(res["m_ML"][t]), int(res["n_ML"][t])), divmod(flat, F.shape[2]),
+                      "status", int(res["status"][t]), int(ref["status"][t]), "lnBtSG", float(res["lnBtSG"][t]), float(ref["lnBtSG"][t]))
         if not ok and rel.max() > RTOL:
             # the documented exception: windows of a few atoms are ill-conditioned; every cell is
             # bounded by 1e-4 max(1, cond / 2e3) with cond the condition number of its antenna-pattern matrix
@@ -70,9 +80,9 @@ for trial in range(trials):
                 t0m = w.t0 + int(m) * w.dt0
                 tau = w.tau + int(nn) * w.dtau
                 i0 = max((t0m - 10**9 + TA // 2) // TA, 0)
-                i1 = min((t0m + 3 * tau - 10**9 + TA // 2) // TA - 1, nmin - 1)
+                i1 = min((t0m + EF * tau - 10**9 + TA // 2) // TA - 1, nmin - 1)
                 ti = 10**9 + TA * np.arange(i0, i1 + 1)
-                wt = np.where(ti >= t0m, np.exp(-(ti - t0m) / tau), 0.0) ** 2
+                wt = np.where(ti >= t0m, np.exp(-(ti - t0m) / tau), 0.0) ** 2 if WIN == 2 else np.ones(len(ti))
                 A, B, C = (a2[i0:i1 + 1] * wt).sum(), (b2[i0:i1 + 1] * wt).sum(), (ab[i0:i1 + 1] * wt).sum()
                 d = np.sqrt((A - B) ** 2 + 4 * C * C)
                 cond = (A + B + d) / max(A + B - d, 1e-300)
@@ -89,6 +99,6 @@ for trial in range(trials):
                                                n_tau=n_tau, exact=bool(exact)), "max rel", float(rel.max()),
                   "at", np.unravel_index(rel.argmax(), rel.shape), "path", int(res["path"][0]))
             sys.exit(1)
-print("fuzz ok: %d trials x 2 exp modes, paths taken %s, worst relative difference %.2e, cells above 1e-4 but within the "
-      "conditioning bound: %d" % (trials, paths, worst, globals().get("n_excused", 0)))
+print("fuzz ok (%s window): %d trials x 2 exp modes, paths taken %s, worst relative difference %.2e, cells above 1e-4 but within the "
+      "conditioning bound: %d" % ("exp" if WIN == 2 else "rect", trials, paths, worst, globals().get("n_excused", 0)))
 h.close()

@@ -65,6 +65,19 @@ for trial in range(trials):
             if not ok and rel.max() <= RTOL:
                 print("  record mismatch t", t, "argmax", (int(res["m_ML"][t]), int(res["n_ML"][t])), divmod(flat, F.shape[2]),
                       "status", int(res["status"][t]), int(ref["status"][t]), "lnBtSG", float(res["lnBtSG"][t]), float(ref["lnBtSG"][t]))
+        # the other reduction modes (no F_mn to the caller, with / without the lnBtSG pass: fused max / argmax, the rect
+        # locate pass) must report the records of the materialised map
+        for extra in (L.WANT_BTSG, 0):
+            r2, none = h.map_batch(b, w, (fl & ~(L.WANT_FMN | L.WANT_BTSG)) | extra, raise_on_degenerate=False)
+            same = none is None and np.array_equal(r2["m_ML"], res["m_ML"]) and np.array_equal(r2["n_ML"], res["n_ML"]) and \
+                np.array_equal(r2["maxF"], res["maxF"]) and np.array_equal(r2["status"], res["status"])
+            if extra:
+                same = same and np.allclose(r2["lnBtSG"], res["lnBtSG"], rtol=0, atol=1e-9) and \
+                    np.array_equal(r2["m_MP"], res["m_MP"]) and np.array_equal(r2["n_MP"], res["n_MP"])
+            if not same:
+                print("  reduction mode", "btsg" if extra else "max only", "differs from the materialised map:",
+                      r2["m_ML"], res["m_ML"], r2["n_ML"], res["n_ML"], r2["maxF"], res["maxF"])
+                ok = False
         if not ok and rel.max() > RTOL:
             # the documented exception: windows of a few atoms are ill-conditioned; every cell is
             # bounded by 1e-4 max(1, cond / 2e3) with cond the condition number of its antenna-pattern matrix

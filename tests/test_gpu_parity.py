@@ -851,7 +851,9 @@ def test_exp_dispatch_fuzz_against_generic_kernels():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for args in (("200", "7"), ("100", "1", "rect")):  # + rectangular window: tiled kernels (one tile per CTA / persistent)
+    # + rectangular window: tiled kernels (one tile per CTA / persistent); + the exponential window's tiled direct sum on
+    # grids of several row classes with per-template index shifts
+    for args in (("200", "7"), ("100", "1", "rect"), ("100", "31", "direct")):
         res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_exp_paths.py"), *args],
                              capture_output=True, text=True, timeout=600)
         assert res.returncode == 0 and "fuzz ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

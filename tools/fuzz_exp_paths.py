@@ -17,6 +17,9 @@ trials = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 20261017)
 WIN = 1 if (len(sys.argv) > 3 and sys.argv[3] == "rect") else 2  # window type: 2 exponential (default), 1 rectangular
 EF = 3 if WIN == 2 else 1
+# "direct": the exponential window's tiled direct sum (TCW_EXP_DIRECT) on grids of up to 4 row classes, with templates
+# whose data start on different atoms (per-template index shifts)
+DIRECT = len(sys.argv) > 3 and sys.argv[3] == "direct"
 h = L.Handle(0)
 TA = 1800
 RTOL = 1e-4
@@ -30,7 +33,8 @@ for trial in range(trials):
     tpls = []
     for t in range(T):  # ragged ends (same first atom: the recurrence path needs equal t0_data)
         cut = int(rng.integers(0, 12)) if t else 0
-        tpls.append([a[: n - cut] for a in full.template(t)])
+        front = int(rng.integers(0, 10)) if (DIRECT and t) else 0
+        tpls.append([a[front: n - cut] for a in full.template(t)])
     b = batch_from_detector_lists(tpls, TA)
     k = int(rng.choice([1, 1, 1, 2, 3, 4, 5, 9]))
     off = int(rng.choice([0, 0, 300, 899, 901, 1500]))
@@ -42,9 +46,14 @@ for trial in range(trials):
     n_tau = int(rng.integers(1, max(2, min(900, 2 * n * TA // dtau))))
     if WIN == 1 and rng.random() < 0.6:
         dtau = k * TA  # dt0 == dtau: the skewed R = 4 tiles / the persistent kernel
-    w = TransientWindowRange(WIN, 10**9 + off, (n_rows - 1) * k * TA, k * TA, tau0, (n_tau - 1) * dtau, dtau)
+    dt0 = k * TA
+    if DIRECT:
+        dt0 = int(rng.choice([TA, TA // 2, 3 * TA // 2, 2 * TA, 3 * TA, 1350, 4 * TA, TA]))
+        n_rows = max(1, int(rng.integers(1, max(2, (n_short - 12) * TA // dt0))))
+        off += 10 * TA  # every template has data at the first row
+    w = TransientWindowRange(WIN, 10**9 + off, (n_rows - 1) * dt0, dt0, tau0, (n_tau - 1) * dtau, dtau)
     for exact in ((0, L.EXP_EXACT) if WIN == 2 else (0,)):
-        fl = L.WANT_FMN | L.WANT_BTSG | L.ALLOW_DEGENERATE | exact
+        fl = L.WANT_FMN | L.WANT_BTSG | L.ALLOW_DEGENERATE | exact | (L.EXP_DIRECT if DIRECT else 0)
         res, F = h.map_batch(b, w, fl, raise_on_degenerate=False)
         ref, Fg = h.map_batch(b, w, fl | L.FORCE_GENERIC, raise_on_degenerate=False)
         assert np.all(ref["path"] == 0)
